@@ -1,0 +1,174 @@
+/*
+ * nrms_b200.h — C-ABI of libnrms_b200.so: the B200 (sm_100a) implementation of the NRMS
+ * train + scoring hot path of 0215Arthur/Pytorch_News_Recommender.
+ *
+ * The reference has no FFI: its boundary is a Python nn.Module
+ * (MIND_2020/model/nrms_v0.py:218-312) driven by MIND_2020/train_eval.py:156-273.  Each entry
+ * point below replaces the ATen op sequence of one reference function; the function it
+ * replaces is cited as file:line (paths relative to the reference's MIND_2020/ directory).
+ * The Python host module (pytorch_news_recommender_b200/model/nrms_v0.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name starts with h_;
+ *   - the library never allocates or frees device memory: inputs, outputs, saved
+ *     activations and scratch are caller-owned blobs sized by the *_bytes() queries;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value 0 = ok, negative = error (see NRMS_ERR_*); nrms_last_error() returns a
+ *     thread-local message for the last failing call;
+ *   - all matrices are row-major fp32, ids are int64, masks are uint8 (the dtypes the
+ *     reference's batches use: data_handler.py:191-234).
+ *
+ * Flat encoder parameter layout (`params`, `d_params`), one block per encoder, D = d_model,
+ * Q = d_query:
+ *     [ W_Q (D*D) | W_K (D*D) | W_V (D*D) | b_Q (D) | b_K (D) | b_V (D) |
+ *       additive.linear.weight (Q*D) | additive.linear.bias (Q) | attention_query_vector (Q) ]
+ * i.e. nn.Linear's [out,in] layout (nrms_v0.py:35-37, 91-93), concatenated.
+ */
+#ifndef NRMS_B200_H
+#define NRMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRMS_ABI_VERSION 1
+
+#define NRMS_OK 0
+#define NRMS_ERR_BAD_SHAPE (-1)   /* unsupported / inconsistent dims */
+#define NRMS_ERR_ALIGN (-2)       /* pointer not 16-byte aligned */
+#define NRMS_ERR_CUDA (-3)        /* CUDA launch/runtime error */
+#define NRMS_ERR_WORKSPACE (-4)   /* saved/scratch blob too small */
+#define NRMS_ERR_NULL (-5)        /* required pointer is NULL */
+
+typedef void* nrms_stream_t; /* cudaStream_t */
+
+/* Shape of one encoder launch.  News encoder: n_seq titles of seq_len words
+ * (nrms_v0.py:154-176).  User encoder: n_seq users of seq_len clicked-news vectors
+ * (nrms_v0.py:188-199). */
+typedef struct nrms_encoder_dims {
+    int32_t n_seq;      /* sequences in this launch */
+    int32_t seq_len;    /* config.n_words_title or config.history_len */
+    int32_t d_model;    /* config.word_embed_size (300) */
+    int32_t n_heads;    /* config.num_attention_heads (10) */
+    int32_t d_query;    /* config.query_vector_dim (200) */
+    int32_t vocab;      /* rows of the word-embedding table (news encoder); 0 for user */
+    float dropout_p;    /* config.dropout when training, 0 in eval (nrms_v0.py:137,171-173) */
+    int32_t gemm_mode;  /* 0 = fp32 SIMT, 1 = tcgen05 split-bf16 (bf16x3, fp32-grade) */
+    uint64_t seed;      /* Philox key of this step's dropout masks */
+} nrms_encoder_dims;
+
+int nrms_abi_version(void);
+const char* nrms_last_error(void);
+
+/* number of floats in one encoder's flat parameter block */
+int64_t nrms_encoder_param_count(int32_t d_model, int32_t d_query);
+/* bytes of the activations the forward saves for the backward */
+int64_t nrms_encoder_saved_bytes(const nrms_encoder_dims* d);
+/* bytes of scratch the backward needs */
+int64_t nrms_encoder_scratch_bytes(const nrms_encoder_dims* d);
+
+/* NewsEncoder.forward (nrms_v0.py:154-176): embedding gather (+dropout), 3 projections,
+ * scaled-dot-product attention per head (nrms_v0.py:13-23, 46-76), dropout, additive
+ * attention pooling (nrms_v0.py:100-126).
+ *   ids   [n_seq, seq_len] int64     table [vocab, d_model]     out [n_seq, d_model]
+ *   saved: caller-owned blob of nrms_encoder_saved_bytes(d) bytes holding the activations
+ *   (needed by the backward; inference callers simply reuse one blob across calls). */
+int nrms_news_encoder_fwd(const nrms_encoder_dims* d, const int64_t* ids, const float* table,
+                          const float* params, float* out, void* saved, int64_t saved_bytes,
+                          nrms_stream_t stream);
+
+/* Autograd mirror of the above (train_eval.py:204).  Writes d_params (overwrite) and the
+ * per-token embedding-row gradients d_rows [n_seq*seq_len, d_model] (dropout mask already
+ * applied) that nrms_embedding_grad_* scatters into the table gradient. */
+int nrms_news_encoder_bwd(const nrms_encoder_dims* d, const int64_t* ids, const float* table,
+                          const float* params, const float* d_out, const void* saved,
+                          int64_t saved_bytes, void* scratch, int64_t scratch_bytes,
+                          float* d_params, float* d_rows, nrms_stream_t stream);
+
+/* UserEncoder.forward (nrms_v0.py:188-199): x [n_seq, seq_len, d_model] -> out [n_seq, d_model] */
+int nrms_user_encoder_fwd(const nrms_encoder_dims* d, const float* x, const float* params,
+                          float* out, void* saved, int64_t saved_bytes, nrms_stream_t stream);
+int nrms_user_encoder_bwd(const nrms_encoder_dims* d, const float* x, const float* params,
+                          const float* d_out, const void* saved, int64_t saved_bytes,
+                          void* scratch, int64_t scratch_bytes, float* d_params, float* d_x,
+                          nrms_stream_t stream);
+
+/* DotProductClickPredictor.forward + candidate masking (nrms_v0.py:205-216, 272-274):
+ *   cand [B,C,D], user [B,D], mask [B,C] uint8 (may be NULL) -> logits [B,C] (pad = -1e9) */
+int nrms_score_fwd(int32_t B, int32_t C, int32_t D, const float* cand, const float* user,
+                   const uint8_t* mask, float* logits, nrms_stream_t stream);
+/* its backward: d_logits [B,C] -> d_cand [B,C,D], d_user [B,D] (masked slots get 0) */
+int nrms_score_bwd(int32_t B, int32_t C, int32_t D, const float* cand, const float* user,
+                   const uint8_t* mask, const float* d_logits, float* d_cand, float* d_user,
+                   nrms_stream_t stream);
+/* Fused scorer + nn.CrossEntropyLoss vs label 0 (train_eval.py:181,194-195) + its backward.
+ * loss_per_row [B] receives logsumexp(s_b)-s_b0; the mean over B is *loss_mean (sum of the
+ * per-row values times 1/B_global, atomically added: zero it first).  d_cand / d_user are
+ * the gradients of the MEAN loss over B_global rows. */
+int nrms_score_ce_fwd_bwd(int32_t B, int32_t C, int32_t D, int32_t B_global, const float* cand,
+                          const float* user, const uint8_t* mask, float* logits,
+                          float* loss_per_row, float* d_cand, float* d_user,
+                          nrms_stream_t stream);
+
+/* Deduplicated sparse scatter-add of the embedding-row gradients (the replacement of the 55
+ * dense embedding_dense_backward calls).  plan = counting sort of the n_rows
+ * ids by vocab row (id 0 = padding_idx, dropped: nrms_v0.py:136).
+ *   plan blob layout is private; size it with nrms_embedding_plan_bytes. */
+int64_t nrms_embedding_plan_bytes(int64_t n_rows, int32_t vocab);
+int nrms_embedding_plan(const int64_t* ids, int64_t n_rows, int32_t vocab, void* plan,
+                        int64_t plan_bytes, nrms_stream_t stream);
+/* d_table [vocab, D] = sum over rows with the same id (every row of d_table is written) */
+int nrms_embedding_grad_dense(const void* plan, int64_t plan_bytes, const float* d_rows,
+                              int64_t n_rows, int32_t vocab, int32_t D, float* d_table,
+                              nrms_stream_t stream);
+/* number of distinct non-pad ids in the plan (device int32 written to *d_unique) */
+int nrms_embedding_plan_unique(const void* plan, int64_t plan_bytes, int32_t vocab,
+                               int32_t* d_unique, nrms_stream_t stream);
+
+/* torch.optim.Adam defaults (train_eval.py:167,205): betas (0.9,0.999), eps 1e-8, no weight
+ * decay, no amsgrad.  step >= 1 is the step being taken.  g may be scaled by grad_scale
+ * (1/world_size after a sum-allreduce). */
+int nrms_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int32_t step,
+                   float lr, float beta1, float beta2, float eps, float grad_scale,
+                   nrms_stream_t stream);
+
+/* Ranking metrics of evaluation.py:6-27 for ragged impressions: impression i owns
+ * scores[offsets[i] .. offsets[i+1]) and labels likewise (labels 0/1 uint8).
+ * max_len >= the longest impression (config.max_candidate_size).
+ * out [n_impr, 4] float64 = AUC (roc_auc_score, midrank ties), MRR, nDCG@5, nDCG@10;
+ * NaN where the reference yields NaN (single-class impressions). */
+int nrms_rank_metrics(const float* scores, const uint8_t* labels, const int64_t* offsets,
+                      int64_t n_impr, int32_t max_len, double* out, nrms_stream_t stream);
+/* Same, reading padded score rows as train_eval.py:219-227 does: impression i owns
+ * scores[i*row_stride .. i*row_stride+len_i), len_i = offsets[i+1]-offsets[i]. */
+int nrms_rank_metrics_padded(const float* scores, int64_t row_stride, const uint8_t* labels,
+                             const int64_t* offsets, int64_t n_impr, int32_t max_len,
+                             double* out, nrms_stream_t stream);
+
+/* Gather rows: out[i,:] = src[idx[i]-base,:] (idx < base -> zeros).  Used to build
+ * [B,H,D]/[B,C,D] from the cached news-vector table keyed by browsed_ids/candidate_ids
+ * (news row + 1, 0 = pad: data_handler.py:88,100) and, with int64 title tables, for the
+ * on-device batch assembly of data_handler.py:206-228. */
+int nrms_gather_rows_f32(const float* src, int64_t n_src, int32_t D, const int64_t* idx,
+                         int64_t n_idx, int64_t base, float* out, nrms_stream_t stream);
+int nrms_gather_rows_i64(const int64_t* src, int64_t n_src, int32_t D, const int64_t* idx,
+                         int64_t n_idx, int64_t base, int64_t* out, nrms_stream_t stream);
+
+/* Test hook: writes the dropout keep-mask scaled by 1/(1-p) (0 or 1/(1-p)) that the
+ * encoder kernels apply to stream `stream_id` (1 = embedding dropout nrms_v0.py:137,
+ * 2 = context dropout nrms_v0.py:171-173) for n flat elements. */
+int nrms_dropout_mask(uint64_t seed, uint32_t stream_id, float p, int64_t n, float* out,
+                      nrms_stream_t stream);
+
+/* out-of-range id check: *d_flag |= 1 if any id < 0 or >= vocab */
+int nrms_validate_ids(const int64_t* ids, int64_t n, int64_t vocab, int32_t* d_flag,
+                      nrms_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRMS_B200_H */

@@ -1,0 +1,159 @@
+// pooling.cuh — additive-attention pooling (AdditiveAttention.forward nrms_v0.py:100-126)
+// after the tanh(linear) projection, and its backward.
+//   a_l = t_l . q            (t = tanh(ctx W_a^T + b_a) comes from the projection GEMM)
+//   w   = softmax_l(a)       (dim=1: over the sequence; pad tokens participate)
+//   out = sum_l w_l ctx_l
+#pragma once
+#include "common.cuh"
+
+namespace nrms {
+
+struct PoolArgs {
+    const float* ctx;   // [M, D]
+    const float* t;     // [M, Q]
+    const float* q;     // [Q]
+    float* w;           // [n_seq, L]  fwd out / bwd in
+    float* out;         // [n_seq, D]  fwd out
+    const float* d_out; // [n_seq, D]  bwd in
+    float* d_ctx;       // [M, D]      bwd out: w_l * d_out (projection path is added by the GEMM)
+    float* d_pre;       // [M, Q]      bwd out: grad wrt pre-tanh activations
+    float* d_part;      // [n_seq, 2Q] bwd out: per-sequence partials of (d_b_a | d_q)
+    int L, D, Q;
+};
+
+// one CTA per sequence; dynamic smem: L floats
+__global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolArgs p) {
+    extern __shared__ float sw[];
+    const int seq = blockIdx.x, L = p.L, D = p.D, Q = p.Q;
+    const long long row0 = (long long)seq * L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int l = warp; l < L; l += nw) {
+        const float* tr = p.t + (row0 + l) * Q;
+        float s = 0.f;
+        for (int j = lane; j < Q; j += 32) s = fmaf(__ldg(tr + j), __ldg(p.q + j), s);
+        s = warp_sum(s);
+        if (lane == 0) sw[l] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float mx = -INFINITY;
+        for (int l = lane; l < L; l += 32) mx = fmaxf(mx, sw[l]);
+        mx = warp_max(mx);
+        float den = 0.f;
+        for (int l = lane; l < L; l += 32) {
+            const float e = __expf(sw[l] - mx);
+            sw[l] = e;
+            den += e;
+        }
+        den = warp_sum(den);
+        const float inv = 1.f / den;
+        for (int l = lane; l < L; l += 32) {
+            const float wv = sw[l] * inv;
+            sw[l] = wv;
+            if (p.w) p.w[(long long)seq * L + l] = wv;
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int l = 0; l < L; ++l) acc = fmaf(sw[l], __ldg(p.ctx + (row0 + l) * D + d), acc);
+        p.out[(long long)seq * D + d] = acc;
+    }
+}
+
+// one CTA per sequence; dynamic smem: 2L floats (w, da)
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
+    extern __shared__ float sm[];
+    const int seq = blockIdx.x, L = p.L, D = p.D, Q = p.Q;
+    float* sw = sm;
+    float* sda = sm + L;
+    __shared__ float s_dot;
+    const long long row0 = (long long)seq * L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float* go = p.d_out + (long long)seq * D;
+    // dw_l = d_out . ctx_l
+    for (int l = warp; l < L; l += nw) {
+        const float* cr = p.ctx + (row0 + l) * D;
+        float s = 0.f;
+        for (int d = lane; d < D; d += 32) s = fmaf(__ldg(go + d), __ldg(cr + d), s);
+        s = warp_sum(s);
+        if (lane == 0) {
+            sda[l] = s;
+            sw[l] = p.w[(long long)seq * L + l];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float s = 0.f;
+        for (int l = lane; l < L; l += 32) s = fmaf(sw[l], sda[l], s);
+        s = warp_sum(s);
+        if (lane == 0) s_dot = s;
+    }
+    __syncthreads();
+    const float dot = s_dot;
+    __syncthreads();
+    for (int l = threadIdx.x; l < L; l += blockDim.x) sda[l] = sw[l] * (sda[l] - dot);
+    __syncthreads();
+    // d_ctx (pooling path)
+    for (int i = threadIdx.x; i < L * D; i += blockDim.x) {
+        const int l = i / D, d = i - l * D;
+        p.d_ctx[(row0 + l) * D + d] = sw[l] * __ldg(go + d);
+    }
+    // d_pre and the bias / query-vector partials
+    for (int j = threadIdx.x; j < Q; j += blockDim.x) {
+        const float qj = __ldg(p.q + j);
+        float db = 0.f, dq = 0.f;
+        for (int l = 0; l < L; ++l) {
+            const float tv = __ldg(p.t + (row0 + l) * Q + j);
+            const float da = sda[l];
+            const float dp = da * qj * (1.f - tv * tv);
+            p.d_pre[(row0 + l) * Q + j] = dp;
+            db += dp;
+            dq = fmaf(da, tv, dq);
+        }
+        p.d_part[(long long)seq * 2 * Q + j] = db;
+        p.d_part[(long long)seq * 2 * Q + Q + j] = dq;
+    }
+}
+
+// out[n] (+)= scale * sum_{r<R} in[r, n]   (deterministic two-level: each thread walks a
+// column; R is at most a few thousand).  Used for bias / query partials and split-K weight
+// gradient partials.
+__global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                   long long R, long long n, long long ld, float scale,
+                                   int accumulate) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    long long r = 0;
+    for (; r + 3 < R; r += 4) {
+        s0 += in[(r + 0) * ld + c];
+        s1 += in[(r + 1) * ld + c];
+        s2 += in[(r + 2) * ld + c];
+        s3 += in[(r + 3) * ld + c];
+    }
+    for (; r < R; ++r) s0 += in[r * ld + c];
+    const float s = ((s0 + s1) + (s2 + s3)) * scale;
+    out[c] = accumulate ? out[c] + s : s;
+}
+
+// first level of the two-level column sum: slice y sums rows [y*per, (y+1)*per) into tmp[y, :]
+__global__ void reduce_rows_sliced_kernel(const float* __restrict__ in, float* __restrict__ tmp,
+                                          long long R, long long n, long long ld, long long per) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const long long r0 = (long long)blockIdx.y * per;
+    const long long r1 = r0 + per < R ? r0 + per : R;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    long long r = r0;
+    for (; r + 3 < r1; r += 4) {
+        s0 += in[(r + 0) * ld + c];
+        s1 += in[(r + 1) * ld + c];
+        s2 += in[(r + 2) * ld + c];
+        s3 += in[(r + 3) * ld + c];
+    }
+    for (; r < r1; ++r) s0 += in[r * ld + c];
+    tmp[(long long)blockIdx.y * n + c] = (s0 + s1) + (s2 + s3);
+}
+
+}  // namespace nrms

@@ -1,0 +1,364 @@
+// train_kernels.cuh — click scorer + cross-entropy, embedding-gradient dedupe/scatter, Adam,
+// row gathers.  All HBM-bound; grids are sized against the 148 SMs.
+#pragma once
+#include "common.cuh"
+
+namespace nrms {
+
+// ---------------------------------------------------------------------------------------
+// DotProductClickPredictor.forward (nrms_v0.py:205-216) + masked_fill (nrms_v0.py:272-274)
+// [+ nn.CrossEntropyLoss vs label 0 (train_eval.py:181,194-195) and the backward of both].
+// One CTA per impression; one warp per candidate slot (looping).
+// ---------------------------------------------------------------------------------------
+struct ScoreArgs {
+    const float* cand;   // [B, C, D]
+    const float* user;   // [B, D]
+    const uint8_t* mask; // [B, C] or nullptr
+    float* logits;       // [B, C]
+    const float* d_logits; // [B, C] (score_bwd only)
+    float* loss_rows;    // [B]    (fused only)
+    float* d_cand;       // [B, C, D]
+    float* d_user;       // [B, D]
+    int B, C, D;
+    float inv_batch;     // 1 / B_global
+};
+
+// MODE 0: logits only. MODE 1: fused logits + CE + grads. MODE 2: grads from d_logits.
+template <int MODE>
+__global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a) {
+    extern __shared__ float sm[];  // C floats: logits then d_logits
+    const int b = blockIdx.x, C = a.C, D = a.D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float* u = a.user + (long long)b * D;
+    const float* cb = a.cand + (long long)b * C * D;
+    if (MODE != 2) {
+        for (int c = warp; c < C; c += nw) {
+            const float* cr = cb + (long long)c * D;
+            float s = 0.f;
+            for (int d = lane; d < D; d += 32) s = fmaf(__ldg(cr + d), __ldg(u + d), s);
+            s = warp_sum(s);
+            if (lane == 0) {
+                if (a.mask && a.mask[(long long)b * C + c] == 0) s = -1e9f;
+                sm[c] = s;
+                a.logits[(long long)b * C + c] = s;
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == 0) return;
+    if (MODE == 1) {
+        if (warp == 0) {
+            float mx = -INFINITY;
+            for (int c = lane; c < C; c += 32) mx = fmaxf(mx, sm[c]);
+            mx = warp_max(mx);
+            float den = 0.f;
+            for (int c = lane; c < C; c += 32) den += expf(sm[c] - mx);
+            den = warp_sum(den);
+            const float lse = mx + logf(den);
+            const float s0 = sm[0];
+            __syncwarp();
+            for (int c = lane; c < C; c += 32) {
+                float g = expf(sm[c] - lse) - (c == 0 ? 1.f : 0.f);
+                if (a.mask && a.mask[(long long)b * C + c] == 0) g = 0.f;  // masked_fill grad
+                sm[c] = g * a.inv_batch;
+            }
+            if (lane == 0) a.loss_rows[b] = lse - s0;
+        }
+    } else {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float g = a.d_logits[(long long)b * C + c];
+            if (a.mask && a.mask[(long long)b * C + c] == 0) g = 0.f;
+            sm[c] = g;
+        }
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float ud = __ldg(u + d);
+        float du = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float g = sm[c];
+            du = fmaf(g, __ldg(cb + (long long)c * D + d), du);
+            a.d_cand[((long long)b * C + c) * D + d] = g * ud;
+        }
+        a.d_user[(long long)b * D + d] = du;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Embedding gradient: counting sort of token rows by vocab id, then a load-balanced
+// segmented reduction (one warp per 32 sorted rows) into the dense table gradient.
+// Replaces 55 x (zero-fill [V,D] + scatter + accumulate) of the reference.
+// plan blob: int32 counts[V] | int32 offsets[V+1] | int32 cursor[V] | int32 perm[n_rows]
+//            | int32 sorted_id[n_rows] | int32 n_valid
+// ---------------------------------------------------------------------------------------
+struct PlanView {
+    int32_t* counts;
+    int32_t* offsets;
+    int32_t* cursor;
+    int32_t* perm;
+    int32_t* sorted_id;
+    int32_t* n_valid;
+};
+inline int64_t plan_bytes(int64_t n_rows, int32_t vocab) {
+    return align_up((int64_t)sizeof(int32_t) * (3ll * vocab + 1 + 2 * n_rows + 4), 256);
+}
+inline PlanView plan_view(void* blob, int64_t n_rows, int32_t vocab) {
+    PlanView v;
+    int32_t* p = reinterpret_cast<int32_t*>(blob);
+    v.counts = p;
+    v.offsets = v.counts + vocab;
+    v.cursor = v.offsets + vocab + 1;
+    v.perm = v.cursor + vocab;
+    v.sorted_id = v.perm + n_rows;
+    v.n_valid = v.sorted_id + n_rows;
+    return v;
+}
+
+__global__ void plan_hist_kernel(const int64_t* __restrict__ ids, long long n, int vocab,
+                                 int32_t* __restrict__ counts) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long id = ids[i];
+        if (id > 0 && id < vocab) atomicAdd(counts + id, 1);
+    }
+}
+
+// single-CTA exclusive scan of counts[V] -> offsets[V+1]; cursor = 0; n_valid = total
+__global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restrict__ counts,
+                                                         int32_t* __restrict__ offsets,
+                                                         int32_t* __restrict__ cursor,
+                                                         int32_t* __restrict__ n_valid,
+                                                         int vocab) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = ceil_div(vocab, 1024);
+    const int beg = tid * per, end = min(vocab, beg + per);
+    int32_t local = 0;
+    for (int i = beg; i < end; ++i) local += counts[i];
+    int32_t inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = warp_tot[lane];
+        int32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        warp_tot[lane] = winc - w;  // exclusive
+        if (lane == 31) carry_s = winc;
+    }
+    __syncthreads();
+    int32_t run = warp_tot[warp] + inc - local;
+    for (int i = beg; i < end; ++i) {
+        offsets[i] = run;
+        cursor[i] = 0;
+        run += counts[i];
+    }
+    if (tid == 0) {
+        offsets[vocab] = carry_s;
+        *n_valid = carry_s;
+    }
+}
+
+__global__ void plan_fill_kernel(const int64_t* __restrict__ ids, long long n, int vocab,
+                                 const int32_t* __restrict__ offsets,
+                                 int32_t* __restrict__ cursor, int32_t* __restrict__ perm,
+                                 int32_t* __restrict__ sorted_id) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long id = ids[i];
+        if (id > 0 && id < vocab) {
+            const int32_t pos = offsets[id] + atomicAdd(cursor + id, 1);
+            perm[pos] = (int32_t)i;
+            sorted_id[pos] = (int32_t)id;
+        }
+    }
+}
+
+// Rows of one id land in arbitrary order inside their segment (atomic cursor); sorting each
+// short segment restores a deterministic summation order.  One warp per vocab row, segments
+// up to 32 entries are bitonic-sorted in registers; longer ones are left as they are.
+__global__ void plan_sort_segments_kernel(const int32_t* __restrict__ offsets,
+                                          int32_t* __restrict__ perm, int vocab) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long v = warp_g; v < vocab; v += nwarps) {
+        const int beg = offsets[v], len = offsets[v + 1] - beg;
+        if (len < 2 || len > 32) continue;
+        int32_t x = lane < len ? perm[beg + lane] : 0x7fffffff;
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const int32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+                const bool up = ((lane & k) == 0);
+                const bool lower = ((lane & j) == 0);
+                x = (lower == up) ? min(x, y) : max(x, y);
+            }
+        }
+        if (lane < len) perm[beg + lane] = x;
+    }
+}
+
+// zero-fill (float4) — the dense gradient is written in full every step
+__global__ void zero_kernel(float4* __restrict__ p, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x)
+        p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// One warp per chunk of 32 sorted rows.  Runs of equal id are summed in registers; a run
+// that lies strictly inside the chunk AND covers its whole segment is stored, any run that
+// touches a chunk edge may continue in the neighbour chunk and is added atomically
+// (red.global.add.v4.f32).  D % 4 == 0, D <= 384 (3 float4 per lane).
+__global__ void __launch_bounds__(256) embgrad_reduce_kernel(
+    const int32_t* __restrict__ perm, const int32_t* __restrict__ sorted_id,
+    const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_valid_p,
+    const float* __restrict__ d_rows, int D, float* __restrict__ d_table) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int n_valid = *n_valid_p;
+    const int d4 = D >> 2;
+    for (long long chunk = warp_g; chunk * 32 < n_valid; chunk += nwarps) {
+        const int base = (int)(chunk * 32);
+        const int cnt = min(32, n_valid - base);
+        const int my_row = lane < cnt ? perm[base + lane] : 0;
+        const int my_id = lane < cnt ? sorted_id[base + lane] : -1;
+        float4 acc[3];
+        int cur = __shfl_sync(0xffffffffu, my_id, 0);
+        acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r <= cnt; ++r) {
+            const int id = r < cnt ? __shfl_sync(0xffffffffu, my_id, r) : -2;
+            if (id != cur) {
+                // flush run [.., r) of id `cur`
+                const int seg_beg = offsets[cur], seg_end = offsets[cur + 1];
+                const bool whole = seg_beg >= base && seg_end <= base + cnt;
+                float* dst = d_table + (long long)cur * D;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int col4 = lane + 32 * c;
+                    if (col4 < d4) {
+                        if (whole) {
+                            reinterpret_cast<float4*>(dst)[col4] = acc[c];
+                        } else {
+                            float* a4 = dst + 4 * col4;
+                            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a4),
+                                         "f"(acc[c].x), "f"(acc[c].y), "f"(acc[c].z),
+                                         "f"(acc[c].w)
+                                         : "memory");
+                        }
+                    }
+                    acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                cur = id;
+            }
+            if (r < cnt) {
+                const int row = __shfl_sync(0xffffffffu, my_row, r);
+                const float4* src = reinterpret_cast<const float4*>(d_rows + (long long)row * D);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int col4 = lane + 32 * c;
+                    if (col4 < d4) {
+                        const float4 v = __ldg(src + col4);
+                        acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void plan_unique_kernel(const int32_t* __restrict__ counts, int vocab,
+                                   int32_t* __restrict__ out) {
+    int local = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < vocab; i += gridDim.x * blockDim.x)
+        local += counts[i] > 0 ? 1 : 0;
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+// ---------------------------------------------------------------------------------------
+// torch.optim.Adam (defaults) — train_eval.py:167,205.  Mirrors torch's single-tensor
+// formulation: m = lerp(m, g, 1-b1); v = b2 v + (1-b2) g^2;
+// p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+// ---------------------------------------------------------------------------------------
+struct AdamArgs {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    long long n;
+    float beta1, beta2, eps, step_size, bc2_sqrt, grad_scale;
+};
+
+__device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamArgs& a) {
+    g *= a.grad_scale;
+    m = m + (g - m) * (1.f - a.beta1);
+    v = a.beta2 * v + (1.f - a.beta2) * g * g;
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    p = p - a.step_size * (m / denom);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const AdamArgs a) {
+    const long long n4 = a.n >> 2;
+    float4* p4 = reinterpret_cast<float4*>(a.p);
+    const float4* g4 = reinterpret_cast<const float4*>(a.g);
+    float4* m4 = reinterpret_cast<float4*>(a.m);
+    float4* v4 = reinterpret_cast<float4*>(a.v);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        float4 p = p4[i], m = m4[i], v = v4[i];
+        const float4 g = g4[i];
+        adam1(p.x, g.x, m.x, v.x, a);
+        adam1(p.y, g.y, m.y, v.y, a);
+        adam1(p.z, g.z, m.z, v.z, a);
+        adam1(p.w, g.w, m.w, v.w, a);
+        p4[i] = p; m4[i] = m; v4[i] = v;
+    }
+    // tail (n % 4)
+    const long long t = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < a.n) adam1(a.p[t], a.g[t], a.m[t], a.v[t], a);
+}
+
+// ---------------------------------------------------------------------------------------
+// row gathers (cached news vectors by news id; title tokens by news id)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gather_rows_kernel(const T* __restrict__ src, long long n_src, int D,
+                                   const int64_t* __restrict__ idx, long long n_idx,
+                                   long long base, T* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp_g; r < n_idx; r += nwarps) {
+        const long long s = idx[r] - base;
+        const bool ok = s >= 0 && s < n_src;
+        for (int d = lane; d < D; d += 32)
+            out[r * D + d] = ok ? __ldg(src + s * D + d) : (T)0;
+    }
+}
+
+__global__ void dropout_mask_kernel(Dropout dr, uint32_t sid, long long n, float* out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        out[i] = dr.enabled() ? dr.mult(sid, (uint64_t)i) : 1.f;
+}
+
+__global__ void validate_ids_kernel(const int64_t* ids, long long n, long long vocab,
+                                    int32_t* flag) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        if (ids[i] < 0 || ids[i] >= vocab) atomicOr(flag, 1);
+}
+
+}  // namespace nrms

@@ -1,0 +1,314 @@
+"""Host-side engine: autograd bridges for the drop-in `nn.Module` path and the fused
+training step (forward + cross-entropy + backward + Adam, all in our kernels).
+
+Two ways to train, same arithmetic:
+  * drop-in  — `outputs = model(datas); loss = criterion(outputs, y); loss.backward();
+               optimizer.step()` exactly as train_eval.py:189-205: the autograd Functions
+               below produce `.grad` for all 19 parameters (the table gradient is dense, as
+               in the reference: SURVEY §0.6) and any torch optimizer can consume them.
+  * fused    — `FusedTrainer.step(datas)`: no autograd graph, gradients land in one flat
+               buffer (+ the table gradient), Adam runs in our kernel on flat views that
+               alias the module's parameters, and with world_size > 1 the two gradient
+               buffers are all-reduced over NCCL.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import NrmsError
+from .ops import BlobCache, EncoderShape
+
+_ENC_PARAM_ORDER = ("W_Q.weight", "W_K.weight", "W_V.weight", "W_Q.bias", "W_K.bias", "W_V.bias",
+                    "linear.weight", "linear.bias", "attention_query_vector")
+
+
+def encoder_param_list(enc) -> List[torch.nn.Parameter]:
+    """The 9 tensors of one encoder in the flat-block order of include/nrms_b200.h."""
+    m, a = enc.multihead_self_attention, enc.additive_attention
+    return [m.W_Q.weight, m.W_K.weight, m.W_V.weight, m.W_Q.bias, m.W_K.bias, m.W_V.bias,
+            a.linear.weight, a.linear.bias, a.attention_query_vector]
+
+
+def pack_params(plist) -> torch.Tensor:
+    first = plist[0]
+    # already views of one flat buffer (FusedTrainer aliases them)? then no copy
+    base = getattr(first, "_nrms_flat", None)
+    if base is not None and base.data_ptr() == first.data_ptr():
+        return base
+    return torch.cat([p.detach().reshape(-1) for p in plist])
+
+
+def split_flat(flat: torch.Tensor, plist) -> List[torch.Tensor]:
+    out, off = [], 0
+    for p in plist:
+        n = p.numel()
+        out.append(flat[off:off + n].view(p.shape))
+        off += n
+    return out
+
+
+_blobs = BlobCache()
+
+
+def _next_seed(module) -> int:
+    cfg = module.config
+    step = getattr(module, "_nrms_dropout_calls", 0)
+    module._nrms_dropout_calls = step + 1
+    return (int(getattr(cfg, "dropout_seed", 0)) + step) & (2**63 - 1)
+
+
+class NewsEncodeFn(torch.autograd.Function):
+    """NewsEncoder.forward (nrms_v0.py:154-176) over a flat list of titles."""
+
+    @staticmethod
+    def forward(ctx, ids, table, dropout_p, seed, gemm_mode, n_heads, *params):
+        ids = ids.contiguous()
+        n_seq, L = ids.shape
+        D = table.shape[1]
+        Q = params[8].numel()
+        shape = EncoderShape(n_seq, L, D, n_heads, Q, table.shape[0])
+        flat = pack_params(params)
+        # a private saved blob per call: several encoder calls may be alive in one graph
+        saved = torch.empty(ops.saved_bytes(shape), dtype=torch.uint8, device=table.device)
+        out = ops.news_encoder_fwd(shape, ids, table.detach(), flat, saved, dropout_p, seed, gemm_mode)
+        ctx.shape, ctx.dropout_p, ctx.seed, ctx.gemm_mode = shape, dropout_p, seed, gemm_mode
+        ctx.save_for_backward(ids, table, flat, saved)
+        ctx.param_shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        ids, table, flat, saved = ctx.saved_tensors
+        shape = ctx.shape
+        dev = table.device
+        scratch = _blobs.get("news_scratch", ops.scratch_bytes(shape), dev)
+        d_flat = torch.empty_like(flat)
+        M = shape.n_seq * shape.seq_len
+        d_rows = torch.empty((M, shape.d_model), dtype=torch.float32, device=dev)
+        ops.news_encoder_bwd(shape, ids, table.detach(), flat, d_out.contiguous(), saved, scratch,
+                             d_flat, d_rows, ctx.dropout_p, ctx.seed, ctx.gemm_mode)
+        plan = _blobs.get("plan", ops.embedding_plan_bytes(M, shape.vocab), dev)
+        ops.embedding_plan(ids, shape.vocab, plan)
+        d_table = torch.empty_like(table)
+        ops.embedding_grad_dense(plan, d_rows, M, shape.vocab, shape.d_model, d_table)
+        grads, off = [], 0
+        for shp in ctx.param_shapes:
+            n = int(torch.Size(shp).numel())
+            grads.append(d_flat[off:off + n].view(shp))
+            off += n
+        return (None, d_table, None, None, None, None, *grads)
+
+
+class UserEncodeFn(torch.autograd.Function):
+    """UserEncoder.forward (nrms_v0.py:188-199)."""
+
+    @staticmethod
+    def forward(ctx, x, gemm_mode, n_heads, *params):
+        x = x.contiguous()
+        n_seq, L, D = x.shape
+        Q = params[8].numel()
+        shape = EncoderShape(n_seq, L, D, n_heads, Q, 0)
+        flat = pack_params(params)
+        saved = torch.empty(ops.saved_bytes(shape), dtype=torch.uint8, device=x.device)
+        out = ops.user_encoder_fwd(shape, x, flat, saved, gemm_mode)
+        ctx.shape, ctx.gemm_mode = shape, gemm_mode
+        ctx.save_for_backward(x, flat, saved)
+        ctx.param_shapes = [p.shape for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, flat, saved = ctx.saved_tensors
+        shape = ctx.shape
+        scratch = _blobs.get("user_scratch", ops.scratch_bytes(shape), x.device)
+        d_flat = torch.empty_like(flat)
+        d_x = torch.empty_like(x)
+        ops.user_encoder_bwd(shape, x, flat, d_out.contiguous(), saved, scratch, d_flat, d_x,
+                             ctx.gemm_mode)
+        grads, off = [], 0
+        for shp in ctx.param_shapes:
+            n = int(torch.Size(shp).numel())
+            grads.append(d_flat[off:off + n].view(shp))
+            off += n
+        return (d_x, None, None, *grads)
+
+
+class ScoreFn(torch.autograd.Function):
+    """DotProductClickPredictor.forward + candidate masking (nrms_v0.py:205-216, 272-274)."""
+
+    @staticmethod
+    def forward(ctx, cand, user, mask):
+        cand, user = cand.contiguous(), user.contiguous()
+        logits = ops.score_fwd(cand, user, mask)
+        ctx.save_for_backward(cand, user)
+        ctx.mask = mask
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        cand, user = ctx.saved_tensors
+        d_cand, d_user = ops.score_bwd(cand, user, ctx.mask, d_logits.contiguous())
+        return d_cand, d_user, None
+
+
+# ------------------------------------------------------------------------------------------
+# fused training step
+# ------------------------------------------------------------------------------------------
+class FusedTrainer:
+    """forward + CrossEntropyLoss(label 0) + backward + Adam (train_eval.py:189-205) without an
+    autograd graph.  The module's parameters are re-pointed at views of two flat buffers
+    (dense block: news encoder then user encoder; table separate), so `state_dict()` and the
+    drop-in forward keep seeing the live weights.
+
+    Data parallel: one process per GPU; every rank passes its own shard of the
+    global batch; gradients carry 1/B_global, are SUM-all-reduced, then every rank applies
+    the same Adam update."""
+
+    def __init__(self, model, lr: Optional[float] = None, betas=(0.9, 0.999), eps: float = 1e-8,
+                 process_group=None, table_sync: str = "dense"):
+        self.model = model
+        cfg = model.config
+        self.cfg = cfg
+        self.lr = float(cfg.learning_rate if lr is None else lr)
+        self.betas, self.eps = betas, eps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.table_sync = table_sync
+        self.step_count = 0
+        self.table = model.news_encoder.word_embedding[0].weight
+        if not self.table.is_cuda:
+            raise NrmsError("FusedTrainer needs the model on a CUDA device (no CPU fallback)")
+        dev = self.table.device
+        self.device = dev
+        self.news_params = encoder_param_list(model.news_encoder)
+        self.user_params = encoder_param_list(model.user_encoder)
+        n_enc = sum(p.numel() for p in self.news_params)
+        self.n_enc = n_enc
+        flat = torch.empty(2 * n_enc, dtype=torch.float32, device=dev)
+        off = 0
+        for plist in (self.news_params, self.user_params):
+            block = flat[off:off + n_enc]
+            o = 0
+            for p in plist:
+                n = p.numel()
+                view = block[o:o + n].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                o += n
+            plist[0]._nrms_flat = block
+            off += n_enc
+        self.flat = flat
+        self.flat_grad = torch.zeros_like(flat)
+        self.flat_m = torch.zeros_like(flat)
+        self.flat_v = torch.zeros_like(flat)
+        self.table_grad = torch.empty_like(self.table.data)
+        self.table_m = torch.zeros_like(self.table.data)
+        self.table_v = torch.zeros_like(self.table.data)
+        self.blobs = BlobCache()
+        self._bufs: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+
+    # -- persistent device buffers per batch shape ----------------------------------------
+    def _buffers(self, B, C, H, T):
+        key = (B, C, H, T)
+        b = self._bufs.get(key)
+        if b is None:
+            dev, D = self.device, self.table.shape[1]
+            n_titles = B * (C + H)
+            b = {
+                "ids": torch.empty((n_titles, T), dtype=torch.int64, device=dev),
+                "mask": torch.empty((B, C), dtype=torch.uint8, device=dev),
+                "news_vec": torch.empty((n_titles, D), dtype=torch.float32, device=dev),
+                "d_news_vec": torch.empty((n_titles, D), dtype=torch.float32, device=dev),
+                "user_vec": torch.empty((B, D), dtype=torch.float32, device=dev),
+                "d_user_vec": torch.empty((B, D), dtype=torch.float32, device=dev),
+                "logits": torch.empty((B, C), dtype=torch.float32, device=dev),
+                "loss_rows": torch.empty((B,), dtype=torch.float32, device=dev),
+                "d_rows": torch.empty((n_titles * T, D), dtype=torch.float32, device=dev),
+            }
+            self._bufs[key] = b
+        return b
+
+    def load_batch(self, batch) -> Dict[str, torch.Tensor]:
+        """H2D copy of the three tensors the path reads (nrms_v0.py:248-250,272) into the
+        persistent device buffers; candidate titles first, then clicked titles."""
+        ct, bt, cm = batch["candidate_titles"], batch["browsed_titles"], batch["candidate_mask"]
+        B, C, T = ct.shape
+        H = bt.shape[1]
+        b = self._buffers(B, C, H, T)
+        b["ids"][:B * C].view(B, C, T).copy_(ct, non_blocking=True)
+        b["ids"][B * C:].view(B, H, T).copy_(bt, non_blocking=True)
+        b["mask"].copy_(cm, non_blocking=True)
+        b["dims"] = (B, C, H, T)
+        return b
+
+    def step(self, batch, b_global: Optional[int] = None) -> torch.Tensor:
+        """One optimisation step on this rank's shard; returns the mean loss of the shard as
+        a 0-dim device tensor (no host sync)."""
+        b = batch if "dims" in batch else self.load_batch(batch)
+        B, C, H, T = b["dims"]
+        cfg, dev = self.cfg, self.device
+        D, V = self.table.shape[1], self.table.shape[0]
+        h, Q = cfg.num_attention_heads, cfg.query_vector_dim
+        gm = int(getattr(cfg, "gemm_mode", 0))
+        training = self.model.training
+        p = float(cfg.dropout) if training else 0.0
+        self.step_count += 1
+        seed = (int(getattr(cfg, "dropout_seed", 0)) + self.step_count) & (2**63 - 1)
+        if b_global is None:
+            b_global = B * self.world
+        n_titles = B * (C + H)
+        news_shape = EncoderShape(n_titles, T, D, h, Q, V)
+        user_shape = EncoderShape(B, H, D, h, Q, 0)
+        news_flat, user_flat = self.flat[:self.n_enc], self.flat[self.n_enc:]
+        news_saved = self.blobs.get("news_saved", ops.saved_bytes(news_shape), dev)
+        user_saved = self.blobs.get("user_saved", ops.saved_bytes(user_shape), dev)
+        news_scratch = self.blobs.get("scratch", max(ops.scratch_bytes(news_shape),
+                                                     ops.scratch_bytes(user_shape)), dev)
+        table = self.table.data
+        # ---- forward ----------------------------------------------------------------------
+        ops.news_encoder_fwd(news_shape, b["ids"], table, news_flat, news_saved, p, seed, gm,
+                             out=b["news_vec"])
+        cand_vec = b["news_vec"][:B * C].view(B, C, D)
+        hist_vec = b["news_vec"][B * C:].view(B, H, D)
+        ops.user_encoder_fwd(user_shape, hist_vec, user_flat, user_saved, gm, out=b["user_vec"])
+        # ---- scorer + CE + their backward ---------------------------------------------------
+        d_cand = b["d_news_vec"][:B * C].view(B, C, D)
+        d_hist = b["d_news_vec"][B * C:].view(B, H, D)
+        ops.score_ce_fwd_bwd(cand_vec, b["user_vec"], b["mask"], b_global, b["logits"],
+                             b["loss_rows"], d_cand, b["d_user_vec"])
+        # ---- backward -----------------------------------------------------------------------
+        ops.user_encoder_bwd(user_shape, hist_vec, user_flat, b["d_user_vec"], user_saved,
+                             news_scratch, self.flat_grad[self.n_enc:], d_hist, gm)
+        ops.news_encoder_bwd(news_shape, b["ids"], table, news_flat, b["d_news_vec"], news_saved,
+                             news_scratch, self.flat_grad[:self.n_enc], b["d_rows"], p, seed, gm)
+        M = n_titles * T
+        plan = self.blobs.get("plan", ops.embedding_plan_bytes(M, V), dev)
+        ops.embedding_plan(b["ids"], V, plan)
+        ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
+        # ---- gradient exchange (data parallel) ----------------------------------------------
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, group=self.pg)
+            dist.all_reduce(self.table_grad, group=self.pg)
+        # ---- Adam ---------------------------------------------------------------------------
+        b1, b2 = self.betas
+        ops.adam_step(self.flat, self.flat_grad, self.flat_m, self.flat_v, self.step_count, self.lr,
+                      b1, b2, self.eps)
+        ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
+                      b1, b2, self.eps)
+        return b["loss_rows"].mean()
+
+    def grads_as_state_dict(self) -> Dict[str, torch.Tensor]:
+        """Last step's gradients keyed like model.state_dict() (for parity tests)."""
+        out = {"news_encoder.word_embedding.0.weight": self.table_grad}
+        for prefix, lo in (("news_encoder.", 0), ("user_encoder.", self.n_enc)):
+            block = self.flat_grad[lo:lo + self.n_enc]
+            plist = self.news_params if lo == 0 else self.user_params
+            names = ["multihead_self_attention." + n for n in _ENC_PARAM_ORDER[:6]] + \
+                    ["additive_attention." + n for n in _ENC_PARAM_ORDER[6:]]
+            for name, g in zip(names, split_flat(block, plist)):
+                out[prefix + name] = g
+        return out

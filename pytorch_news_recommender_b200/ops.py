@@ -1,0 +1,235 @@
+"""Thin host wrappers over the C-ABI (include/nrms_b200.h): torch CUDA tensors in, torch CUDA
+tensors out, every byte of device memory owned by torch, every kernel ours.
+
+torch is plumbing here (allocation, streams, autograd bookkeeping); no op below has a
+PyTorch/CPU fallback — a non-CUDA tensor or a missing library raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EncoderDims, NrmsError, check, ptr
+
+DROP_EMBEDDING = 1
+DROP_CONTEXT = 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise NrmsError("this path runs on a CUDA device only (sm_100a kernels); "
+                            "got a CPU tensor and there is no CPU fallback")
+
+
+def _cf32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise NrmsError(f"expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+@dataclass(frozen=True)
+class EncoderShape:
+    n_seq: int
+    seq_len: int
+    d_model: int
+    n_heads: int
+    d_query: int
+    vocab: int = 0
+
+    def dims(self, dropout_p: float = 0.0, seed: int = 0, gemm_mode: int = 0) -> EncoderDims:
+        return EncoderDims(self.n_seq, self.seq_len, self.d_model, self.n_heads, self.d_query,
+                           self.vocab, float(dropout_p), int(gemm_mode), int(seed) & (2**64 - 1))
+
+
+def encoder_param_count(d_model: int, d_query: int) -> int:
+    return int(_lib.load().nrms_encoder_param_count(d_model, d_query))
+
+
+def saved_bytes(shape: EncoderShape) -> int:
+    n = int(_lib.load().nrms_encoder_saved_bytes(shape.dims()))
+    if n < 0:
+        check(-1, "nrms_encoder_saved_bytes")
+    return n
+
+
+def scratch_bytes(shape: EncoderShape) -> int:
+    n = int(_lib.load().nrms_encoder_scratch_bytes(shape.dims()))
+    if n < 0:
+        check(-1, "nrms_encoder_scratch_bytes")
+    return n
+
+
+class BlobCache:
+    """Caller-owned device blobs (saved activations / scratch), grown on demand and reused."""
+
+    def __init__(self):
+        self._blobs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, nbytes: int, device) -> torch.Tensor:
+        b = self._blobs.get(name)
+        if b is None or b.numel() < nbytes or b.device != torch.device(device):
+            b = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
+            self._blobs[name] = b
+        return b
+
+    def clear(self):
+        self._blobs.clear()
+
+
+def news_encoder_fwd(shape: EncoderShape, ids, table, params, saved, dropout_p=0.0, seed=0,
+                     gemm_mode=0, out=None):
+    _require_cuda(ids, table, params, saved)
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        raise NrmsError("ids must be contiguous int64")
+    if out is None:
+        out = torch.empty((shape.n_seq, shape.d_model), dtype=torch.float32, device=table.device)
+    d = shape.dims(dropout_p, seed, gemm_mode)
+    check(_lib.load().nrms_news_encoder_fwd(d, ptr(ids), ptr(table), ptr(params), ptr(out),
+                                            ptr(saved), saved.numel(), _stream()),
+          "nrms_news_encoder_fwd")
+    return out
+
+
+def news_encoder_bwd(shape: EncoderShape, ids, table, params, d_out, saved, scratch, d_params,
+                     d_rows, dropout_p=0.0, seed=0, gemm_mode=0):
+    _require_cuda(ids, table, params, d_out, saved, scratch, d_params, d_rows)
+    d = shape.dims(dropout_p, seed, gemm_mode)
+    check(_lib.load().nrms_news_encoder_bwd(d, ptr(ids), ptr(table), ptr(params), ptr(d_out),
+                                            ptr(saved), saved.numel(), ptr(scratch),
+                                            scratch.numel(), ptr(d_params), ptr(d_rows), _stream()),
+          "nrms_news_encoder_bwd")
+
+
+def user_encoder_fwd(shape: EncoderShape, x, params, saved, gemm_mode=0, out=None):
+    _require_cuda(x, params, saved)
+    if out is None:
+        out = torch.empty((shape.n_seq, shape.d_model), dtype=torch.float32, device=x.device)
+    d = shape.dims(0.0, 0, gemm_mode)
+    check(_lib.load().nrms_user_encoder_fwd(d, ptr(x), ptr(params), ptr(out), ptr(saved),
+                                            saved.numel(), _stream()), "nrms_user_encoder_fwd")
+    return out
+
+
+def user_encoder_bwd(shape: EncoderShape, x, params, d_out, saved, scratch, d_params, d_x,
+                     gemm_mode=0):
+    _require_cuda(x, params, d_out, saved, scratch, d_params, d_x)
+    d = shape.dims(0.0, 0, gemm_mode)
+    check(_lib.load().nrms_user_encoder_bwd(d, ptr(x), ptr(params), ptr(d_out), ptr(saved),
+                                            saved.numel(), ptr(scratch), scratch.numel(),
+                                            ptr(d_params), ptr(d_x), _stream()),
+          "nrms_user_encoder_bwd")
+
+
+def score_fwd(cand, user, mask):
+    _require_cuda(cand, user, mask)
+    B, Cn, D = cand.shape
+    logits = torch.empty((B, Cn), dtype=torch.float32, device=cand.device)
+    check(_lib.load().nrms_score_fwd(B, Cn, D, ptr(cand), ptr(user), ptr(mask), ptr(logits),
+                                     _stream()), "nrms_score_fwd")
+    return logits
+
+
+def score_bwd(cand, user, mask, d_logits, d_cand=None, d_user=None):
+    _require_cuda(cand, user, mask, d_logits)
+    B, Cn, D = cand.shape
+    if d_cand is None:
+        d_cand = torch.empty_like(cand)
+    if d_user is None:
+        d_user = torch.empty_like(user)
+    check(_lib.load().nrms_score_bwd(B, Cn, D, ptr(cand), ptr(user), ptr(mask), ptr(d_logits),
+                                     ptr(d_cand), ptr(d_user), _stream()), "nrms_score_bwd")
+    return d_cand, d_user
+
+
+def score_ce_fwd_bwd(cand, user, mask, b_global, logits, loss_rows, d_cand, d_user):
+    _require_cuda(cand, user, mask, logits, loss_rows, d_cand, d_user)
+    B, Cn, D = cand.shape
+    check(_lib.load().nrms_score_ce_fwd_bwd(B, Cn, D, int(b_global), ptr(cand), ptr(user),
+                                            ptr(mask), ptr(logits), ptr(loss_rows), ptr(d_cand),
+                                            ptr(d_user), _stream()), "nrms_score_ce_fwd_bwd")
+
+
+def embedding_plan_bytes(n_rows: int, vocab: int) -> int:
+    return int(_lib.load().nrms_embedding_plan_bytes(n_rows, vocab))
+
+
+def embedding_plan(ids, vocab: int, plan):
+    _require_cuda(ids, plan)
+    check(_lib.load().nrms_embedding_plan(ptr(ids), ids.numel(), vocab, ptr(plan), plan.numel(),
+                                          _stream()), "nrms_embedding_plan")
+
+
+def embedding_grad_dense(plan, d_rows, n_rows: int, vocab: int, D: int, d_table):
+    _require_cuda(plan, d_rows, d_table)
+    check(_lib.load().nrms_embedding_grad_dense(ptr(plan), plan.numel(), ptr(d_rows), n_rows, vocab,
+                                                D, ptr(d_table), _stream()),
+          "nrms_embedding_grad_dense")
+
+
+def embedding_plan_unique(plan, vocab: int) -> torch.Tensor:
+    out = torch.zeros(1, dtype=torch.int32, device=plan.device)
+    check(_lib.load().nrms_embedding_plan_unique(ptr(plan), plan.numel(), vocab, ptr(out), _stream()),
+          "nrms_embedding_plan_unique")
+    return out
+
+
+def adam_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    _require_cuda(p, g, m, v)
+    check(_lib.load().nrms_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), float(lr),
+                                     float(beta1), float(beta2), float(eps), float(grad_scale),
+                                     _stream()), "nrms_adam_step")
+
+
+def rank_metrics(scores, labels, offsets, max_len: int, row_stride: Optional[int] = None):
+    """scores ragged [sum n_i] (row_stride None) or padded [N, row_stride]; labels uint8 ragged;
+    offsets int64 [N+1].  Returns float64 [N, 4] = AUC, MRR, nDCG@5, nDCG@10."""
+    _require_cuda(scores, labels, offsets)
+    n = offsets.numel() - 1
+    out = torch.empty((n, 4), dtype=torch.float64, device=scores.device)
+    lib = _lib.load()
+    if row_stride is None:
+        check(lib.nrms_rank_metrics(ptr(scores), ptr(labels), ptr(offsets), n, int(max_len), ptr(out),
+                                    _stream()), "nrms_rank_metrics")
+    else:
+        check(lib.nrms_rank_metrics_padded(ptr(scores), int(row_stride), ptr(labels), ptr(offsets), n,
+                                           int(max_len), ptr(out), _stream()),
+              "nrms_rank_metrics_padded")
+    return out
+
+
+def gather_rows(src, idx, base: int = 0):
+    """out[i] = src[idx[i] - base] (zeros when idx[i] < base).  src float32 or int64 [n, D]."""
+    _require_cuda(src, idx)
+    n_src, D = src.shape
+    out = torch.empty((idx.numel(), D), dtype=src.dtype, device=src.device)
+    lib = _lib.load()
+    fn = lib.nrms_gather_rows_f32 if src.dtype == torch.float32 else lib.nrms_gather_rows_i64
+    if src.dtype not in (torch.float32, torch.int64):
+        raise NrmsError(f"gather_rows: unsupported dtype {src.dtype}")
+    check(fn(ptr(src), n_src, D, ptr(idx), idx.numel(), int(base), ptr(out), _stream()),
+          "nrms_gather_rows")
+    return out
+
+
+def dropout_mask(seed: int, stream_id: int, p: float, n: int, device) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    check(_lib.load().nrms_dropout_mask(int(seed) & (2**64 - 1), stream_id, float(p), n, ptr(out),
+                                        _stream()), "nrms_dropout_mask")
+    return out
+
+
+def validate_ids(ids, vocab: int) -> bool:
+    """True when every id is inside [0, vocab) (synchronises: debugging aid, not hot path)."""
+    _require_cuda(ids)
+    flag = torch.zeros(1, dtype=torch.int32, device=ids.device)
+    check(_lib.load().nrms_validate_ids(ptr(ids), ids.numel(), vocab, ptr(flag), _stream()),
+          "nrms_validate_ids")
+    return int(flag.item()) == 0
