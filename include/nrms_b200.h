@@ -64,6 +64,14 @@ typedef struct nrms_encoder_dims {
 int nrms_abi_version(void);
 const char* nrms_last_error(void);
 
+/* Kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t nrms_launch_count(void);
+/* Opt-in per-kernel timing: CUDA events recorded around every launch on its own stream.
+ * nrms_profile_collect synchronises and writes "kernel count total_ms" lines into the HOST
+ * buffer h_buf, then clears the log. */
+void nrms_profile_enable(int on);
+int nrms_profile_collect(char* h_buf, int64_t h_buf_bytes);
+
 /* number of floats in one encoder's flat parameter block */
 int64_t nrms_encoder_param_count(int32_t d_model, int32_t d_query);
 /* bytes of the activations the forward saves for the backward */

@@ -44,6 +44,9 @@ _DIMS = C.POINTER(EncoderDims)
 SIGNATURES = {
     "nrms_abi_version": (C.c_int, []),
     "nrms_last_error": (C.c_char_p, []),
+    "nrms_launch_count": (_I64, []),
+    "nrms_profile_enable": (None, [C.c_int]),
+    "nrms_profile_collect": (C.c_int, [C.c_char_p, _I64]),
     "nrms_encoder_param_count": (_I64, [_I32, _I32]),
     "nrms_encoder_saved_bytes": (_I64, [_DIMS]),
     "nrms_encoder_scratch_bytes": (_I64, [_DIMS]),

@@ -12,6 +12,7 @@
 #include "gemm_simt.cuh"
 #include "metrics.cuh"
 #include "pooling.cuh"
+#include "profiler.cuh"
 #include "train_kernels.cuh"
 
 using namespace nrms;
@@ -179,15 +180,15 @@ int reduce_rows(const float* in, float* out, long long R, long long n, long long
                 float* tmp, cudaStream_t s) {
     const int threads = 256;
     if (R <= 256 || tmp == nullptr) {
-        reduce_rows_kernel<<<(unsigned)ceil_div64(n, threads), threads, 0, s>>>(in, out, R, n, ld,
-                                                                               scale, 0);
+        NRMS_LAUNCH("reduce_rows", s, reduce_rows_kernel<<<(unsigned)ceil_div64(n, threads), threads, 0, s>>>(in, out, R, n, ld,
+                                                                               scale, 0));
     } else {
         const long long per = ceil_div64(R, kReduceSlices);
         const int slices = (int)ceil_div64(R, per);
-        reduce_rows_sliced_kernel<<<dim3((unsigned)ceil_div64(n, threads), slices), threads, 0, s>>>(
-            in, tmp, R, n, ld, per);
-        reduce_rows_kernel<<<(unsigned)ceil_div64(n, threads), threads, 0, s>>>(tmp, out, slices, n,
-                                                                               n, scale, 0);
+        NRMS_LAUNCH("reduce_rows_sliced", s, reduce_rows_sliced_kernel<<<dim3((unsigned)ceil_div64(n, threads), slices), threads, 0, s>>>(
+            in, tmp, R, n, ld, per));
+        NRMS_LAUNCH("reduce_rows", s, reduce_rows_kernel<<<(unsigned)ceil_div64(n, threads), threads, 0, s>>>(tmp, out, slices, n,
+                                                                               n, scale, 0));
     }
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
@@ -216,7 +217,7 @@ int linear_fwd(const nrms_encoder_dims& d, const float* x, const int64_t* gather
     g.drop_on = (drop_in && g.drop.enabled()) ? 1 : 0;
     g.drop_sid = kDropEmbedding;
     if (d.gemm_mode == 1) return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode=1 (tcgen05) not built");
-    NRMS_CHECK_CUDA(launch_gemm_simt(g, true, true, 1, s));
+    NRMS_CHECK_CUDA(launch_gemm_simt(g, true, true, 1, s, N == 3 * K ? "gemm_fwd_qkv" : "gemm_fwd_additive"));
     return NRMS_OK;
 }
 
@@ -250,7 +251,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
         const int warps = a.hpb * ceil_div(L, 32);
-        attn_fwd_kernel<<<dim3(d.n_seq, ceil_div(h, a.hpb)), warps * 32, smem, s>>>(a);
+        NRMS_LAUNCH("attn_fwd", s, attn_fwd_kernel<<<dim3(d.n_seq, ceil_div(h, a.hpb)), warps * 32, smem, s>>>(a));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     // 3. additive-attention projection t = tanh(ctx W_a^T + b_a) (nrms_v0.py:108)
@@ -261,7 +262,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         PoolArgs p{};
         p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.out = out;
         p.L = L; p.D = D; p.Q = Q;
-        pool_fwd_kernel<<<d.n_seq, 256, L * sizeof(float), s>>>(p);
+        NRMS_LAUNCH("pool_fwd", s, pool_fwd_kernel<<<d.n_seq, 256, L * sizeof(float), s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     return NRMS_OK;
@@ -292,7 +293,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.d_out = d_out;
         p.d_ctx = sc.d_ctx; p.d_pre = sc.d_pre; p.d_part = sc.part_q;
         p.L = L; p.D = D; p.Q = Q;
-        pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p);
+        NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     // [d_b_a | d_query] are adjacent in the flat block, as in part_q
@@ -304,7 +305,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.A = sc.d_pre; g.B = pv.Wa; g.C = sc.d_ctx;
         g.M = M; g.N = D; g.K = Q; g.lda = Q; g.ldb = D; g.ldc = D;
         g.k_chunk = Q; g.accumulate = 1;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s));
+        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_additive"));
     }
     // 3. dW_a = d_pre^T ctx   (reduction over the M token rows, split + deterministic reduce)
     {
@@ -314,7 +315,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.M = Q; g.N = D; g.K = M; g.lda = Q; g.ldb = D; g.ldc = D;
         g.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
         g.c_split_stride = (long long)Q * D;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, false, false, ceil_div(M, g.k_chunk), s));
+        NRMS_CHECK_CUDA(launch_gemm_simt(g, false, false, ceil_div(M, g.k_chunk), s, "gemm_wgrad_additive"));
         rc = reduce_rows(sc.wpart, gv.Wa, ceil_div(M, g.k_chunk), (long long)Q * D,
                          (long long)Q * D, 1.f, nullptr, s);
         if (rc) return rc;
@@ -333,7 +334,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem));
         const int warps = a.hpb * ceil_div(L, 32);
-        attn_bwd_kernel<<<dim3(d.n_seq, ceil_div(h, a.hpb)), warps * 32, smem, s>>>(a);
+        NRMS_LAUNCH("attn_bwd", s, attn_bwd_kernel<<<dim3(d.n_seq, ceil_div(h, a.hpb)), warps * 32, smem, s>>>(a));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     rc = reduce_rows(sc.part_b, gv.bqkv, d.n_seq, 3 * D, 3 * D, 1.f, sc.red_tmp, s);
@@ -349,7 +350,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.c_split_stride = 3ll * D * D;
         g.drop = drop; g.drop_sid = kDropEmbedding;
         g.drop_on = (news && drop.enabled()) ? 2 : 0;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, false, false, ceil_div(M, g.k_chunk), s));
+        NRMS_CHECK_CUDA(launch_gemm_simt(g, false, false, ceil_div(M, g.k_chunk), s, "gemm_wgrad_qkv"));
         rc = reduce_rows(sc.wpart, gv.Wqkv, ceil_div(M, g.k_chunk), 3ll * D * D, 3ll * D * D, 1.f,
                          nullptr, s);
         if (rc) return rc;
@@ -362,7 +363,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.k_chunk = 3 * D;
         g.drop = drop; g.drop_sid = kDropEmbedding;
         g.drop_on = (news && drop.enabled()) ? 3 : 0;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s));
+        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_qkv"));
     }
     return NRMS_OK;
 }
@@ -373,6 +374,17 @@ extern "C" {
 
 int nrms_abi_version(void) { return NRMS_ABI_VERSION; }
 const char* nrms_last_error(void) { return g_err; }
+
+int64_t nrms_launch_count(void) { return Profiler::get().launches; }
+void nrms_profile_enable(int on) { Profiler::get().on = on != 0; }
+int nrms_profile_collect(char* h_buf, int64_t h_buf_bytes) {
+    const std::string s = Profiler::get().collect();
+    if (!h_buf || h_buf_bytes < 1) return fail(NRMS_ERR_NULL, "h_buf is NULL");
+    const int64_t n = (int64_t)s.size() < h_buf_bytes - 1 ? (int64_t)s.size() : h_buf_bytes - 1;
+    memcpy(h_buf, s.data(), (size_t)n);
+    h_buf[n] = 0;
+    return NRMS_OK;
+}
 
 int64_t nrms_encoder_param_count(int32_t D, int32_t Q) {
     return 3ll * D * D + 3ll * D + (int64_t)Q * D + 2ll * Q;
@@ -446,7 +458,7 @@ int nrms_score_fwd(int32_t B, int32_t C, int32_t D, const float* cand, const flo
     NRMS_REQUIRE_PTR(cand); NRMS_REQUIRE_PTR(user); NRMS_REQUIRE_PTR(logits);
     ScoreArgs a{};
     a.cand = cand; a.user = user; a.mask = mask; a.logits = logits; a.B = B; a.C = C; a.D = D;
-    score_kernel<0><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(a);
+    NRMS_LAUNCH("score_0", (cudaStream_t)stream, score_kernel<0><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(a));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -460,7 +472,7 @@ int nrms_score_bwd(int32_t B, int32_t C, int32_t D, const float* cand, const flo
     ScoreArgs a{};
     a.cand = cand; a.user = user; a.mask = mask; a.d_logits = d_logits; a.d_cand = d_cand;
     a.d_user = d_user; a.B = B; a.C = C; a.D = D;
-    score_kernel<2><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(a);
+    NRMS_LAUNCH("score_2", (cudaStream_t)stream, score_kernel<2><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(a));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -478,7 +490,7 @@ int nrms_score_ce_fwd_bwd(int32_t B, int32_t C, int32_t D, int32_t B_global, con
     a.cand = cand; a.user = user; a.mask = mask; a.logits = logits; a.loss_rows = loss_per_row;
     a.d_cand = d_cand; a.d_user = d_user; a.B = B; a.C = C; a.D = D;
     a.inv_batch = 1.f / (float)B_global;
-    score_kernel<1><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(a);
+    NRMS_LAUNCH("score_1", (cudaStream_t)stream, score_kernel<1><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(a));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -498,12 +510,12 @@ int nrms_embedding_plan(const int64_t* ids, int64_t n_rows, int32_t vocab, void*
     cudaStream_t s = (cudaStream_t)stream;
     PlanView v = plan_view(plan, n_rows, vocab);
     NRMS_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int32_t) * vocab, s));
-    plan_hist_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.counts);
-    plan_scan_kernel<<<1, 1024, 0, s>>>(v.counts, v.offsets, v.cursor, v.n_valid, vocab);
-    plan_fill_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.offsets, v.cursor,
-                                                          v.perm, v.sorted_id);
-    plan_sort_segments_kernel<<<grid_for((long long)vocab * 32, 256), 256, 0, s>>>(v.offsets, v.perm,
-                                                                                  vocab);
+    NRMS_LAUNCH("plan_hist", s, plan_hist_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.counts));
+    NRMS_LAUNCH("plan_scan", s, plan_scan_kernel<<<1, 1024, 0, s>>>(v.counts, v.offsets, v.cursor, v.n_valid, vocab));
+    NRMS_LAUNCH("plan_fill", s, plan_fill_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.offsets, v.cursor,
+                                                          v.perm, v.sorted_id));
+    NRMS_LAUNCH("plan_sort_segments", s, plan_sort_segments_kernel<<<grid_for((long long)vocab * 32, 256), 256, 0, s>>>(v.offsets, v.perm,
+                                                                                  vocab));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -518,9 +530,9 @@ int nrms_embedding_grad_dense(const void* plan, int64_t plan_bytes_, const float
     cudaStream_t s = (cudaStream_t)stream;
     PlanView v = plan_view(const_cast<void*>(plan), n_rows, vocab);
     const long long n4 = (long long)vocab * D / 4;
-    zero_kernel<<<grid_for(n4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(d_table), n4);
-    embgrad_reduce_kernel<<<grid_for(n_rows, 256, 16), 256, 0, s>>>(v.perm, v.sorted_id, v.offsets,
-                                                                   v.n_valid, d_rows, D, d_table);
+    NRMS_LAUNCH("zero", s, zero_kernel<<<grid_for(n4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(d_table), n4));
+    NRMS_LAUNCH("embgrad_reduce", s, embgrad_reduce_kernel<<<grid_for(n_rows, 256, 16), 256, 0, s>>>(v.perm, v.sorted_id, v.offsets,
+                                                                   v.n_valid, d_rows, D, d_table));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -531,8 +543,8 @@ int nrms_embedding_plan_unique(const void* plan, int64_t plan_bytes_, int32_t vo
     (void)plan_bytes_;
     cudaStream_t s = (cudaStream_t)stream;
     NRMS_CHECK_CUDA(cudaMemsetAsync(d_unique, 0, sizeof(int32_t), s));
-    plan_unique_kernel<<<grid_for(vocab, 256), 256, 0, s>>>(
-        reinterpret_cast<const int32_t*>(plan), vocab, d_unique);
+    NRMS_LAUNCH("plan_unique", s, plan_unique_kernel<<<grid_for(vocab, 256), 256, 0, s>>>(
+        reinterpret_cast<const int32_t*>(plan), vocab, d_unique));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -550,7 +562,7 @@ int nrms_adam_step(float* p, const float* g, float* m, float* v, int64_t n, int3
     const double bc2 = 1.0 - pow((double)beta2, (double)step);
     a.step_size = (float)((double)lr / bc1);
     a.bc2_sqrt = (float)sqrt(bc2);
-    adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    NRMS_LAUNCH("adam", (cudaStream_t)stream, adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -565,8 +577,8 @@ static int metrics_impl(const float* scores, long long row_stride, const uint8_t
     NRMS_CHECK_CUDA(cudaFuncSetAttribute(rank_metrics_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = grid_for(n_impr * 32, kMetricWarps * 32, 8);
-    rank_metrics_kernel<<<grid, kMetricWarps * 32, smem, s>>>(scores, row_stride, labels, offsets,
-                                                             n_impr, max_len, out);
+    NRMS_LAUNCH("rank_metrics", s, rank_metrics_kernel<<<grid, kMetricWarps * 32, smem, s>>>(scores, row_stride, labels, offsets,
+                                                             n_impr, max_len, out));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -588,8 +600,8 @@ int nrms_gather_rows_f32(const float* src, int64_t n_src, int32_t D, const int64
                          int64_t n_idx, int64_t base, float* out, nrms_stream_t stream) {
     if (n_src < 1 || D < 1 || n_idx < 1) return fail(NRMS_ERR_BAD_SHAPE, "bad gather shape");
     if (!src || !idx || !out) return fail(NRMS_ERR_NULL, "NULL argument");
-    gather_rows_kernel<float><<<grid_for(n_idx * 32, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-        src, n_src, D, idx, n_idx, base, out);
+    NRMS_LAUNCH("gather_rows_float", (cudaStream_t)stream, gather_rows_kernel<float><<<grid_for(n_idx * 32, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        src, n_src, D, idx, n_idx, base, out));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -597,8 +609,8 @@ int nrms_gather_rows_i64(const int64_t* src, int64_t n_src, int32_t D, const int
                          int64_t n_idx, int64_t base, int64_t* out, nrms_stream_t stream) {
     if (n_src < 1 || D < 1 || n_idx < 1) return fail(NRMS_ERR_BAD_SHAPE, "bad gather shape");
     if (!src || !idx || !out) return fail(NRMS_ERR_NULL, "NULL argument");
-    gather_rows_kernel<int64_t><<<grid_for(n_idx * 32, 256, 16), 256, 0, (cudaStream_t)stream>>>(
-        src, n_src, D, idx, n_idx, base, out);
+    NRMS_LAUNCH("gather_rows_int64_t", (cudaStream_t)stream, gather_rows_kernel<int64_t><<<grid_for(n_idx * 32, 256, 16), 256, 0, (cudaStream_t)stream>>>(
+        src, n_src, D, idx, n_idx, base, out));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -607,8 +619,8 @@ int nrms_dropout_mask(uint64_t seed, uint32_t stream_id, float p, int64_t n, flo
                       nrms_stream_t stream) {
     if (n < 1 || p < 0.f || p >= 1.f) return fail(NRMS_ERR_BAD_SHAPE, "n=%lld p=%f", (long long)n, (double)p);
     if (!out) return fail(NRMS_ERR_NULL, "out is NULL");
-    dropout_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_dropout(p, seed),
-                                                                           stream_id, n, out);
+    NRMS_LAUNCH("dropout_mask", (cudaStream_t)stream, dropout_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_dropout(p, seed),
+                                                                           stream_id, n, out));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -617,7 +629,7 @@ int nrms_validate_ids(const int64_t* ids, int64_t n, int64_t vocab, int32_t* d_f
                       nrms_stream_t stream) {
     if (n < 1) return fail(NRMS_ERR_BAD_SHAPE, "n=%lld", (long long)n);
     if (!ids || !d_flag) return fail(NRMS_ERR_NULL, "NULL argument");
-    validate_ids_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(ids, n, vocab, d_flag);
+    NRMS_LAUNCH("validate_ids", (cudaStream_t)stream, validate_ids_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(ids, n, vocab, d_flag));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }

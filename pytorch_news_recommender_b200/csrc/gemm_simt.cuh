@@ -13,6 +13,7 @@
 // All contiguous extents are feature dims (300/900/200) => multiples of 4 => float4 access.
 #pragma once
 #include "common.cuh"
+#include "profiler.cuh"
 
 namespace nrms {
 
@@ -214,16 +215,16 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_simt_kernel(const GemmArgs g
 
 // Host launcher.  Returns cudaGetLastError().
 inline cudaError_t launch_gemm_simt(const GemmArgs& g, bool a_kc, bool b_kc, int splits,
-                                    cudaStream_t s) {
+                                    cudaStream_t s, const char* name = "gemm_simt") {
     dim3 grid(ceil_div(g.M, GBM), ceil_div(g.N, GBN), splits);
     if (a_kc && b_kc)
-        gemm_simt_kernel<true, true><<<grid, GTHREADS, 0, s>>>(g);
+        NRMS_LAUNCH(name, s, gemm_simt_kernel<true, true><<<grid, GTHREADS, 0, s>>>(g));
     else if (a_kc && !b_kc)
-        gemm_simt_kernel<true, false><<<grid, GTHREADS, 0, s>>>(g);
+        NRMS_LAUNCH(name, s, gemm_simt_kernel<true, false><<<grid, GTHREADS, 0, s>>>(g));
     else if (!a_kc && !b_kc)
-        gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, s>>>(g);
+        NRMS_LAUNCH(name, s, gemm_simt_kernel<false, false><<<grid, GTHREADS, 0, s>>>(g));
     else
-        gemm_simt_kernel<false, true><<<grid, GTHREADS, 0, s>>>(g);
+        NRMS_LAUNCH(name, s, gemm_simt_kernel<false, true><<<grid, GTHREADS, 0, s>>>(g));
     return cudaGetLastError();
 }
 

@@ -1,0 +1,317 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) vs the oracle and the committed
+golden fixtures generated from the reference.  Tolerances: forward scores 1e-3 relative
+(BASELINE.json north_star, fp32); indices/grouping exact; metrics 1e-9 (float64 on device).
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nrms_oracle as O
+from _golden import GOLDEN_DIR, Case, check_summary
+
+pytestmark = pytest.mark.gpu
+
+GEMM_MODES = [0]
+
+
+def _cfg_from_case(c, dropout=None, gemm_mode=0):
+    from pytorch_news_recommender_b200.config import Config
+    from pytorch_news_recommender_b200 import synthetic as S
+    cfg = Config("NRMS_V0_TEST")
+    cfg.__nrms__()
+    cfg.n_words_title, cfg.history_len, cfg.sample_size = c.T, c.H, c.C - 1
+    cfg.word_embed_size, cfg.num_attention_heads, cfg.query_vector_dim = c.D, c.h, c.Q
+    cfg.dropout = c.cfg.dropout if dropout is None else dropout
+    cfg.learning_rate = c.cfg.learning_rate
+    cfg.gemm_mode = gemm_mode
+    tmp = tempfile.mkdtemp()
+    S.save_embedding_npz(os.path.join(tmp, "emb.npz"), c.table)
+    cfg.data_path, cfg.word_embedding_pretrained = tmp + "/", "emb.npz"
+    cfg.device = torch.device("cuda:0")
+    return cfg
+
+
+def _model_from_case(c, dropout=None, gemm_mode=0):
+    from pytorch_news_recommender_b200.model import NRMS_V0
+    cfg = _cfg_from_case(c, dropout, gemm_mode)
+    torch.manual_seed(42)
+    model = NRMS_V0(cfg)
+    sd = c.state_dict()
+    model.load_state_dict(sd)
+    return model.to(cfg.device), cfg, sd
+
+
+def _rel_err(a, b, floor=1e-3):
+    a, b = a.double(), b.double()
+    return ((a - b).abs() / b.abs().clamp_min(floor)).max().item()
+
+
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+@pytest.mark.parametrize("name", ["tiny", "mind", "long"])
+def test_seeded_init_and_eval_logits_match_reference(name, gemm_mode, built_lib):
+    from pytorch_news_recommender_b200.model import NRMS_V0
+    c = Case(name)
+    cfg = _cfg_from_case(c, gemm_mode=gemm_mode)
+    torch.manual_seed(42)                      # run_demo.py:22 — same RNG stream as the reference
+    model = NRMS_V0(cfg).to(cfg.device)
+    assert list(model.state_dict().keys()) == O.state_dict_keys()
+    check_summary(c, "sd0sum", {k: v for k, v in model.state_dict().items()}, rtol=0.0, atol_frac=0.0,
+                  abs_floor=0.0)
+    model.eval()
+    with torch.no_grad():
+        logits = model(c.batch)
+        assert logits.is_cuda and logits.shape == (c.B, c.C)
+        cand = model.get_news_vector(c.batch["candidate_titles"].reshape(-1, c.T).cuda())
+        hist = model.get_news_vector(c.batch["browsed_titles"].reshape(-1, c.T).cuda()).view(c.B, c.H, -1)
+        user = model.get_user_vector(hist)
+        pred0 = model.get_prediction(cand.view(c.B, c.C, -1)[0], user[0])
+    gold = torch.from_numpy(c.z["eval/logits"])
+    real = c.batch["candidate_mask"].bool()
+    assert torch.equal(logits.cpu()[~real], gold[~real])            # -1e9 fill, exact
+    assert _rel_err(logits.cpu()[real], gold[real]) < 1e-3
+    np.testing.assert_allclose(cand.cpu().numpy().reshape(c.B, c.C, -1), c.z["eval/cand_vec"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(user.cpu().numpy(), c.z["eval/user_vec"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(hist.cpu().numpy()[:, ::7], c.z["eval/hist_vec_sample"], rtol=1e-3, atol=2e-5)
+    assert _rel_err(pred0.cpu()[real[0]], gold[0][real[0]]) < 1e-3
+
+
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+@pytest.mark.parametrize("name", ["tiny", "mind"])
+def test_dropin_backward_matches_reference(name, gemm_mode, built_lib):
+    """model(datas) -> CrossEntropyLoss -> loss.backward() exactly as train_eval.py:189-204."""
+    c = Case(name)
+    model, cfg, _ = _model_from_case(c, dropout=0.0, gemm_mode=gemm_mode)
+    model.train()
+    out = model(c.batch)
+    model.zero_grad()
+    y = torch.zeros(len(out)).long().to(cfg.device)
+    loss = torch.nn.CrossEntropyLoss()(out, y)
+    loss.backward()
+    assert abs(loss.item() - float(c.z["evalgrad/loss"])) < 1e-4
+    grads = {k: p.grad for k, p in model.named_parameters()}
+    assert all(g is not None for g in grads.values())
+    check_summary(c, "evalgrad", grads, rtol=2e-3, atol_frac=2e-3)
+    assert float(grads[O.TABLE_KEY][0].abs().max()) == 0.0          # padding_idx row stays 0
+    if name == "tiny":
+        for k, g in grads.items():
+            gold = c.z[f"evalgrad/full/{k}"]
+            scale = max(float(np.abs(gold).max()), 1e-6)
+            np.testing.assert_allclose(g.cpu().numpy(), gold, rtol=2e-3, atol=2e-4 * scale + 1e-7)
+
+
+def _kernel_masks(cfg, c, seed):
+    from pytorch_news_recommender_b200 import ops
+    n = c.B * (c.C + c.H) * c.T * c.D
+    m1 = ops.dropout_mask(seed, ops.DROP_EMBEDDING, cfg.dropout, n, "cuda:0").view(-1, c.T, c.D).cpu()
+    m2 = ops.dropout_mask(seed, ops.DROP_CONTEXT, cfg.dropout, n, "cuda:0").view(-1, c.T, c.D).cpu()
+    return m1, m2
+
+
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+@pytest.mark.parametrize("name", ["tiny", "mind"])
+def test_fused_train_steps_with_dropout_match_oracle(name, gemm_mode, built_lib):
+    """Fused forward+CE+backward+Adam in train mode.  The Philox masks the kernels apply are
+    exported through the C-ABI test hook and fed to the oracle, so the comparison is exact
+    arithmetic parity, dropout included."""
+    from pytorch_news_recommender_b200.engine import FusedTrainer
+    c = Case(name)
+    model, cfg, sd = _model_from_case(c, gemm_mode=gemm_mode)
+    cfg.dropout_seed = 1234
+    model.train()
+    trainer = FusedTrainer(model)
+    st = O.adam_init(sd)
+    for step in range(1, 3):
+        loss = trainer.step(c.batch).item()
+        masks = _kernel_masks(cfg, c, cfg.dropout_seed + step)
+        keep = float((masks[0] > 0).float().mean())
+        assert abs(keep - (1 - cfg.dropout)) < 0.02
+        assert set(np.unique(masks[1].numpy()).tolist()) <= {0.0, np.float32(1.0 / (1.0 - cfg.dropout)).item()}
+        ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd, c.batch, c.cfg, training=True, masks=masks,
+                                                           per_slot=False)
+        assert abs(loss - float(ref_loss)) < 2e-4 * max(1.0, abs(float(ref_loss)))
+        got = trainer.grads_as_state_dict()
+        for k, g in ref_grads.items():
+            gn = float(g.norm())
+            dn = float((got[k].cpu() - g).norm())
+            assert dn <= 2e-3 * gn + 1e-6 * np.sqrt(g.numel()), f"step {step} grad {k}: |d|={dn} |g|={gn}"
+        O.adam_step(sd, ref_grads, st, c.cfg.learning_rate)
+        new_sd = model.state_dict()
+        for k in sd:
+            if k.endswith("W_K.bias"):
+                continue        # zero-gradient tensor: Adam amplifies rounding noise (see oracle test)
+            d = (new_sd[k].cpu() - sd[k]).abs()
+            # entries whose gradient is not eps-sized must agree tightly
+            big = ref_grads[k].abs() > 1e-5
+            if big.any():
+                assert d[big].max().item() < 0.02 * c.cfg.learning_rate * step, f"step {step} param {k}"
+            assert d.max().item() < 2.1 * c.cfg.learning_rate * step, f"step {step} param {k}"
+        # keep the oracle weights in lock-step with the device weights for the next step
+        sd = {k: v.detach().cpu().clone() for k, v in new_sd.items()}
+        st.m = {k: v.clone() for k, v in st.m.items()}
+
+
+def test_golden_train_losses_with_reference_masks_unavailable_on_device():
+    """The reference's dropout masks come from ATen's RNG stream and cannot be reproduced by
+    the kernels' Philox counters (SURVEY §7 hard parts): train-mode parity is therefore pinned
+    through the oracle (test above), and the oracle is pinned to the reference with injected
+    masks (tests/test_oracle_golden.py::test_train_steps_with_reference_masks)."""
+    assert os.path.exists(os.path.join(GOLDEN_DIR, "mind.npz"))
+
+
+def test_embedding_grad_dedupe_exact_and_deterministic(built_lib):
+    from pytorch_news_recommender_b200 import ops
+    torch.manual_seed(0)
+    V, D, M = 1000, 300, 50000
+    ids = torch.randint(0, V, (M,), dtype=torch.int64)
+    ids[::7] = 3            # one very hot row
+    ids[1::11] = 0          # padding ids are dropped
+    rows = torch.randint(-8, 9, (M, D)).float()      # integers: fp32 sums are exact
+    want = torch.zeros(V, D).index_add_(0, ids, rows)
+    want[0] = 0
+    ids_d, rows_d = ids.cuda(), rows.cuda()
+    plan = torch.empty(ops.embedding_plan_bytes(M, V), dtype=torch.uint8, device="cuda")
+    ops.embedding_plan(ids_d, V, plan)
+    out = torch.full((V, D), 7.0, device="cuda")
+    ops.embedding_grad_dense(plan, rows_d, M, V, D, out)
+    assert torch.equal(out.cpu(), want)
+    uniq = int(ops.embedding_plan_unique(plan, V).item())
+    assert uniq == int((torch.bincount(ids, minlength=V)[1:] > 0).sum())
+    # idempotent / repeatable
+    out2 = torch.empty_like(out)
+    ops.embedding_plan(ids_d, V, plan)
+    ops.embedding_grad_dense(plan, rows_d, M, V, D, out2)
+    assert torch.equal(out, out2)
+
+
+def test_adam_matches_torch(built_lib):
+    from pytorch_news_recommender_b200 import ops
+    torch.manual_seed(1)
+    n = 100003 * 4
+    p = torch.randn(n, device="cuda")
+    ref_p = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([ref_p], lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        g = torch.randn(n, device="cuda") * 0.01
+        ref_p.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g, m, v, step, 1e-3)
+        assert (p - ref_p.data).abs().max().item() < 1e-6
+
+
+def test_metrics_kernel_vs_reference_fixture(built_lib):
+    from pytorch_news_recommender_b200 import ops
+    z = np.load(os.path.join(GOLDEN_DIR, "metrics.npz"))
+    off = z["offsets"]
+    out = ops.rank_metrics(torch.from_numpy(z["scores"]).cuda(), torch.from_numpy(z["labels"]).cuda(),
+                           torch.from_numpy(off).cuda(), max_len=int(np.diff(off).max())).cpu().numpy()
+    for i in range(len(off) - 1):
+        s = z["scores"][off[i]:off[i + 1]]
+        y = z["labels"][off[i]:off[i + 1]].astype(np.int64)
+        cols = slice(0, 4) if len(np.unique(s)) == len(s) else slice(0, 1)
+        np.testing.assert_allclose(out[i][cols], z["expected"][i][cols], rtol=1e-9, atol=1e-12, equal_nan=True)
+        # ties: our documented order (stable ascending, reversed) == the oracle's
+        np.testing.assert_allclose(out[i], O.impression_metrics(y, s), rtol=1e-9, atol=1e-12, equal_nan=True)
+    # padded-row variant (train_eval.py:219-227 reads rank_score[i][:len(y_true[i])])
+    n = len(off) - 1
+    stride = 300
+    padded = torch.full((n, stride), -1e9)
+    for i in range(n):
+        padded[i, :off[i + 1] - off[i]] = torch.from_numpy(z["scores"][off[i]:off[i + 1]])
+    out2 = ops.rank_metrics(padded.cuda(), torch.from_numpy(z["labels"]).cuda(), torch.from_numpy(off).cuda(),
+                            max_len=stride, row_stride=stride).cpu().numpy()
+    np.testing.assert_array_equal(np.isnan(out), np.isnan(out2))
+    np.testing.assert_allclose(np.nan_to_num(out2), np.nan_to_num(out), rtol=0, atol=0)
+
+
+def test_score_ce_and_gather(built_lib):
+    from pytorch_news_recommender_b200 import ops
+    torch.manual_seed(3)
+    B, C, D = 33, 5, 300
+    cand = torch.randn(B, C, D, device="cuda") * 0.2
+    user = torch.randn(B, D, device="cuda") * 0.2
+    mask = (torch.rand(B, C, device="cuda") > 0.2).to(torch.uint8)
+    mask[:, 0] = 1
+    logits = torch.empty(B, C, device="cuda")
+    loss_rows = torch.empty(B, device="cuda")
+    d_cand, d_user = torch.empty_like(cand), torch.empty_like(user)
+    ops.score_ce_fwd_bwd(cand, user, mask, B, logits, loss_rows, d_cand, d_user)
+    c2, u2 = cand.clone().requires_grad_(True), user.clone().requires_grad_(True)
+    ref = torch.bmm(c2, u2.unsqueeze(-1)).squeeze(-1).masked_fill(mask == 0, -1e9)
+    loss = torch.nn.functional.cross_entropy(ref, torch.zeros(B, dtype=torch.long, device="cuda"))
+    loss.backward()
+    assert torch.allclose(logits, ref, rtol=1e-5, atol=1e-5)
+    assert abs(loss_rows.mean().item() - loss.item()) < 1e-5
+    assert torch.allclose(d_cand, c2.grad, rtol=1e-4, atol=1e-7)
+    assert torch.allclose(d_user, u2.grad, rtol=1e-4, atol=1e-7)
+    # row gathers used by the cached scorer / device batch assembly
+    src = torch.randn(100, D, device="cuda")
+    idx = torch.randint(0, 101, (1000,), device="cuda")
+    got = ops.gather_rows(src, idx, base=1)
+    want = torch.where((idx > 0)[:, None], src[(idx - 1).clamp_min(0)], torch.zeros(1, D, device="cuda"))
+    assert torch.equal(got, want)
+    src_i = torch.randint(0, 70000, (100, 30), device="cuda")
+    assert torch.equal(ops.gather_rows(src_i, idx, base=1),
+                       torch.where((idx > 0)[:, None], src_i[(idx - 1).clamp_min(0)], torch.zeros(1, 30, dtype=torch.int64, device="cuda")))
+
+
+def test_errors_are_loud(built_lib):
+    from pytorch_news_recommender_b200 import ops
+    from pytorch_news_recommender_b200._lib import NrmsError
+    with pytest.raises(NrmsError):
+        ops.saved_bytes(ops.EncoderShape(4, 300, 300, 10, 200, 10))     # seq_len > 256
+    with pytest.raises(NrmsError):
+        ops.saved_bytes(ops.EncoderShape(4, 30, 300, 7, 200, 10))       # D % heads
+    c = Case("tiny")
+    model, cfg, _ = _model_from_case(c)
+    with pytest.raises(NrmsError):
+        model.cpu()(c.batch)                                            # no CPU fallback
+    assert not ops.validate_ids(torch.tensor([1, 5, 99999], device="cuda"), 100)
+    assert ops.validate_ids(torch.tensor([0, 5, 99], device="cuda"), 100)
+
+
+def test_full_size_properties(built_lib):
+    """BASELINE cfg2 shapes (B=64, T=30, H=50, K=4, V=70k): size-independent properties —
+    permutation equivariance over impressions, padded-slot fill, loss decreases under the
+    fused trainer, table row 0 stays zero, only touched rows move."""
+    from pytorch_news_recommender_b200 import synthetic as S
+    from pytorch_news_recommender_b200.config import Config
+    from pytorch_news_recommender_b200.engine import FusedTrainer
+    from pytorch_news_recommender_b200.model import NRMS_V0
+    cfg = Config("NRMS_V0_FULL")
+    cfg.__nrms__()
+    cfg.n_words_title, cfg.history_len, cfg.sample_size, cfg.dropout = 30, 50, 4, 0.2
+    V, B = 70000, 64
+    tmp = tempfile.mkdtemp()
+    S.save_embedding_npz(os.path.join(tmp, "emb.npz"), S.make_embedding_table(V, 300, 0))
+    cfg.data_path, cfg.word_embedding_pretrained, cfg.device = tmp + "/", "emb.npz", torch.device("cuda:0")
+    pool = S.make_news_pool(65000, 30, V, seed=0)
+    batch = S.make_train_batch(pool, B, 50, 4, seed=0)
+    torch.manual_seed(42)
+    model = NRMS_V0(cfg).to(cfg.device)
+    model.eval()
+    with torch.no_grad():
+        a = model(batch)
+        perm = torch.randperm(B)
+        b = model({k: v[perm] for k, v in batch.items()})
+    assert torch.allclose(a[perm], b, rtol=1e-5, atol=1e-5)
+    assert torch.equal(a.cpu()[batch["candidate_mask"] == 0], torch.full_like(a.cpu()[batch["candidate_mask"] == 0], -1e9))
+    model.train()
+    trainer = FusedTrainer(model, lr=1e-3)
+    table0 = model.state_dict()[O.TABLE_KEY].clone()
+    losses = [trainer.step(batch).item() for _ in range(6)]
+    assert losses[-1] < losses[0]
+    table1 = model.state_dict()[O.TABLE_KEY]
+    assert float(table1[0].abs().max()) == 0.0
+    # an impression whose only real candidate is the positive has softmax prob 1 -> exactly
+    # zero gradient (in the reference too), so only impressions with >= 2 real slots count
+    live = batch["candidate_mask"].sum(1) >= 2
+    touched = torch.zeros(V, dtype=torch.bool)
+    touched[batch["browsed_titles"][live].reshape(-1)] = True
+    touched[batch["candidate_titles"][live].reshape(-1)] = True
+    touched[0] = False
+    moved = ((table1 - table0).abs().amax(dim=1) > 0).cpu()
+    assert torch.equal(moved, touched)
