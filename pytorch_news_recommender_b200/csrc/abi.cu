@@ -10,6 +10,7 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "metrics.cuh"
 #include "pooling.cuh"
 #include "profiler.cuh"
@@ -85,6 +86,11 @@ struct Saved {
     float* ctx;  // [M, D]   (post-dropout)
     float* t;    // [M, Q]
     float* w;    // [n_seq, L]
+    // tcgen05 path: weights pre-split to bf16 hi/lo in the swizzled smem image (gemm_tc.cuh)
+    uint8_t* pk_qkv;    // B = W_qkv   [3D, D]   (forward projections)
+    uint8_t* pk_a;      // B = W_a     [Q, D]    (forward additive projection)
+    uint8_t* pk_qkv_t;  // B = W_qkv^T [D, 3D]   (data gradient)
+    uint8_t* pk_a_t;    // B = W_a^T   [D, Q]    (data gradient)
     int64_t bytes;
 };
 Saved saved_layout(void* blob, const nrms_encoder_dims& d) {
@@ -102,6 +108,16 @@ Saved saved_layout(void* blob, const nrms_encoder_dims& d) {
     s.ctx = take(M * d.d_model);
     s.t = take(M * d.d_query);
     s.w = take((int64_t)d.n_seq * d.seq_len);
+    auto take_bytes = [&](int64_t n) {
+        uint8_t* r = reinterpret_cast<uint8_t*>(p + off);
+        off += align_up(n, 1024);
+        return r;
+    };
+    const int D = d.d_model, Q = d.d_query;
+    s.pk_qkv = take_bytes(tc::packed_b_bytes(3 * D, D, tc::pick_n_tile(3 * D)));
+    s.pk_a = take_bytes(tc::packed_b_bytes(Q, D, tc::pick_n_tile(Q)));
+    s.pk_qkv_t = take_bytes(tc::packed_b_bytes(D, 3 * D, tc::pick_n_tile(D)));
+    s.pk_a_t = take_bytes(tc::packed_b_bytes(D, Q, tc::pick_n_tile(D)));
     s.bytes = off;
     return s;
 }
@@ -208,7 +224,7 @@ int pick_hpb(int L, int n_heads, bool bwd) {
 // y[M,N] = epi(x W^T + b): dispatches on gemm_mode
 int linear_fwd(const nrms_encoder_dims& d, const float* x, const int64_t* gather_rows, int M,
                int N, int K, const float* W, const float* bias, float* y, int epilogue,
-               bool drop_in, cudaStream_t s) {
+               bool drop_in, uint8_t* packed, cudaStream_t s) {
     GemmArgs g{};
     g.A = x; g.B = W; g.C = y; g.bias = bias; g.a_rows = gather_rows; g.b_rows = nullptr;
     g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N;
@@ -216,8 +232,13 @@ int linear_fwd(const nrms_encoder_dims& d, const float* x, const int64_t* gather
     g.drop = make_dropout(d.dropout_p, d.seed);
     g.drop_on = (drop_in && g.drop.enabled()) ? 1 : 0;
     g.drop_sid = kDropEmbedding;
-    if (d.gemm_mode == 1) return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode=1 (tcgen05) not built");
-    NRMS_CHECK_CUDA(launch_gemm_simt(g, true, true, 1, s, N == 3 * K ? "gemm_fwd_qkv" : "gemm_fwd_additive"));
+    const char* name = N == 3 * K ? "gemm_fwd_qkv" : "gemm_fwd_additive";
+    if (d.gemm_mode == 1) {
+        NRMS_CHECK_CUDA(tc::pack_b(W, N, K, K, 1, packed, s));
+        NRMS_CHECK_CUDA(tc::launch(g, packed, 3, s, name));
+        return NRMS_OK;
+    }
+    NRMS_CHECK_CUDA(launch_gemm_simt(g, true, true, 1, s, name));
     return NRMS_OK;
 }
 
@@ -236,7 +257,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     // 1. Q|K|V projections (nrms_v0.py:53-58) with the embedding gather + dropout fused into
     //    the A-operand load (nrms_v0.py:166)
     int rc = linear_fwd(d, x_or_table, news ? ids : nullptr, M, 3 * D, D, pv.Wqkv, pv.bqkv,
-                        sv.qkv, 0, news, s);
+                        sv.qkv, 0, news, sv.pk_qkv, s);
     if (rc) return rc;
     // 2. per-head attention (+ context dropout for the news encoder)
     {
@@ -255,7 +276,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     // 3. additive-attention projection t = tanh(ctx W_a^T + b_a) (nrms_v0.py:108)
-    rc = linear_fwd(d, sv.ctx, nullptr, M, Q, D, pv.Wa, pv.ba, sv.t, 1, false, s);
+    rc = linear_fwd(d, sv.ctx, nullptr, M, Q, D, pv.Wa, pv.ba, sv.t, 1, false, sv.pk_a, s);
     if (rc) return rc;
     // 4. softmax over the sequence + weighted sum (nrms_v0.py:110-126)
     {
@@ -305,7 +326,13 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.A = sc.d_pre; g.B = pv.Wa; g.C = sc.d_ctx;
         g.M = M; g.N = D; g.K = Q; g.lda = Q; g.ldb = D; g.ldc = D;
         g.k_chunk = Q; g.accumulate = 1;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_additive"));
+        if (d.gemm_mode == 1) {
+            // B(n = d, k = q) = W_a[q, d]
+            NRMS_CHECK_CUDA(tc::pack_b(pv.Wa, D, Q, 1, D, sv.pk_a_t, s));
+            NRMS_CHECK_CUDA(tc::launch(g, sv.pk_a_t, 3, s, "gemm_dgrad_additive"));
+        } else {
+            NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_additive"));
+        }
     }
     // 3. dW_a = d_pre^T ctx   (reduction over the M token rows, split + deterministic reduce)
     {
@@ -363,7 +390,13 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.k_chunk = 3 * D;
         g.drop = drop; g.drop_sid = kDropEmbedding;
         g.drop_on = (news && drop.enabled()) ? 3 : 0;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_qkv"));
+        if (d.gemm_mode == 1) {
+            // B(n = d_in, k = qkv column) = W_qkv[k, n]
+            NRMS_CHECK_CUDA(tc::pack_b(pv.Wqkv, D, 3 * D, 1, D, sv.pk_qkv_t, s));
+            NRMS_CHECK_CUDA(tc::launch(g, sv.pk_qkv_t, 3, s, "gemm_dgrad_qkv"));
+        } else {
+            NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_qkv"));
+        }
     }
     return NRMS_OK;
 }

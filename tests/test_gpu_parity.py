@@ -14,7 +14,7 @@ from _golden import GOLDEN_DIR, Case, check_summary
 
 pytestmark = pytest.mark.gpu
 
-GEMM_MODES = [0]
+GEMM_MODES = [0, 1]
 
 
 def _cfg_from_case(c, dropout=None, gemm_mode=0):
