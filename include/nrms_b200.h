@@ -57,7 +57,8 @@ typedef struct nrms_encoder_dims {
     int32_t d_query;    /* config.query_vector_dim (200) */
     int32_t vocab;      /* rows of the word-embedding table (news encoder); 0 for user */
     float dropout_p;    /* config.dropout when training, 0 in eval (nrms_v0.py:137,171-173) */
-    int32_t gemm_mode;  /* 0 = fp32 SIMT, 1 = tcgen05 split-bf16 (bf16x3, fp32-grade) */
+    int32_t gemm_mode;  /* 0 = fp32 CUDA-core GEMMs, 1 = tcgen05 split-bf16 (bf16x3, fp32-grade);
+                           mode 1 needs d_model <= 320, d_query <= 208 and an even head dim */
     uint64_t seed;      /* Philox key of this step's dropout masks */
 } nrms_encoder_dims;
 
@@ -166,11 +167,22 @@ int nrms_gather_rows_f32(const float* src, int64_t n_src, int32_t D, const int64
 int nrms_gather_rows_i64(const int64_t* src, int64_t n_src, int32_t D, const int64_t* idx,
                          int64_t n_idx, int64_t base, int64_t* out, nrms_stream_t stream);
 
-/* Test hook: writes the dropout keep-mask scaled by 1/(1-p) (0 or 1/(1-p)) that the
- * encoder kernels apply to stream `stream_id` (1 = embedding dropout nrms_v0.py:137,
- * 2 = context dropout nrms_v0.py:171-173) for n flat elements. */
-int nrms_dropout_mask(uint64_t seed, uint32_t stream_id, float p, int64_t n, float* out,
-                      nrms_stream_t stream);
+/* Test hook: writes the dropout multiplier (0 or 1/(1-p)) that the encoder kernels apply to
+ * element (r, c) of a [n_rows, n_cols] activation in stream `stream_id` (1 = embedding dropout
+ * nrms_v0.py:137 over the gathered rows [n_titles*T, D], 2 = context dropout nrms_v0.py:171-173
+ * over the attention output [n_titles*T, D]).  out is [n_rows, n_cols] fp32. */
+int nrms_dropout_mask(uint64_t seed, uint32_t stream_id, float p, int64_t n_rows, int32_t n_cols,
+                      float* out, nrms_stream_t stream);
+
+/* Self-test of the tcgen05 GEMM layer (gemm_img.cuh): packs fp32 row-major operands into
+ * split-bf16 images and runs one of the three operand orientations the path uses:
+ *   variant 0: C[M,N] = A[M,K] * B[N,K]^T   forward projection        (K-major  x K-major)
+ *   variant 1: C[M,N] = A[M,K] * B[K,N]     data gradient, N <= 320   (K-major  x MN-major)
+ *   variant 2: C[M,N] = A[K,M]^T * B[K,N]   weight gradient, N <= 320 (MN-major x MN-major, split-K)
+ * work: caller-owned scratch of nrms_gemm_selftest_bytes() bytes.  N % 4 == 0. */
+int64_t nrms_gemm_selftest_bytes(int32_t variant, int32_t M, int32_t N, int32_t K);
+int nrms_gemm_selftest(int32_t variant, const float* A, const float* B, float* C, int32_t M,
+                       int32_t N, int32_t K, void* work, int64_t work_bytes, nrms_stream_t stream);
 
 /* out-of-range id check: *d_flag |= 1 if any id < 0 or >= vocab */
 int nrms_validate_ids(const int64_t* ids, int64_t n, int64_t vocab, int32_t* d_flag,

@@ -66,7 +66,9 @@ SIGNATURES = {
     "nrms_rank_metrics_padded": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _P, _P]),
     "nrms_gather_rows_f32": (C.c_int, [_P, _I64, _I32, _P, _I64, _I64, _P, _P]),
     "nrms_gather_rows_i64": (C.c_int, [_P, _I64, _I32, _P, _I64, _I64, _P, _P]),
-    "nrms_dropout_mask": (C.c_int, [C.c_uint64, C.c_uint32, _F, _I64, _P, _P]),
+    "nrms_dropout_mask": (C.c_int, [C.c_uint64, C.c_uint32, _F, _I64, _I32, _P, _P]),
+    "nrms_gemm_selftest_bytes": (_I64, [_I32, _I32, _I32, _I32]),
+    "nrms_gemm_selftest": (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "nrms_validate_ids": (C.c_int, [_P, _I64, _I64, _P, _P]),
 }
 

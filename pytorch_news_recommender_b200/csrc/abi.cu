@@ -10,7 +10,8 @@
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
-#include "gemm_tc.cuh"
+#include "gather.cuh"
+#include "gemm_img.cuh"
 #include "metrics.cuh"
 #include "pooling.cuh"
 #include "profiler.cuh"
@@ -80,55 +81,76 @@ V param_view(P base, int D, int Q) {
 }
 
 // ---- saved / scratch blob layouts -------------------------------------------------------
+// gemm_mode 1 keeps every GEMM operand as a split-bf16 image (gemm_img.cuh); gemm_mode 0 keeps
+// them as fp32 matrices for the CUDA-core GEMM.  Image sizes are fixed by the tile shapes of
+// the kernels (rows / chunks an operand tile may touch), not only by the matrix dims.
+constexpr int kXChunks = 5;      // D <= 320: K-major k-chunks and the 5 blocks of an N=320 tile
+constexpr int kPreChunks = 4;    // Q <= 208
+constexpr int kQkvChunks = 16;   // 3D <= 960 (+ the second block of the last 128-row tile)
+constexpr int kWqkvRows = 1024, kWaRows = 256;
+
+inline int mask_bytes_for(int D) { return (int)align_up(ceil_div(D, 8), 4); }
+
 struct Saved {
-    float* qkv;  // [M, 3D]
-    float* lse;  // [M, h]
-    float* ctx;  // [M, D]   (post-dropout)
-    float* t;    // [M, Q]
-    float* w;    // [n_seq, L]
-    // tcgen05 path: weights pre-split to bf16 hi/lo in the swizzled smem image (gemm_tc.cuh)
-    uint8_t* pk_qkv;    // B = W_qkv   [3D, D]   (forward projections)
-    uint8_t* pk_a;      // B = W_a     [Q, D]    (forward additive projection)
-    uint8_t* pk_qkv_t;  // B = W_qkv^T [D, 3D]   (data gradient)
-    uint8_t* pk_a_t;    // B = W_a^T   [D, Q]    (data gradient)
+    float* qkv;      // [M, 3D]
+    float* lse;      // [M, h]
+    float* ctx;      // [M, D]   (post-dropout)
+    float* t;        // [M, Q]
+    float* score;    // [M]      a_l = t_l . q
+    float* w;        // [n_seq, L]
+    uint8_t* xmask;  // [M, mask_bytes] embedding-dropout keep bits
+    uint8_t* cmask;  // [M, mask_bytes] context-dropout keep bits
+    float* x_f32;    // mode 0, news encoder: gathered + dropped rows [M, D]
+    ig::Img x_img, ctx_img, wqkv_img, wa_img;   // mode 1
     int64_t bytes;
 };
 Saved saved_layout(void* blob, const nrms_encoder_dims& d) {
     const int64_t M = (int64_t)d.n_seq * d.seq_len;
+    const int D = d.d_model, Q = d.d_query;
     char* p = reinterpret_cast<char*>(blob);
     int64_t off = 0;
-    auto take = [&](int64_t nfloat) {
-        float* r = reinterpret_cast<float*>(p + off);
-        off += align_up(nfloat * (int64_t)sizeof(float), 256);
-        return r;
-    };
-    Saved s;
-    s.qkv = take(M * 3 * d.d_model);
-    s.lse = take(M * d.n_heads);
-    s.ctx = take(M * d.d_model);
-    s.t = take(M * d.d_query);
-    s.w = take((int64_t)d.n_seq * d.seq_len);
     auto take_bytes = [&](int64_t n) {
-        uint8_t* r = reinterpret_cast<uint8_t*>(p + off);
+        char* r = p + off;
         off += align_up(n, 1024);
         return r;
     };
-    const int D = d.d_model, Q = d.d_query;
-    s.pk_qkv = take_bytes(tc::packed_b_bytes(3 * D, D, tc::pick_n_tile(3 * D)));
-    s.pk_a = take_bytes(tc::packed_b_bytes(Q, D, tc::pick_n_tile(Q)));
-    s.pk_qkv_t = take_bytes(tc::packed_b_bytes(D, 3 * D, tc::pick_n_tile(D)));
-    s.pk_a_t = take_bytes(tc::packed_b_bytes(D, Q, tc::pick_n_tile(D)));
+    auto take = [&](int64_t nfloat) { return reinterpret_cast<float*>(take_bytes(nfloat * 4)); };
+    Saved s{};
+    s.qkv = take(M * 3 * D);
+    s.lse = take(M * d.n_heads);
+    s.ctx = take(M * D);
+    s.t = take(M * Q);
+    s.score = take(M);
+    s.w = take(M);
+    const int mb = mask_bytes_for(D);
+    s.xmask = reinterpret_cast<uint8_t*>(take_bytes(M * mb));
+    s.cmask = reinterpret_cast<uint8_t*>(take_bytes(M * mb));
+    if (d.gemm_mode == 1) {
+        s.x_img = ig::img_view(take_bytes(ig::img_bytes(M, kXChunks)), M, kXChunks);
+        s.ctx_img = ig::img_view(take_bytes(ig::img_bytes(M, kXChunks)), M, kXChunks);
+        s.wqkv_img = ig::img_view(take_bytes(ig::img_bytes(kWqkvRows, kXChunks)), kWqkvRows, kXChunks);
+        s.wa_img = ig::img_view(take_bytes(ig::img_bytes(kWaRows, kXChunks)), kWaRows, kXChunks);
+    } else {
+        s.x_f32 = take(M * D);
+    }
     s.bytes = off;
     return s;
 }
 
-constexpr int kMaxSplits = 32;
 constexpr int kReduceSlices = 128;
 
-int wgrad_splits(int out_rows, int out_cols, long long k_rows) {
+// k-splits of a weight-gradient GEMM: fill the SMs, never more splits than 64-row k chunks
+int wgrad_splits_tc(int m_tiles, int k_chunks) {
+    int s = kNumSMs / m_tiles;
+    if (s > k_chunks) s = k_chunks;
+    if (s < 1) s = 1;
+    // the kernel gives every split ceil(k_chunks/s) chunks: drop the splits that would be empty
+    return ceil_div(k_chunks, ceil_div(k_chunks, s));
+}
+int wgrad_splits_simt(int out_rows, int out_cols, long long k_rows) {
     const int tiles = ceil_div(out_rows, GBM) * ceil_div(out_cols, GBN);
     int s = ceil_div(4 * kNumSMs, tiles);
-    if (s > kMaxSplits) s = kMaxSplits;
+    if (s > 32) s = 32;
     const long long max_by_k = ceil_div64(k_rows, 4 * GBK);
     if (s > max_by_k) s = (int)max_by_k;
     return s < 1 ? 1 : s;
@@ -136,11 +158,12 @@ int wgrad_splits(int out_rows, int out_cols, long long k_rows) {
 
 struct Scratch {
     float* d_ctx;      // [M, D]
-    float* d_pre;      // [M, Q]
-    float* d_qkv;      // [M, 3D]
+    float* d_pre;      // mode 0: [M, Q]
+    float* d_qkv;      // mode 0: [M, 3D]
+    ig::Img d_pre_img, d_qkv_img;   // mode 1
     float* part_q;     // [n_seq, 2Q]
     float* part_b;     // [n_seq, 3D]
-    float* wpart;      // [kMaxSplits, 3D*D]
+    float* wpart;      // [splits, out*in] weight-gradient partials
     float* red_tmp;    // [kReduceSlices, max(3D, 2Q)]
     int64_t bytes;
 };
@@ -149,18 +172,30 @@ Scratch scratch_layout(void* blob, const nrms_encoder_dims& d) {
     const int64_t D = d.d_model, Q = d.d_query;
     char* p = reinterpret_cast<char*>(blob);
     int64_t off = 0;
-    auto take = [&](int64_t nfloat) {
-        float* r = reinterpret_cast<float*>(p + off);
-        off += align_up(nfloat * (int64_t)sizeof(float), 256);
+    auto take_bytes = [&](int64_t n) {
+        char* r = p + off;
+        off += align_up(n, 1024);
         return r;
     };
-    Scratch s;
+    auto take = [&](int64_t nfloat) { return reinterpret_cast<float*>(take_bytes(nfloat * 4)); };
+    Scratch s{};
     s.d_ctx = take(M * D);
-    s.d_pre = take(M * Q);
-    s.d_qkv = take(M * 3 * D);
+    int64_t wpart;
+    if (d.gemm_mode == 1) {
+        s.d_pre_img = ig::img_view(take_bytes(ig::img_bytes(M, kPreChunks)), M, kPreChunks);
+        s.d_qkv_img = ig::img_view(take_bytes(ig::img_bytes(M, kQkvChunks)), M, kQkvChunks);
+        const int kch = ig::img_rows_pad(M) / 64;
+        const int64_t a = (int64_t)wgrad_splits_tc(ceil_div((int)(3 * D), 128), kch) * 3 * D * D;
+        const int64_t b = (int64_t)wgrad_splits_tc(ceil_div((int)Q, 128), kch) * Q * D;
+        wpart = a > b ? a : b;
+    } else {
+        s.d_pre = take(M * Q);
+        s.d_qkv = take(M * 3 * D);
+        wpart = 32 * 3 * D * (D > Q ? D : Q);
+    }
     s.part_q = take((int64_t)d.n_seq * 2 * Q);
     s.part_b = take((int64_t)d.n_seq * 3 * D);
-    s.wpart = take((int64_t)kMaxSplits * 3 * D * (D > Q ? D : Q));
+    s.wpart = take(wpart);
     s.red_tmp = take((int64_t)kReduceSlices * (3 * D > 2 * Q ? 3 * D : 2 * Q));
     s.bytes = off;
     return s;
@@ -188,6 +223,15 @@ int check_dims(const nrms_encoder_dims* d, bool news) {
         return fail(NRMS_ERR_BAD_SHAPE, "n_seq*seq_len too large");
     if (d->gemm_mode != 0 && d->gemm_mode != 1)
         return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode=%d unknown", d->gemm_mode);
+    if (d->gemm_mode == 1) {
+        // tile shapes of the tcgen05 path (gemm_img.cuh): N tiles of 240 / 208 / 320 columns
+        if (d->d_model > 320 || d->d_query > 208)
+            return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode 1 supports d_model <= 320 and d_query <= 208 "
+                        "(got %d, %d); use gemm_mode 0", d->d_model, d->d_query);
+        if ((d->d_model / d->n_heads) % 2)
+            return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode 1 needs an even head dim (got %d); use gemm_mode 0",
+                        d->d_model / d->n_heads);
+    }
     return NRMS_OK;
 }
 
@@ -210,36 +254,52 @@ int reduce_rows(const float* in, float* out, long long R, long long n, long long
     return NRMS_OK;
 }
 
-int pick_hpb(int L, int n_heads, bool bwd) {
-    const int rc = ceil_div(L, 32);
-    const int max_warps = bwd ? 8 : 16;
-    const size_t budget = 100 * 1024;
+// ---- attention launch configuration ---------------------------------------------------------
+struct AttnCfg {
+    int hpb, threads, unit;
+    size_t smem;
+};
+AttnCfg attn_fwd_cfg(int L, int n_heads) {
+    AttnCfg c;
+    c.unit = L <= 32 ? 16 : 32;                       // lanes per (head, row-block) task; 2 rows per lane
+    const int rb = ceil_div(L, 2 * c.unit);
+    const size_t budget = 110 * 1024;                 // 2 CTAs per SM (registers allow no more)
     int hpb = n_heads;
-    while (hpb > 1 && (hpb * rc > max_warps ||
-                       (bwd ? attn_bwd_smem_bytes(L, hpb) : attn_fwd_smem_bytes(L, hpb)) > budget))
-        --hpb;
-    return hpb;
+    while (hpb > 1 && (attn_fwd_smem_bytes(L, hpb) > budget || hpb * rb * c.unit > 256)) --hpb;
+    hpb = ceil_div(n_heads, ceil_div(n_heads, hpb));  // balance the head groups
+    c.hpb = hpb;
+    int threads = hpb * rb * c.unit;
+    if (threads > 256) threads = 256;
+    c.threads = (int)align_up(threads, 32);
+    c.smem = attn_fwd_smem_bytes(L, hpb);
+    return c;
+}
+AttnCfg attn_bwd_cfg(int L, int n_heads) {
+    AttnCfg c;
+    c.unit = 32;
+    const int rc = ceil_div(L, 32);
+    const size_t budget = 110 * 1024;                 // 2 CTAs per SM
+    int hpb = n_heads;
+    while (hpb > 1 && (hpb * rc > 8 || attn_bwd_smem_bytes(L, hpb) > budget)) --hpb;
+    hpb = ceil_div(n_heads, ceil_div(n_heads, hpb));  // balance the head groups
+    c.hpb = hpb;
+    c.threads = hpb * rc * 32;
+    c.smem = attn_bwd_smem_bytes(L, hpb);
+    return c;
 }
 
-// y[M,N] = epi(x W^T + b): dispatches on gemm_mode
-int linear_fwd(const nrms_encoder_dims& d, const float* x, const int64_t* gather_rows, int M,
-               int N, int K, const float* W, const float* bias, float* y, int epilogue,
-               bool drop_in, uint8_t* packed, cudaStream_t s) {
-    GemmArgs g{};
-    g.A = x; g.B = W; g.C = y; g.bias = bias; g.a_rows = gather_rows; g.b_rows = nullptr;
-    g.M = M; g.N = N; g.K = K; g.lda = K; g.ldb = K; g.ldc = N;
-    g.k_chunk = K; g.c_split_stride = 0; g.accumulate = 0; g.epilogue = epilogue;
-    g.drop = make_dropout(d.dropout_p, d.seed);
-    g.drop_on = (drop_in && g.drop.enabled()) ? 1 : 0;
-    g.drop_sid = kDropEmbedding;
-    const char* name = N == 3 * K ? "gemm_fwd_qkv" : "gemm_fwd_additive";
-    if (d.gemm_mode == 1) {
-        NRMS_CHECK_CUDA(tc::pack_b(W, N, K, K, 1, packed, s));
-        NRMS_CHECK_CUDA(tc::launch(g, packed, 3, s, name));
-        return NRMS_OK;
-    }
-    NRMS_CHECK_CUDA(launch_gemm_simt(g, true, true, 1, s, name));
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+    NRMS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     return NRMS_OK;
+}
+
+ig::IgArgs ig_args(const ig::Img& A, const ig::Img& B, float* C, int ldc, int M, int N) {
+    ig::IgArgs g{};
+    g.A = A; g.B = B; g.C = C; g.ldc = ldc; g.M = M; g.N = N;
+    g.splits = 1;
+    g.mask_scale = 1.f;
+    return g;
 }
 
 int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_or_table,
@@ -251,38 +311,95 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     (long long)sv.bytes);
     const int D = d.d_model, Q = d.d_query, L = d.seq_len, h = d.n_heads, dk = D / h;
     const int M = d.n_seq * L;
+    const bool tcm = d.gemm_mode == 1;
     const ParamView pv = param_view<ParamView>(params, D, Q);
     const Dropout drop = make_dropout(d.dropout_p, d.seed);
+    const int mb = mask_bytes_for(D);
+    int rc;
 
-    // 1. Q|K|V projections (nrms_v0.py:53-58) with the embedding gather + dropout fused into
-    //    the A-operand load (nrms_v0.py:166)
-    int rc = linear_fwd(d, x_or_table, news ? ids : nullptr, M, 3 * D, D, pv.Wqkv, pv.bqkv,
-                        sv.qkv, 0, news, sv.pk_qkv, s);
-    if (rc) return rc;
-    // 2. per-head attention (+ context dropout for the news encoder)
+    // 1. embedding gather + embedding dropout (nrms_v0.py:166) -> GEMM operand.  The user
+    //    encoder's input is already a matrix: identity gather into an image (mode 1 only).
+    const float* x_f32 = x_or_table;
+    if (news || tcm) {
+        GatherArgs g{};
+        g.table = x_or_table; g.ids = news ? ids : nullptr; g.M = M; g.vocab = news ? d.vocab : M; g.D = D;
+        g.x_f32 = tcm ? nullptr : sv.x_f32;
+        if (tcm) g.x_img = sv.x_img;
+        g.mask = sv.xmask; g.mask_bytes = mb;
+        g.drop = news ? drop : make_dropout(0.f, 0);
+        const long long rows = tcm ? sv.x_img.rows_pad : M;
+        NRMS_LAUNCH("gather", s, gather_rows_img_kernel<<<grid_for(rows * 32, 256, 16), 256, 0, s>>>(g));
+        NRMS_CHECK_CUDA(cudaGetLastError());
+        x_f32 = sv.x_f32;
+    }
+    // 2. Q|K|V projections (nrms_v0.py:53-58)
+    if (tcm) {
+        NRMS_CHECK_CUDA(ig::img_pack(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, s));
+        NRMS_CHECK_CUDA(ig::img_pack(pv.Wa, Q, D, D, sv.wa_img, s));
+        ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, sv.qkv, 3 * D, M, 3 * D);
+        g.bias = pv.bqkv;
+        g.m_tiles = sv.x_img.rows_pad / 128; g.n_tiles = ceil_div(3 * D, 240);
+        g.k_steps = ceil_div(D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+        NRMS_CHECK_CUDA((ig::ig_launch<false, false, 240, ig::EPI_BIAS>(g, s, "gemm_fwd_qkv")));
+    } else {
+        GemmArgs g{};
+        g.A = x_f32; g.B = pv.Wqkv; g.C = sv.qkv; g.bias = pv.bqkv;
+        g.M = M; g.N = 3 * D; g.K = D; g.lda = D; g.ldb = D; g.ldc = 3 * D; g.k_chunk = D;
+        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, true, 1, s, "gemm_fwd_qkv"));
+    }
+    // 3. per-head attention (+ context dropout for the news encoder)
     {
         AttnArgs a{};
-        a.qkv = sv.qkv; a.ctx = sv.ctx; a.lse = sv.lse;
-        a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
-        a.hpb = pick_hpb(L, h, false);
+        a.qkv = sv.qkv; a.ctx = sv.ctx; a.lse = sv.lse; a.cmask = sv.cmask; a.mask_bytes = mb;
+        if (tcm) a.ctx_img = sv.ctx_img;
+        a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = news ? drop : make_dropout(0.f, 0);
-        const size_t smem = attn_fwd_smem_bytes(L, a.hpb);
-        NRMS_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-        const int warps = a.hpb * ceil_div(L, 32);
-        NRMS_LAUNCH("attn_fwd", s, attn_fwd_kernel<<<dim3(d.n_seq, ceil_div(h, a.hpb)), warps * 32, smem, s>>>(a));
+        const AttnCfg c = attn_fwd_cfg(L, h);
+        a.hpb = c.hpb;
+        const bool vec2 = (dk % 2 == 0);
+        const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
+        if (a.drop.enabled() && c.hpb < h && ((c.hpb * dk) % 8))
+            ;  // groups straddling head groups are written twice with identical bits: fine
+        if (c.unit == 16) {
+            if (vec2) {
+                if ((rc = set_smem(attn_fwd_kernel<16, true>, c.smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<16, true><<<grid, c.threads, c.smem, s>>>(a)));
+            } else {
+                if ((rc = set_smem(attn_fwd_kernel<16, false>, c.smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<16, false><<<grid, c.threads, c.smem, s>>>(a)));
+            }
+        } else {
+            if (vec2) {
+                if ((rc = set_smem(attn_fwd_kernel<32, true>, c.smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<32, true><<<grid, c.threads, c.smem, s>>>(a)));
+            } else {
+                if ((rc = set_smem(attn_fwd_kernel<32, false>, c.smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<32, false><<<grid, c.threads, c.smem, s>>>(a)));
+            }
+        }
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
-    // 3. additive-attention projection t = tanh(ctx W_a^T + b_a) (nrms_v0.py:108)
-    rc = linear_fwd(d, sv.ctx, nullptr, M, Q, D, pv.Wa, pv.ba, sv.t, 1, false, sv.pk_a, s);
-    if (rc) return rc;
-    // 4. softmax over the sequence + weighted sum (nrms_v0.py:110-126)
+    // 4. additive-attention projection t = tanh(ctx W_a^T + b_a) (nrms_v0.py:108); the tcgen05
+    //    epilogue also reduces a_l = t_l . q (nrms_v0.py:110)
+    if (tcm) {
+        ig::IgArgs g = ig_args(sv.ctx_img, sv.wa_img, sv.t, Q, M, Q);
+        g.bias = pv.ba; g.qv = pv.qv; g.dot_out = sv.score;
+        g.m_tiles = sv.ctx_img.rows_pad / 128; g.n_tiles = 1;
+        g.k_steps = ceil_div(D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+        NRMS_CHECK_CUDA((ig::ig_launch<false, false, 208, ig::EPI_TANH_DOT>(g, s, "gemm_fwd_additive")));
+    } else {
+        GemmArgs g{};
+        g.A = sv.ctx; g.B = pv.Wa; g.C = sv.t; g.bias = pv.ba;
+        g.M = M; g.N = Q; g.K = D; g.lda = D; g.ldb = D; g.ldc = Q; g.k_chunk = D; g.epilogue = 1;
+        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, true, 1, s, "gemm_fwd_additive"));
+    }
+    // 5. softmax over the sequence + weighted sum (nrms_v0.py:110-126)
     {
         PoolArgs p{};
         p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.out = out;
-        p.L = L; p.D = D; p.Q = Q;
+        p.score = tcm ? sv.score : nullptr;
+        p.M = M; p.L = L; p.D = D; p.Q = Q;
         NRMS_LAUNCH("pool_fwd", s, pool_fwd_kernel<<<d.n_seq, 256, L * sizeof(float), s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
@@ -293,6 +410,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 const float* params, const float* d_out, const void* saved_blob,
                 int64_t saved_bytes, void* scratch_blob, int64_t scratch_bytes, float* d_params,
                 float* d_x, bool news, cudaStream_t s) {
+    (void)ids;
     const Saved sv = saved_layout(const_cast<void*>(saved_blob), d);
     if (saved_bytes < sv.bytes)
         return fail(NRMS_ERR_WORKSPACE, "saved blob %lld < %lld bytes", (long long)saved_bytes,
@@ -303,98 +421,125 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     (long long)sc.bytes);
     const int D = d.d_model, Q = d.d_query, L = d.seq_len, h = d.n_heads, dk = D / h;
     const int M = d.n_seq * L;
+    const bool tcm = d.gemm_mode == 1;
     const ParamView pv = param_view<ParamView>(params, D, Q);
     const GradView gv = param_view<GradView>(d_params, D, Q);
-    const Dropout drop = make_dropout(d.dropout_p, d.seed);
+    const Dropout drop = make_dropout(news ? d.dropout_p : 0.f, d.seed);
+    const int mb = mask_bytes_for(D);
+    const float* x_f32 = news ? sv.x_f32 : x_or_table;   // mode 0 operand of dW_qkv
     int rc;
 
     // 1. pooling backward: d_ctx (pool path), d_pre, partials of d_b_a and d_query
     {
         PoolArgs p{};
         p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.d_out = d_out;
-        p.d_ctx = sc.d_ctx; p.d_pre = sc.d_pre; p.d_part = sc.part_q;
-        p.L = L; p.D = D; p.Q = Q;
+        p.d_ctx = sc.d_ctx; p.d_part = sc.part_q;
+        if (tcm) p.d_pre_img = sc.d_pre_img; else p.d_pre = sc.d_pre;
+        p.M = M; p.L = L; p.D = D; p.Q = Q;
         NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     // [d_b_a | d_query] are adjacent in the flat block, as in part_q
     rc = reduce_rows(sc.part_q, gv.ba, d.n_seq, 2 * Q, 2 * Q, 1.f, sc.red_tmp, s);
     if (rc) return rc;
-    // 2. d_ctx += d_pre W_a
-    {
+    const int tok_tiles = ig::img_rows_pad(M) / 128;
+    // 2. d_ctx += d_pre W_a        3. dW_a = d_pre^T ctx (split over the token rows)
+    if (tcm) {
+        ig::IgArgs g = ig_args(sc.d_pre_img, sv.wa_img, sc.d_ctx, D, M, D);
+        g.m_tiles = tok_tiles; g.n_tiles = 1;
+        g.k_steps = ceil_div(Q, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+        NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_ACCUM>(g, s, "gemm_dgrad_additive")));
+
+        ig::IgArgs w = ig_args(sc.d_pre_img, sv.ctx_img, sc.wpart, D, Q, D);
+        w.m_tiles = ceil_div(Q, 128); w.n_tiles = 1;
+        w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
+        w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
+        w.c_split_stride = (long long)Q * D;
+        NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_additive")));
+        rc = reduce_rows(sc.wpart, gv.Wa, w.splits, (long long)Q * D, (long long)Q * D, 1.f, nullptr, s);
+        if (rc) return rc;
+    } else {
         GemmArgs g{};
         g.A = sc.d_pre; g.B = pv.Wa; g.C = sc.d_ctx;
         g.M = M; g.N = D; g.K = Q; g.lda = Q; g.ldb = D; g.ldc = D;
         g.k_chunk = Q; g.accumulate = 1;
-        if (d.gemm_mode == 1) {
-            // B(n = d, k = q) = W_a[q, d]
-            NRMS_CHECK_CUDA(tc::pack_b(pv.Wa, D, Q, 1, D, sv.pk_a_t, s));
-            NRMS_CHECK_CUDA(tc::launch(g, sv.pk_a_t, 3, s, "gemm_dgrad_additive"));
-        } else {
-            NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_additive"));
-        }
-    }
-    // 3. dW_a = d_pre^T ctx   (reduction over the M token rows, split + deterministic reduce)
-    {
-        const int splits = wgrad_splits(Q, D, M);
-        GemmArgs g{};
-        g.A = sc.d_pre; g.B = sv.ctx; g.C = sc.wpart;
-        g.M = Q; g.N = D; g.K = M; g.lda = Q; g.ldb = D; g.ldc = D;
-        g.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
-        g.c_split_stride = (long long)Q * D;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, false, false, ceil_div(M, g.k_chunk), s, "gemm_wgrad_additive"));
-        rc = reduce_rows(sc.wpart, gv.Wa, ceil_div(M, g.k_chunk), (long long)Q * D,
+        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_additive"));
+
+        const int splits = wgrad_splits_simt(Q, D, M);
+        GemmArgs w{};
+        w.A = sc.d_pre; w.B = sv.ctx; w.C = sc.wpart;
+        w.M = Q; w.N = D; w.K = M; w.lda = Q; w.ldb = D; w.ldc = D;
+        w.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
+        w.c_split_stride = (long long)Q * D;
+        NRMS_CHECK_CUDA(launch_gemm_simt(w, false, false, ceil_div(M, w.k_chunk), s, "gemm_wgrad_additive"));
+        rc = reduce_rows(sc.wpart, gv.Wa, ceil_div(M, w.k_chunk), (long long)Q * D,
                          (long long)Q * D, 1.f, nullptr, s);
         if (rc) return rc;
     }
     // 4. attention backward -> d_qkv and bias partials
     {
         AttnArgs a{};
-        a.qkv = sv.qkv; a.ctx = sv.ctx; a.lse = sv.lse; a.d_ctx = sc.d_ctx; a.d_qkv = sc.d_qkv;
+        a.qkv = sv.qkv; a.ctx = sv.ctx; a.lse = sv.lse; a.d_ctx = sc.d_ctx;
+        a.cmask = sv.cmask; a.mask_bytes = mb;
+        if (tcm) a.d_qkv_img = sc.d_qkv_img; else a.d_qkv = sc.d_qkv;
         a.d_bias_part = sc.part_b;
-        a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
-        a.hpb = pick_hpb(L, h, true);
+        a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
         a.scale = 1.f / sqrtf((float)dk);
-        a.drop = news ? drop : make_dropout(0.f, 0);
-        const size_t smem = attn_bwd_smem_bytes(L, a.hpb);
-        NRMS_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-        const int warps = a.hpb * ceil_div(L, 32);
-        NRMS_LAUNCH("attn_bwd", s, attn_bwd_kernel<<<dim3(d.n_seq, ceil_div(h, a.hpb)), warps * 32, smem, s>>>(a));
+        a.drop = drop;
+        const AttnCfg c = attn_bwd_cfg(L, h);
+        a.hpb = c.hpb;
+        const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
+        if (dk % 2 == 0) {
+            if ((rc = set_smem(attn_bwd_kernel<true>, c.smem))) return rc;
+            NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<true><<<grid, c.threads, c.smem, s>>>(a)));
+        } else {
+            if ((rc = set_smem(attn_bwd_kernel<false>, c.smem))) return rc;
+            NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<false><<<grid, c.threads, c.smem, s>>>(a)));
+        }
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     rc = reduce_rows(sc.part_b, gv.bqkv, d.n_seq, 3 * D, 3 * D, 1.f, sc.red_tmp, s);
     if (rc) return rc;
-    // 5. dW_qkv = d_qkv^T x   (x = gathered + dropped embedding rows for the news encoder)
-    {
-        const int splits = wgrad_splits(3 * D, D, M);
-        GemmArgs g{};
-        g.A = sc.d_qkv; g.B = x_or_table; g.C = sc.wpart;
-        g.b_rows = news ? ids : nullptr;
-        g.M = 3 * D; g.N = D; g.K = M; g.lda = 3 * D; g.ldb = D; g.ldc = D;
-        g.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
-        g.c_split_stride = 3ll * D * D;
-        g.drop = drop; g.drop_sid = kDropEmbedding;
-        g.drop_on = (news && drop.enabled()) ? 2 : 0;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, false, false, ceil_div(M, g.k_chunk), s, "gemm_wgrad_qkv"));
-        rc = reduce_rows(sc.wpart, gv.Wqkv, ceil_div(M, g.k_chunk), 3ll * D * D, 3ll * D * D, 1.f,
+    // 5. dW_qkv = d_qkv^T x        6. d_x = d_qkv W_qkv (x the embedding dropout mask)
+    if (tcm) {
+        ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D, 3 * D, D);
+        w.m_tiles = ceil_div(3 * D, 128); w.n_tiles = 1;
+        w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
+        w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
+        w.c_split_stride = 3ll * D * D;
+        NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_qkv")));
+        rc = reduce_rows(sc.wpart, gv.Wqkv, w.splits, 3ll * D * D, 3ll * D * D, 1.f, nullptr, s);
+        if (rc) return rc;
+        if (d_x) {
+            ig::IgArgs g = ig_args(sc.d_qkv_img, sv.wqkv_img, d_x, D, M, D);
+            g.m_tiles = tok_tiles; g.n_tiles = 1;
+            g.k_steps = ceil_div(3 * D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+            if (drop.enabled()) {
+                g.mask_bits = reinterpret_cast<const uint32_t*>(sv.xmask);
+                g.mask_words = mb / 4;
+                g.mask_scale = drop.scale;
+            }
+            NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_MASK>(g, s, "gemm_dgrad_qkv")));
+        }
+    } else {
+        const int splits = wgrad_splits_simt(3 * D, D, M);
+        GemmArgs w{};
+        w.A = sc.d_qkv; w.B = x_f32; w.C = sc.wpart;
+        w.M = 3 * D; w.N = D; w.K = M; w.lda = 3 * D; w.ldb = D; w.ldc = D;
+        w.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
+        w.c_split_stride = 3ll * D * D;
+        NRMS_CHECK_CUDA(launch_gemm_simt(w, false, false, ceil_div(M, w.k_chunk), s, "gemm_wgrad_qkv"));
+        rc = reduce_rows(sc.wpart, gv.Wqkv, ceil_div(M, w.k_chunk), 3ll * D * D, 3ll * D * D, 1.f,
                          nullptr, s);
         if (rc) return rc;
-    }
-    // 6. d_x = d_qkv W_qkv (x the embedding dropout mask for the news encoder)
-    if (d_x) {
-        GemmArgs g{};
-        g.A = sc.d_qkv; g.B = pv.Wqkv; g.C = d_x;
-        g.M = M; g.N = D; g.K = 3 * D; g.lda = 3 * D; g.ldb = D; g.ldc = D;
-        g.k_chunk = 3 * D;
-        g.drop = drop; g.drop_sid = kDropEmbedding;
-        g.drop_on = (news && drop.enabled()) ? 3 : 0;
-        if (d.gemm_mode == 1) {
-            // B(n = d_in, k = qkv column) = W_qkv[k, n]
-            NRMS_CHECK_CUDA(tc::pack_b(pv.Wqkv, D, 3 * D, 1, D, sv.pk_qkv_t, s));
-            NRMS_CHECK_CUDA(tc::launch(g, sv.pk_qkv_t, 3, s, "gemm_dgrad_qkv"));
-        } else {
+        if (d_x) {
+            GemmArgs g{};
+            g.A = sc.d_qkv; g.B = pv.Wqkv; g.C = d_x;
+            g.M = M; g.N = D; g.K = 3 * D; g.lda = 3 * D; g.ldb = D; g.ldc = D;
+            g.k_chunk = 3 * D;
+            if (drop.enabled()) {
+                g.mask = sv.xmask; g.mask_bytes = mb; g.mask_scale = drop.scale;
+            }
             NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_qkv"));
         }
     }
@@ -648,13 +793,97 @@ int nrms_gather_rows_i64(const int64_t* src, int64_t n_src, int32_t D, const int
     return NRMS_OK;
 }
 
-int nrms_dropout_mask(uint64_t seed, uint32_t stream_id, float p, int64_t n, float* out,
-                      nrms_stream_t stream) {
-    if (n < 1 || p < 0.f || p >= 1.f) return fail(NRMS_ERR_BAD_SHAPE, "n=%lld p=%f", (long long)n, (double)p);
+int nrms_dropout_mask(uint64_t seed, uint32_t stream_id, float p, int64_t n_rows, int32_t n_cols,
+                      float* out, nrms_stream_t stream) {
+    if (n_rows < 1 || n_cols < 1 || p < 0.f || p >= 1.f)
+        return fail(NRMS_ERR_BAD_SHAPE, "n_rows=%lld n_cols=%d p=%f", (long long)n_rows, n_cols, (double)p);
     if (!out) return fail(NRMS_ERR_NULL, "out is NULL");
-    NRMS_LAUNCH("dropout_mask", (cudaStream_t)stream, dropout_mask_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(make_dropout(p, seed),
-                                                                           stream_id, n, out));
+    NRMS_LAUNCH("dropout_mask", (cudaStream_t)stream,
+                dropout_mask_kernel<<<grid_for(n_rows * ceil_div(n_cols, 8), 256), 256, 0, (cudaStream_t)stream>>>(
+                    make_dropout(p, seed), stream_id, n_rows, n_cols, out));
     NRMS_CHECK_CUDA(cudaGetLastError());
+    return NRMS_OK;
+}
+
+// ---- self-test of the tcgen05 GEMM layer (tests/test_gpu_gemm.py) ------------------------------
+namespace {
+struct SelfTestLayout {
+    ig::Img a, b;
+    float* bias;
+    float* part;
+    int splits, a_rows, a_chunks, b_rows, b_chunks;
+    int64_t bytes;
+};
+SelfTestLayout selftest_layout(void* blob, int variant, int M, int N, int K) {
+    SelfTestLayout L{};
+    char* p = reinterpret_cast<char*>(blob);
+    int64_t off = 0;
+    auto take = [&](int64_t n) {
+        char* r = p + off;
+        off += align_up(n, 1024);
+        return r;
+    };
+    if (variant == 0) {
+        L.a_rows = M; L.a_chunks = ceil_div(K, 64);
+        L.b_rows = ceil_div(N, 240) * 240; L.b_chunks = L.a_chunks;
+    } else if (variant == 1) {
+        L.a_rows = M; L.a_chunks = ceil_div(K, 64);
+        L.b_rows = K; L.b_chunks = 5;
+    } else {
+        L.a_rows = K; L.a_chunks = 2 * ceil_div(M, 128);
+        L.b_rows = K; L.b_chunks = 5;
+    }
+    L.a = ig::img_view(take(ig::img_bytes(L.a_rows, L.a_chunks)), L.a_rows, L.a_chunks);
+    L.b = ig::img_view(take(ig::img_bytes(L.b_rows, L.b_chunks)), L.b_rows, L.b_chunks);
+    L.bias = reinterpret_cast<float*>(take((int64_t)N * 4));
+    L.splits = variant == 2 ? wgrad_splits_tc(ceil_div(M, 128), L.a.rows_pad / 64) : 1;
+    L.part = reinterpret_cast<float*>(take(variant == 2 ? (int64_t)L.splits * M * N * 4 : 0));
+    L.bytes = off;
+    return L;
+}
+}  // namespace
+
+int64_t nrms_gemm_selftest_bytes(int32_t variant, int32_t M, int32_t N, int32_t K) {
+    if (variant < 0 || variant > 2 || M < 1 || N < 1 || K < 1) return -1;
+    return selftest_layout(nullptr, variant, M, N, K).bytes;
+}
+int nrms_gemm_selftest(int32_t variant, const float* A, const float* B, float* C, int32_t M,
+                       int32_t N, int32_t K, void* work, int64_t work_bytes, nrms_stream_t stream) {
+    if (variant < 0 || variant > 2 || M < 1 || N < 1 || K < 1 || N % 4)
+        return fail(NRMS_ERR_BAD_SHAPE, "variant=%d M=%d N=%d K=%d", variant, M, N, K);
+    if (variant != 0 && N > 320) return fail(NRMS_ERR_BAD_SHAPE, "N=%d > 320 for variant %d", N, variant);
+    NRMS_REQUIRE_PTR(A); NRMS_REQUIRE_PTR(B); NRMS_REQUIRE_PTR(C); NRMS_REQUIRE_PTR(work);
+    const SelfTestLayout L = selftest_layout(work, variant, M, N, K);
+    if (work_bytes < L.bytes) return fail(NRMS_ERR_WORKSPACE, "work blob %lld < %lld", (long long)work_bytes, (long long)L.bytes);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (variant == 0) {
+        NRMS_CHECK_CUDA(ig::img_pack(A, M, K, K, L.a, s));
+        NRMS_CHECK_CUDA(ig::img_pack(B, N, K, K, L.b, s));
+        NRMS_CHECK_CUDA(cudaMemsetAsync(L.bias, 0, (size_t)N * 4, s));
+        ig::IgArgs g = ig_args(L.a, L.b, C, N, M, N);
+        g.bias = L.bias;
+        g.m_tiles = L.a.rows_pad / 128; g.n_tiles = ceil_div(N, 240);
+        g.k_steps = ceil_div(K, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+        NRMS_CHECK_CUDA((ig::ig_launch<false, false, 240, ig::EPI_BIAS>(g, s, "selftest_nt")));
+    } else if (variant == 1) {
+        NRMS_CHECK_CUDA(ig::img_pack(A, M, K, K, L.a, s));
+        NRMS_CHECK_CUDA(ig::img_pack(B, K, N, N, L.b, s));
+        ig::IgArgs g = ig_args(L.a, L.b, C, N, M, N);
+        g.m_tiles = L.a.rows_pad / 128; g.n_tiles = 1;
+        g.k_steps = ceil_div(K, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+        NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_MASK>(g, s, "selftest_nn")));
+    } else {
+        NRMS_CHECK_CUDA(ig::img_pack(A, K, M, M, L.a, s));
+        NRMS_CHECK_CUDA(ig::img_pack(B, K, N, N, L.b, s));
+        ig::IgArgs g = ig_args(L.a, L.b, L.part, N, M, N);
+        g.m_tiles = ceil_div(M, 128); g.n_tiles = 1;
+        g.k_chunks = L.a.rows_pad / 64; g.k_steps = 4 * g.k_chunks;
+        g.splits = L.splits;
+        g.c_split_stride = (long long)M * N;
+        NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(g, s, "selftest_tn")));
+        int rc = reduce_rows(L.part, C, g.splits, (long long)M * N, (long long)M * N, 1.f, nullptr, s);
+        if (rc) return rc;
+    }
     return NRMS_OK;
 }
 

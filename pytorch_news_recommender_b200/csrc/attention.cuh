@@ -2,51 +2,77 @@
 // (title: 20-48 words, history: 50-200 news), forward and backward.
 // Reference: ScaledDotProductAttention.forward nrms_v0.py:13-23 called from
 // MultiHeadSelfAttention.forward nrms_v0.py:46-76 — softmax(Q K^T / sqrt(d_k)) V, NO mask
-// (length=None always, nrms_v0.py:170,196), NO output projection.
+// (length=None always, nrms_v0.py:170,196), NO output projection; NewsEncoder then applies
+// F.dropout to the context (nrms_v0.py:171-173).
 //
 // Layout: qkv [M, 3D] rows = tokens, [Q | K | V], head h owns columns h*dk .. h*dk+dk-1 of
-// each third (the view/transpose of nrms_v0.py:53-58).  One CTA handles one sequence and a
-// group of `hpb` heads; one warp handles (head, 32-row chunk); one LANE owns one query row
-// and streams over the keys held in shared memory (broadcast float4 reads) with an online
-// softmax, so scores never leave registers.  d_k <= 32 (30 in the reference config).
+// each third (the view/transpose of nrms_v0.py:53-58).  A CTA handles one sequence and a
+// group of `hpb` heads staged in shared memory (rows padded to 36 floats: 16-byte aligned and
+// conflict-free for lane-per-row float4 reads).  Scores never leave registers:
+//   forward : a unit of U (16|32) lanes owns a head; each lane owns TWO query rows and streams
+//             over the keys (broadcast float4 reads shared by both rows) with a softmax that
+//             is rescaled once per group of 6 keys;
+//   backward: one warp per (head, 32-row block); pass A: lane = query row (dQ), pass B:
+//             lane = key row (dK, dV); P is recomputed from the saved log-sum-exp.
+// Global traffic is coalesced 8-byte (two-column) units in both directions; the forward writes
+// the context as fp32 (pooling input), as a split-bf16 image (additive-projection operand,
+// gemm_img.cuh) and the dropout keep bits; the backward writes dQ|dK|dV as an image and/or fp32.
 #pragma once
 #include "common.cuh"
+#include "gemm_img.cuh"
 
 namespace nrms {
 
-constexpr int kDkPad = 32;   // per-head dim padded to 32 (pad lanes are zero)
-constexpr int kRowStride = 36;  // smem row stride in floats: float4-aligned and conflict-free
-                                // both for broadcast reads and lane-per-row float4 reads
+constexpr int kDkPad = 32;      // per-head dim padded to 32 (pad lanes are zero)
+constexpr int kRowStride = 36;  // smem row stride in floats
+constexpr int kKeyGroup = 6;    // keys per softmax rescale in the forward
 
 struct AttnArgs {
-    const float* qkv;   // [M, 3D]
-    float* ctx;         // fwd out / bwd in (post-dropout context) [M, D]
-    float* lse;         // [M, n_heads] log-sum-exp of the scaled scores
-    const float* d_ctx; // bwd: grad wrt post-dropout context [M, D]
-    float* d_qkv;       // bwd out [M, 3D]
-    float* d_bias_part; // bwd out [n_seq, 3D]: per-sequence column sums of d_qkv
-    int L, D, n_heads, dk, hpb;
-    float scale;        // 1/sqrt(dk)
-    Dropout drop;       // context dropout (stream kDropContext), disabled in eval / user encoder
+    const float* qkv;    // [M, 3D]
+    float* ctx;          // fwd out / bwd in: post-dropout context [M, D]
+    ig::Img ctx_img;     // fwd out (optional): image of the post-dropout context
+    uint8_t* cmask;      // fwd out / bwd in (optional): keep bits [M, mask_bytes] (dropout only)
+    float* lse;          // [M, n_heads] log-sum-exp of the scaled scores
+    const float* d_ctx;  // bwd: grad wrt post-dropout context [M, D]
+    float* d_qkv;        // bwd out (optional) fp32 [M, 3D]
+    ig::Img d_qkv_img;   // bwd out (optional) image of [M, 3D]
+    float* d_bias_part;  // bwd out [n_seq, 3D]: per-sequence column sums of d_qkv
+    long long M;         // total token rows (n_seq * L)
+    int L, D, n_heads, dk, hpb, mask_bytes;
+    float scale;         // 1/sqrt(dk)
+    Dropout drop;        // context dropout (stream kDropContext); disabled in eval / user encoder
 };
 
 __host__ __device__ inline size_t attn_fwd_smem_bytes(int L, int hpb) {
-    return (size_t)3 * hpb * L * kRowStride * sizeof(float);
+    return (size_t)3 * hpb * L * kRowStride * sizeof(float) + (size_t)L * 64;
 }
 __host__ __device__ inline size_t attn_bwd_smem_bytes(int L, int hpb) {
     return (size_t)4 * hpb * L * kRowStride * sizeof(float);
 }
 
-// cooperative load of one of the three thirds (or d_ctx) for the CTA's heads into smem
-// dst[(hh*L + l)*kRowStride + d], zero padded for d in [dk, 32).
-__device__ __forceinline__ void load_heads(float* dst, const float* src, long long row0,
-                                           int ld, int col0, int L, int dk, int hpb,
-                                           float mul) {
+// Cooperative coalesced load of `ncol` columns starting at `col0` of rows [row0, row0+L) of a
+// row-major matrix with leading dimension ld into dst[(hh*L + l)*kRowStride + d] (column c ->
+// head hh = c/dk, d = c%dk), scaled by mul, pad lanes d in [dk, 32) zeroed.  8-byte units when
+// VEC2 (dk, col0 and ld even), scalar otherwise.
+template <bool VEC2>
+__device__ __forceinline__ void load_heads(float* dst, const float* src, long long row0, int ld,
+                                           int col0, int L, int dk, int hpb, float mul) {
     const int ncol = hpb * dk;
-    for (int i = threadIdx.x; i < L * ncol; i += blockDim.x) {
-        const int l = i / ncol, c = i - l * ncol;
-        const int hh = c / dk, d = c - hh * dk;
-        dst[(hh * L + l) * kRowStride + d] = __ldg(src + (row0 + l) * ld + col0 + c) * mul;
+    if (VEC2) {
+        const int n2 = ncol >> 1;
+        for (int i = threadIdx.x; i < L * n2; i += blockDim.x) {
+            const int l = i / n2, c = (i - l * n2) << 1;
+            const int hh = c / dk, d = c - hh * dk;
+            float2 v = __ldg(reinterpret_cast<const float2*>(src + (row0 + l) * ld + col0 + c));
+            v.x *= mul; v.y *= mul;
+            *reinterpret_cast<float2*>(dst + (hh * L + l) * kRowStride + d) = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < L * ncol; i += blockDim.x) {
+            const int l = i / ncol, c = i - l * ncol;
+            const int hh = c / dk, d = c - hh * dk;
+            dst[(hh * L + l) * kRowStride + d] = __ldg(src + (row0 + l) * ld + col0 + c) * mul;
+        }
     }
     const int npad = kDkPad - dk;
     if (npad > 0) {
@@ -57,97 +83,189 @@ __device__ __forceinline__ void load_heads(float* dst, const float* src, long lo
     }
 }
 
-__global__ void __launch_bounds__(512) attn_fwd_kernel(const AttnArgs a) {
+__device__ __forceinline__ void load_row32(float* r, const float* p) {
+#pragma unroll
+    for (int c = 0; c < kDkPad / 4; ++c) {
+        const float4 v = *reinterpret_cast<const float4*>(p + 4 * c);
+        r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+    }
+}
+__device__ __forceinline__ void store_row32(float* p, const float* r, float mul) {
+#pragma unroll
+    for (int c = 0; c < kDkPad / 4; ++c)
+        *reinterpret_cast<float4*>(p + 4 * c) =
+            make_float4(r[4 * c] * mul, r[4 * c + 1] * mul, r[4 * c + 2] * mul, r[4 * c + 3] * mul);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int U, bool VEC2>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int L = a.L, D = a.D, dk = a.dk;
     const int seq = blockIdx.x;
     const int h0 = blockIdx.y * a.hpb;
     const int hpb = min(a.hpb, a.n_heads - h0);
-    float* Qs = smem;
-    float* Ks = Qs + (size_t)a.hpb * L * kRowStride;
-    float* Vs = Ks + (size_t)a.hpb * L * kRowStride;
+    const size_t per = (size_t)a.hpb * L * kRowStride;
+    float* Qs = smem;   // scale*Q, later the normalised output O
+    float* Ks = Qs + per;
+    float* Vs = Ks + per;
+    uint8_t* s_mask = reinterpret_cast<uint8_t*>(Vs + per);   // [L][64] keep bytes (dropout only)
     const long long row0 = (long long)seq * L;
     const int ld = 3 * D;
+    const int col0 = h0 * dk, ncol = hpb * dk;
 
-    load_heads(Qs, a.qkv, row0, ld, h0 * dk, L, dk, hpb, a.scale);
-    load_heads(Ks, a.qkv, row0, ld, D + h0 * dk, L, dk, hpb, 1.f);
-    load_heads(Vs, a.qkv, row0, ld, 2 * D + h0 * dk, L, dk, hpb, 1.f);
-    __syncthreads();
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rc = ceil_div(L, 32);
-    const int nwarps = blockDim.x >> 5;
-    for (int task = warp; task < hpb * rc; task += nwarps) {
-        const int hh = task / rc;
-        const int i = (task - hh * rc) * 32 + lane;
-        const bool active = i < L;
-        const int ii = active ? i : 0;
-        float q[kDkPad], acc[kDkPad];
-        const float* qrow = Qs + (size_t)(hh * L + ii) * kRowStride;
-#pragma unroll
-        for (int c = 0; c < kDkPad / 4; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(qrow + 4 * c);
-            q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
-        }
-#pragma unroll
-        for (int d = 0; d < kDkPad; ++d) acc[d] = 0.f;
-        float mx = -INFINITY, den = 0.f;
-        const float* kbase = Ks + (size_t)hh * L * kRowStride;
-        const float* vbase = Vs + (size_t)hh * L * kRowStride;
-        for (int j = 0; j < L; ++j) {
-            const float* kr = kbase + j * kRowStride;
-            float s = 0.f;
-#pragma unroll
-            for (int c = 0; c < kDkPad / 4; ++c) {
-                const float4 kv = *reinterpret_cast<const float4*>(kr + 4 * c);
-                s = fmaf(q[4 * c], kv.x, s);
-                s = fmaf(q[4 * c + 1], kv.y, s);
-                s = fmaf(q[4 * c + 2], kv.z, s);
-                s = fmaf(q[4 * c + 3], kv.w, s);
-            }
-            const float mnew = fmaxf(mx, s);
-            const float corr = __expf(mx - mnew);  // exp(-inf)=0 on the first key
-            const float p = __expf(s - mnew);
-            den = den * corr + p;
-            const float* vr = vbase + j * kRowStride;
-#pragma unroll
-            for (int c = 0; c < kDkPad / 4; ++c) {
-                const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * c);
-                acc[4 * c] = fmaf(p, vv.x, acc[4 * c] * corr);
-                acc[4 * c + 1] = fmaf(p, vv.y, acc[4 * c + 1] * corr);
-                acc[4 * c + 2] = fmaf(p, vv.z, acc[4 * c + 2] * corr);
-                acc[4 * c + 3] = fmaf(p, vv.w, acc[4 * c + 3] * corr);
-            }
-            mx = mnew;
-        }
-        if (active) {
-            const float inv = 1.f / den;
-            float* orow = Qs + (size_t)(hh * L + i) * kRowStride;  // own row: safe to overwrite
-#pragma unroll
-            for (int c = 0; c < kDkPad / 4; ++c)
-                *reinterpret_cast<float4*>(orow + 4 * c) = make_float4(
-                    acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv,
-                    acc[4 * c + 3] * inv);
-            a.lse[(row0 + i) * a.n_heads + h0 + hh] = mx + __logf(den);
+    load_heads<VEC2>(Qs, a.qkv, row0, ld, col0, L, dk, hpb, a.scale);
+    load_heads<VEC2>(Ks, a.qkv, row0, ld, D + col0, L, dk, hpb, 1.f);
+    load_heads<VEC2>(Vs, a.qkv, row0, ld, 2 * D + col0, L, dk, hpb, 1.f);
+    if (a.drop.enabled()) {
+        // keep bits of the 8-column groups overlapping this CTA's columns: one Philox call each
+        const int g0 = col0 >> 3, g1 = (col0 + ncol + 7) >> 3;
+        const int ng = g1 - g0;
+        for (int i = threadIdx.x; i < L * ng; i += blockDim.x) {
+            const int l = i / ng, g = g0 + (i - l * ng);
+            const uint32_t keep = a.drop.keep8(kDropContext, (uint64_t)(row0 + l), (uint32_t)g);
+            s_mask[l * 64 + g] = (uint8_t)keep;
+            // a group straddling two head groups is written twice with the same value
+            if (a.cmask && g < a.mask_bytes) a.cmask[(row0 + l) * a.mask_bytes + g] = (uint8_t)keep;
         }
     }
     __syncthreads();
-    // coalesced write-out (+ context dropout, nrms_v0.py:171-173)
-    const int ncol = hpb * dk;
-    for (int i = threadIdx.x; i < L * ncol; i += blockDim.x) {
-        const int l = i / ncol, c = i - l * ncol;
-        const int hh = c / dk, d = c - hh * dk;
-        float v = Qs[(size_t)(hh * L + l) * kRowStride + d];
-        const long long e = (row0 + l) * D + h0 * dk + c;
-        if (a.drop.enabled()) v *= a.drop.mult(kDropContext, (uint64_t)e);
-        a.ctx[e] = v;
+
+    const int unit = threadIdx.x / U, ul = threadIdx.x % U;
+    const int units = blockDim.x / U;
+    const int rb_n = ceil_div(L, 2 * U);
+    for (int task = unit; task < hpb * rb_n; task += units) {
+        const int hh = task / rb_n;
+        const int r0 = (task - hh * rb_n) * 2 * U + ul, r1 = r0 + U;
+        const bool act0 = r0 < L, act1 = r1 < L;
+        float q0[kDkPad], q1[kDkPad], acc0[kDkPad], acc1[kDkPad];
+        load_row32(q0, Qs + (size_t)(hh * L + (act0 ? r0 : 0)) * kRowStride);
+        load_row32(q1, Qs + (size_t)(hh * L + (act1 ? r1 : 0)) * kRowStride);
+#pragma unroll
+        for (int d = 0; d < kDkPad; ++d) { acc0[d] = 0.f; acc1[d] = 0.f; }
+        float m0 = -INFINITY, m1 = -INFINITY, den0 = 0.f, den1 = 0.f;
+        const float* kbase = Ks + (size_t)hh * L * kRowStride;
+        const float* vbase = Vs + (size_t)hh * L * kRowStride;
+        for (int j0 = 0; j0 < L; j0 += kKeyGroup) {
+            float s0[kKeyGroup], s1[kKeyGroup];
+#pragma unroll
+            for (int g = 0; g < kKeyGroup; ++g) {
+                const int j = min(j0 + g, L - 1);
+                const float* kr = kbase + j * kRowStride;
+                float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < kDkPad / 4; ++c) {
+                    const float4 kv = *reinterpret_cast<const float4*>(kr + 4 * c);
+                    x0 = fmaf(q0[4 * c], kv.x, x0); x1 = fmaf(q1[4 * c], kv.x, x1);
+                    x0 = fmaf(q0[4 * c + 1], kv.y, x0); x1 = fmaf(q1[4 * c + 1], kv.y, x1);
+                    x0 = fmaf(q0[4 * c + 2], kv.z, x0); x1 = fmaf(q1[4 * c + 2], kv.z, x1);
+                    x0 = fmaf(q0[4 * c + 3], kv.w, x0); x1 = fmaf(q1[4 * c + 3], kv.w, x1);
+                }
+                const bool valid = j0 + g < L;
+                s0[g] = valid ? x0 : -INFINITY;
+                s1[g] = valid ? x1 : -INFINITY;
+            }
+            float n0 = m0, n1 = m1;
+#pragma unroll
+            for (int g = 0; g < kKeyGroup; ++g) { n0 = fmaxf(n0, s0[g]); n1 = fmaxf(n1, s1[g]); }
+            const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);   // exp(-inf) = 0 on the first group
+            m0 = n0; m1 = n1;
+            den0 *= c0; den1 *= c1;
+#pragma unroll
+            for (int d = 0; d < kDkPad; ++d) { acc0[d] *= c0; acc1[d] *= c1; }
+#pragma unroll
+            for (int g = 0; g < kKeyGroup; ++g) {
+                const int j = min(j0 + g, L - 1);
+                const float p0 = __expf(s0[g] - n0), p1 = __expf(s1[g] - n1);   // 0 for invalid keys
+                den0 += p0; den1 += p1;
+                const float* vr = vbase + j * kRowStride;
+#pragma unroll
+                for (int c = 0; c < kDkPad / 4; ++c) {
+                    const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * c);
+                    acc0[4 * c] = fmaf(p0, vv.x, acc0[4 * c]); acc1[4 * c] = fmaf(p1, vv.x, acc1[4 * c]);
+                    acc0[4 * c + 1] = fmaf(p0, vv.y, acc0[4 * c + 1]); acc1[4 * c + 1] = fmaf(p1, vv.y, acc1[4 * c + 1]);
+                    acc0[4 * c + 2] = fmaf(p0, vv.z, acc0[4 * c + 2]); acc1[4 * c + 2] = fmaf(p1, vv.z, acc1[4 * c + 2]);
+                    acc0[4 * c + 3] = fmaf(p0, vv.w, acc0[4 * c + 3]); acc1[4 * c + 3] = fmaf(p1, vv.w, acc1[4 * c + 3]);
+                }
+            }
+        }
+        // own rows of Qs: nobody else reads them, safe to overwrite with the output
+        if (act0) {
+            store_row32(Qs + (size_t)(hh * L + r0) * kRowStride, acc0, 1.f / den0);
+            a.lse[(row0 + r0) * a.n_heads + h0 + hh] = m0 + __logf(den0);
+        }
+        if (act1) {
+            store_row32(Qs + (size_t)(hh * L + r1) * kRowStride, acc1, 1.f / den1);
+            a.lse[(row0 + r1) * a.n_heads + h0 + hh] = m1 + __logf(den1);
+        }
+    }
+    __syncthreads();
+
+    // coalesced write-out in 2-column units (+ context dropout, nrms_v0.py:171-173)
+    const bool img = a.ctx_img.hi != nullptr;
+    const bool drop = a.drop.enabled();
+    if (VEC2) {
+        const int n2 = ncol >> 1;
+        for (int i = threadIdx.x; i < L * n2; i += blockDim.x) {
+            const int l = i / n2, c = (i - l * n2) << 1;
+            const int hh = c / dk, d = c - hh * dk;
+            float2 v = *reinterpret_cast<const float2*>(Qs + (size_t)(hh * L + l) * kRowStride + d);
+            const int col = col0 + c;
+            if (drop) {
+                const uint32_t keep = (uint32_t)s_mask[l * 64 + (col >> 3)] >> (col & 7);
+                v.x = (keep & 1u) ? v.x * a.drop.scale : 0.f;
+                v.y = (keep & 2u) ? v.y * a.drop.scale : 0.f;
+            }
+            *reinterpret_cast<float2*>(a.ctx + (row0 + l) * D + col) = v;
+            if (img) {
+                __nv_bfloat16 h0b, l0b, h1b, l1b;
+                tc::split_bf16(v.x, h0b, l0b);
+                tc::split_bf16(v.y, h1b, l1b);
+                const long long off = ig::img_unit_off(a.ctx_img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
+                *reinterpret_cast<uint32_t*>(a.ctx_img.hi + off) =
+                    (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+                *reinterpret_cast<uint32_t*>(a.ctx_img.lo + off) =
+                    (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < L * ncol; i += blockDim.x) {
+            const int l = i / ncol, c = i - l * ncol;
+            const int hh = c / dk, d = c - hh * dk;
+            float v = Qs[(size_t)(hh * L + l) * kRowStride + d];
+            const int col = col0 + c;
+            if (drop) v = ((s_mask[l * 64 + (col >> 3)] >> (col & 7)) & 1u) ? v * a.drop.scale : 0.f;
+            a.ctx[(row0 + l) * D + col] = v;
+        }
+    }
+    if (img) {
+        // image padding: columns [D, 64*chunks) of this sequence's rows (the last head group does
+        // it) and, by the very last CTA, the rows [M, rows_pad) — both enter GEMM reductions
+        if (h0 + hpb == a.n_heads) {
+            const int cpad = a.ctx_img.chunks * 64 - D;   // even
+            for (int i = threadIdx.x; i < L * (cpad >> 1); i += blockDim.x) {
+                const int l = i / (cpad >> 1), col = D + ((i - l * (cpad >> 1)) << 1);
+                const long long off = ig::img_unit_off(a.ctx_img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
+                *reinterpret_cast<uint32_t*>(a.ctx_img.hi + off) = 0u;
+                *reinterpret_cast<uint32_t*>(a.ctx_img.lo + off) = 0u;
+            }
+        }
+        if (seq == (int)gridDim.x - 1 && blockIdx.y == 0) {
+            const int groups = a.ctx_img.chunks * 8;
+            const long long npad = a.ctx_img.rows_pad - a.M;
+            for (long long i = threadIdx.x; i < npad * groups; i += blockDim.x)
+                ig::img_store8_zero(a.ctx_img, a.M + i / groups, (int)(i % groups));
+        }
     }
 }
 
-// Backward.  With P = softmax(S), S = scale * Q K^T, O = P V, dO given:
+// ------------------------------------------------------------------------------------------------
+// backward.  With P = softmax(S), S = scale * Q K^T, O = P V, dO given:
 //   dV = P^T dO ; dP = dO V^T ; dS = P * (dP - rowsum(dO*O)) ; dQ = scale dS K ; dK = scale dS^T Q
-// Pass A: lane = query row i (accumulates dQ_i); pass B: lane = key row j (accumulates
-// dK_j, dV_j).  P is recomputed from the saved log-sum-exp.
+// ------------------------------------------------------------------------------------------------
+template <bool VEC2>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
     extern __shared__ __align__(16) float smem[];
     const int L = a.L, D = a.D, dk = a.dk;
@@ -158,54 +276,51 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
     float* Qs = smem;  // holds scale*Q
     float* Ks = Qs + per;
     float* Vs = Ks + per;
-    float* Gs = Vs + per;  // dO (grad wrt pre-dropout context)
+    float* Gs = Vs + per;  // dO (grad wrt pre-dropout context); spare columns 32,33: delta, lse
     const long long row0 = (long long)seq * L;
     const int ld = 3 * D;
+    const int col0 = h0 * dk, ncol = hpb * dk;
+    const bool drop = a.drop.enabled() && a.cmask != nullptr;
 
-    load_heads(Qs, a.qkv, row0, ld, h0 * dk, L, dk, hpb, a.scale);
-    load_heads(Ks, a.qkv, row0, ld, D + h0 * dk, L, dk, hpb, 1.f);
-    load_heads(Vs, a.qkv, row0, ld, 2 * D + h0 * dk, L, dk, hpb, 1.f);
-    {
-        const int ncol = hpb * dk;
-        for (int i = threadIdx.x; i < L * ncol; i += blockDim.x) {
-            const int l = i / ncol, c = i - l * ncol;
-            const int hh = c / dk, d = c - hh * dk;
-            const long long e = (row0 + l) * D + h0 * dk + c;
-            float v = __ldg(a.d_ctx + e);
-            if (a.drop.enabled()) v *= a.drop.mult(kDropContext, (uint64_t)e);
-            Gs[(size_t)(hh * L + l) * kRowStride + d] = v;
-        }
-        // column 31 of every Gs row carries delta_i = rowsum(dO*O) (dk <= 30) or it is
-        // kept in a register when dk > 30 -> we always recompute it per lane below and
-        // broadcast through column `kDkPad` .. kRowStride-1 (4 spare floats per row).
-        const int npad = kDkPad - dk;
-        if (npad > 0)
-            for (int i = threadIdx.x; i < hpb * L * npad; i += blockDim.x) {
-                const int r = i / npad, d = dk + (i - r * npad);
-                Gs[(size_t)r * kRowStride + d] = 0.f;
-            }
-    }
+    // phase 0: dO = d_ctx * mask -> Gs, post-dropout context -> Qs (temporarily), then
+    // delta_i = sum_d dO_raw * O_raw = (sum_d dO * ctx_post) / drop.scale, one (head,row) per
+    // thread in a fixed order (deterministic; no atomics)
+    load_heads<VEC2>(Ks, a.qkv, row0, ld, D + col0, L, dk, hpb, 1.f);
+    load_heads<VEC2>(Vs, a.qkv, row0, ld, 2 * D + col0, L, dk, hpb, 1.f);
+    load_heads<VEC2>(Qs, a.ctx, row0, D, col0, L, dk, hpb, 1.f);
+    load_heads<VEC2>(Gs, a.d_ctx, row0, D, col0, L, dk, hpb, 1.f);
     __syncthreads();
-    // delta_i and lse_i go to the spare columns 32,33 of Gs rows
+    const float inv_drop = drop ? 1.f / a.drop.scale : 1.f;
     for (int i = threadIdx.x; i < hpb * L; i += blockDim.x) {
         const int hh = i / L, l = i - hh * L;
-        const float* g = Gs + (size_t)i * kRowStride;
-        const float* o = a.ctx + (row0 + l) * D + (h0 + hh) * dk;  // post-dropout context
-        const float* go = a.d_ctx + (row0 + l) * D + (h0 + hh) * dk;
+        float* g = Gs + (size_t)i * kRowStride;
+        const float* o = Qs + (size_t)i * kRowStride;
+        if (drop) {
+            for (int d = 0; d < dk; ++d) {
+                const int col = col0 + hh * dk + d;
+                const uint32_t keep = ((uint32_t)a.cmask[(row0 + l) * a.mask_bytes + (col >> 3)] >> (col & 7)) & 1u;
+                g[d] = keep ? g[d] * a.drop.scale : 0.f;
+            }
+        }
         float dl = 0.f;
-        // sum(dO_raw * O_raw) == sum(dO_out * O_out) because both carry the same mask factor
-        for (int d = 0; d < dk; ++d) dl = fmaf(__ldg(go + d), __ldg(o + d), dl);
-        (void)g;
-        Gs[(size_t)i * kRowStride + kDkPad] = dl;
-        Gs[(size_t)i * kRowStride + kDkPad + 1] = a.lse[(row0 + l) * a.n_heads + h0 + hh];
+#pragma unroll
+        for (int c = 0; c < kDkPad / 4; ++c) {
+            const float4 gv = *reinterpret_cast<const float4*>(g + 4 * c);
+            const float4 ov = *reinterpret_cast<const float4*>(o + 4 * c);
+            dl = fmaf(gv.x, ov.x, dl); dl = fmaf(gv.y, ov.y, dl);
+            dl = fmaf(gv.z, ov.z, dl); dl = fmaf(gv.w, ov.w, dl);
+        }
+        g[kDkPad] = dl * inv_drop;
+        g[kDkPad + 1] = a.lse[(row0 + l) * a.n_heads + h0 + hh];
     }
+    __syncthreads();
+    load_heads<VEC2>(Qs, a.qkv, row0, ld, col0, L, dk, hpb, a.scale);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rc = ceil_div(L, 32);
-    const int nwarps = blockDim.x >> 5;
-    // results are staged in registers until every warp has finished reading smem
-    // (tasks per warp is small: hpb*rc / nwarps, launch config guarantees exactly 1)
+    // one (head, 32-row block) task per warp (the launch configuration guarantees it); results
+    // stay in registers until every warp has finished reading shared memory
     const int task = warp;
     const bool has_task = task < hpb * rc;
     const int hh = has_task ? task / rc : 0;
@@ -221,18 +336,14 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
     {
         // ---- pass A: lane = query row ---------------------------------------------------
         float q[kDkPad], go[kDkPad];
-#pragma unroll
-        for (int c = 0; c < kDkPad / 4; ++c) {
-            const float4 v = *reinterpret_cast<const float4*>(qb + ii * kRowStride + 4 * c);
-            q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
-            const float4 w = *reinterpret_cast<const float4*>(gb + ii * kRowStride + 4 * c);
-            go[4 * c] = w.x; go[4 * c + 1] = w.y; go[4 * c + 2] = w.z; go[4 * c + 3] = w.w;
-        }
+        load_row32(q, qb + ii * kRowStride);
+        load_row32(go, gb + ii * kRowStride);
         const float delta = gb[ii * kRowStride + kDkPad];
         const float lse = gb[ii * kRowStride + kDkPad + 1];
 #pragma unroll
         for (int d = 0; d < kDkPad; ++d) dq[d] = 0.f;
         if (has_task) {
+#pragma unroll 2
             for (int j = 0; j < L; ++j) {
                 const float* kr = kb + j * kRowStride;
                 const float* vr = vb + j * kRowStride;
@@ -260,16 +371,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
     {
         // ---- pass B: lane = key row -------------------------------------------------------
         float k[kDkPad], v[kDkPad];
-#pragma unroll
-        for (int c = 0; c < kDkPad / 4; ++c) {
-            const float4 x = *reinterpret_cast<const float4*>(kb + ii * kRowStride + 4 * c);
-            k[4 * c] = x.x; k[4 * c + 1] = x.y; k[4 * c + 2] = x.z; k[4 * c + 3] = x.w;
-            const float4 y = *reinterpret_cast<const float4*>(vb + ii * kRowStride + 4 * c);
-            v[4 * c] = y.x; v[4 * c + 1] = y.y; v[4 * c + 2] = y.z; v[4 * c + 3] = y.w;
-        }
+        load_row32(k, kb + ii * kRowStride);
+        load_row32(v, vb + ii * kRowStride);
 #pragma unroll
         for (int d = 0; d < kDkPad; ++d) { dkk[d] = 0.f; dvv[d] = 0.f; }
         if (has_task) {
+#pragma unroll 2
             for (int r = 0; r < L; ++r) {
                 const float* qr = qb + r * kRowStride;  // scale*Q_r
                 const float* gr = gb + r * kRowStride;
@@ -301,35 +408,67 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
     }
     __syncthreads();  // everyone is done reading Q/K/V/dO
     if (active) {
-        float* r0 = Qs + (size_t)(hh * L + i) * kRowStride;
-        float* r1 = Ks + (size_t)(hh * L + i) * kRowStride;
-        float* r2 = Vs + (size_t)(hh * L + i) * kRowStride;
-#pragma unroll
-        for (int c = 0; c < kDkPad / 4; ++c) {
-            *reinterpret_cast<float4*>(r0 + 4 * c) =
-                make_float4(dq[4 * c], dq[4 * c + 1], dq[4 * c + 2], dq[4 * c + 3]);
-            *reinterpret_cast<float4*>(r1 + 4 * c) =
-                make_float4(dkk[4 * c], dkk[4 * c + 1], dkk[4 * c + 2], dkk[4 * c + 3]);
-            *reinterpret_cast<float4*>(r2 + 4 * c) =
-                make_float4(dvv[4 * c], dvv[4 * c + 1], dvv[4 * c + 2], dvv[4 * c + 3]);
-        }
+        store_row32(Qs + (size_t)(hh * L + i) * kRowStride, dq, 1.f);
+        store_row32(Ks + (size_t)(hh * L + i) * kRowStride, dkk, 1.f);
+        store_row32(Vs + (size_t)(hh * L + i) * kRowStride, dvv, 1.f);
     }
     __syncthreads();
     // coalesced write-out of dQ|dK|dV and the per-sequence column sums (bias gradients)
-    const int ncol = hpb * dk;
+    const bool img = a.d_qkv_img.hi != nullptr;
     for (int third = 0; third < 3; ++third) {
         const float* src = smem + third * per;
-        for (int idx = threadIdx.x; idx < L * ncol; idx += blockDim.x) {
-            const int l = idx / ncol, c = idx - l * ncol;
-            const int h2 = c / dk, d = c - h2 * dk;
-            a.d_qkv[(row0 + l) * ld + third * D + h0 * dk + c] =
-                src[(size_t)(h2 * L + l) * kRowStride + d];
+        if (VEC2) {
+            const int n2 = ncol >> 1;
+            for (int idx = threadIdx.x; idx < L * n2; idx += blockDim.x) {
+                const int l = idx / n2, c = (idx - l * n2) << 1;
+                const int h2 = c / dk, d = c - h2 * dk;
+                const float2 v = *reinterpret_cast<const float2*>(src + (size_t)(h2 * L + l) * kRowStride + d);
+                const int col = third * D + col0 + c;
+                if (a.d_qkv) *reinterpret_cast<float2*>(a.d_qkv + (row0 + l) * ld + col) = v;
+                if (img) {
+                    __nv_bfloat16 h0b, l0b, h1b, l1b;
+                    tc::split_bf16(v.x, h0b, l0b);
+                    tc::split_bf16(v.y, h1b, l1b);
+                    const long long off = ig::img_unit_off(a.d_qkv_img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
+                    *reinterpret_cast<uint32_t*>(a.d_qkv_img.hi + off) =
+                        (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+                    *reinterpret_cast<uint32_t*>(a.d_qkv_img.lo + off) =
+                        (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+                }
+            }
+        } else {
+            for (int idx = threadIdx.x; idx < L * ncol; idx += blockDim.x) {
+                const int l = idx / ncol, c = idx - l * ncol;
+                const int h2 = c / dk, d = c - h2 * dk;
+                if (a.d_qkv)
+                    a.d_qkv[(row0 + l) * ld + third * D + col0 + c] = src[(size_t)(h2 * L + l) * kRowStride + d];
+            }
         }
         for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
             const int h2 = c / dk, d = c - h2 * dk;
             float sum = 0.f;
             for (int l = 0; l < L; ++l) sum += src[(size_t)(h2 * L + l) * kRowStride + d];
-            a.d_bias_part[(long long)seq * ld + third * D + h0 * dk + c] = sum;
+            a.d_bias_part[(long long)seq * ld + third * D + col0 + c] = sum;
+        }
+    }
+    if (img) {
+        // image padding: columns [3D, 16*ceil(3D/16)) are read by the data-gradient GEMM's last
+        // k-step, rows [M, rows_pad) by the weight-gradient reduction: both must be zero
+        if (h0 + hpb == a.n_heads) {
+            const int cend = ceil_div(3 * D, 16) * 16;
+            const int cpad = cend - 3 * D;   // even
+            for (int idx = threadIdx.x; idx < L * (cpad >> 1); idx += blockDim.x) {
+                const int l = idx / (cpad >> 1), col = 3 * D + ((idx - l * (cpad >> 1)) << 1);
+                const long long off = ig::img_unit_off(a.d_qkv_img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
+                *reinterpret_cast<uint32_t*>(a.d_qkv_img.hi + off) = 0u;
+                *reinterpret_cast<uint32_t*>(a.d_qkv_img.lo + off) = 0u;
+            }
+        }
+        if (seq == (int)gridDim.x - 1 && blockIdx.y == 0) {
+            const int groups = a.d_qkv_img.chunks * 8;
+            const long long npad = a.d_qkv_img.rows_pad - a.M;
+            for (long long idx = threadIdx.x; idx < npad * groups; idx += blockDim.x)
+                ig::img_store8_zero(a.d_qkv_img, a.M + idx / groups, (int)(idx % groups));
         }
     }
 }

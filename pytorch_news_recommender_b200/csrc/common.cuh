@@ -17,9 +17,7 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 __host__ __device__ inline int64_t align_up(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
 
 // ---------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG.  One call yields 4 x 32 random bits for 4 consecutive flat
-// elements of a dropout stream; forward and backward regenerate the same mask from
-// (seed, stream_id, flat element index), so no mask is ever stored.
+// Philox4x32-10 counter RNG (128 random bits per call) keyed by the step's dropout seed.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
@@ -34,30 +32,29 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
     return ctr;
 }
 
+// Dropout masks are addressed by (stream, row, 8-column group): one Philox call yields the 8
+// keep decisions of columns [8g, 8g+8) of a row (16 random bits per element), so a kernel that
+// owns 8 consecutive columns pays one call, and the keep bits are stored (1 bit per element,
+// byte g of a row = group g) for the backward instead of being regenerated.
 struct Dropout {
-    uint32_t thresh;  // drop when bits < thresh ; 0 => dropout disabled
+    uint32_t thresh;  // drop when the 16 random bits < thresh ; 0 => dropout disabled
     float scale;      // 1/(1-p)
     uint32_t seed_lo, seed_hi;
 
     __host__ __device__ bool enabled() const { return thresh != 0u; }
 
-    // bits for the 4-element group `group` (= flat_index >> 2) of stream `sid`
-    __device__ __forceinline__ uint4 bits(uint32_t sid, uint64_t group) const {
-        return philox4x32_10(make_uint4((uint32_t)group, (uint32_t)(group >> 32), sid, 0u),
-                             make_uint2(seed_lo, seed_hi));
-    }
-    // multiplier (0 or scale) of flat element e
-    __device__ __forceinline__ float mult(uint32_t sid, uint64_t e) const {
-        const uint4 r = bits(sid, e >> 2);
-        const uint32_t c = (uint32_t)(e & 3u);
-        const uint32_t b = c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
-        return b >= thresh ? scale : 0.f;
-    }
-    // multipliers of the aligned 4-group starting at flat element e (e % 4 == 0)
-    __device__ __forceinline__ float4 mult4(uint32_t sid, uint64_t e) const {
-        const uint4 r = bits(sid, e >> 2);
-        return make_float4(r.x >= thresh ? scale : 0.f, r.y >= thresh ? scale : 0.f,
-                           r.z >= thresh ? scale : 0.f, r.w >= thresh ? scale : 0.f);
+    // 8 keep bits (bit j = column 8g+j is kept) of group g of row `row` in stream `sid`
+    __device__ __forceinline__ uint32_t keep8(uint32_t sid, uint64_t row, uint32_t g) const {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)row, (uint32_t)(row >> 32), g, sid),
+                                      make_uint2(seed_lo, seed_hi));
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t v = (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+            bits |= (v >= thresh ? 1u : 0u) << j;
+        }
+        return bits;
     }
 };
 
@@ -67,8 +64,8 @@ inline Dropout make_dropout(float p, uint64_t seed) {
         d.thresh = 0u;
         d.scale = 1.f;
     } else {
-        double t = (double)p * 4294967296.0;
-        if (t > 4294967295.0) t = 4294967295.0;
+        double t = (double)p * 65536.0;
+        if (t > 65535.0) t = 65535.0;
         if (t < 1.0) t = 1.0;
         d.thresh = (uint32_t)t;
         d.scale = 1.f / (1.f - p);

@@ -1,0 +1,419 @@
+// gemm_img.cuh — tcgen05 GEMMs of the NRMS path over "split-bf16 images".
+//
+// Every dense contraction of the path (Q|K|V and additive-attention projections, their data
+// gradients and their weight gradients; reference nrms_v0.py:53-58,108 and autograd) is
+//
+//     C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )          fp32 in, fp32 out
+//
+// computed fp32-grade on the 5th-gen tensor cores through a 3-term bf16 split ("bf16x3"):
+// x = hi + lo, hi = bf16(x), lo = bf16(x - hi); A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo with fp32
+// accumulation in TMEM (dropped term ~2^-16 relative).
+//
+// Operand format — the split-bf16 IMAGE of a row-major fp32 matrix X[R, C]:
+//   two byte planes (hi, lo); plane = C/64 column CHUNKS, each chunk = R_pad rows of 128 bytes
+//   (64 bf16), rows grouped in 8-row / 1024-byte swizzle atoms (16-byte unit index XOR row%8):
+//       off(r, c) = (c/64)*R_pad*128 + (r/8)*1024 + (r%8)*128 + ((((c%64)/8) ^ (r%8)) * 16) + (c%8)*2
+//   This is byte-for-byte the shared-memory layout tcgen05 expects for SWIZZLE_128B, and the
+//   SAME bytes serve both operand orientations:
+//     * K-major  (k = columns of X): rows [r0,r0+n) of chunk c are n*128 contiguous bytes;
+//     * MN-major (k = rows of X)   : rows [k0,k0+64) of chunk c are 8192 contiguous bytes, one
+//       64-wide M/N block of the operand.
+//   So a weight image W[out,in] feeds the forward (K-major) and the data gradient (MN-major),
+//   and an activation image feeds a forward/data-gradient GEMM (K-major) and the weight
+//   gradient (MN-major, k = tokens), all with plain cp.async.bulk copies — no conversion, no
+//   transposition and no tensor maps in the GEMM kernel.  The kernels that PRODUCE activations
+//   (embedding gather, attention, pooling backward) write the images directly.
+//
+// Kernel structure (persistent, one CTA per SM, warp-specialised):
+//   warp 0     one thread streams operand stages with cp.async.bulk into a shared-memory ring,
+//   warp 1     one thread issues tcgen05.mma (cta_group::1, kind::f16, M=128) and commits to
+//              the stage-empty / accumulator-full mbarriers,
+//   warps 2-5  epilogue: tcgen05.ld the accumulator (TMEM lane = output row), apply
+//              bias / tanh+dot / accumulate / dropout-mask, store fp32.
+// Accumulators are double-buffered in TMEM when 2*N_T <= 512 columns so the epilogue of one
+// tile overlaps the main loop of the next.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tcgen05_ptx.cuh"
+#include "profiler.cuh"
+
+namespace nrms {
+namespace ig {
+
+constexpr int IMG_CH = 64;          // bf16 columns per chunk
+constexpr int IMG_ROW_B = 128;      // bytes per image row
+constexpr int IMG_BLOCK_B = 8192;   // 64 rows x 128 B: one MN-major 64-wide block per k-chunk
+constexpr int A_TILE_B = 16384;     // 128 rows x 128 B (K-major) == 2 blocks (MN-major)
+
+struct Img {
+    uint8_t* hi;
+    uint8_t* lo;
+    long long chunk_stride;  // rows_pad * 128
+    int rows_pad;            // multiple of 128
+    int chunks;
+};
+__host__ __device__ inline int img_rows_pad(long long rows) { return (int)(align_up(rows, 128)); }
+__host__ __device__ inline int img_chunks(int cols) { return ceil_div(cols, IMG_CH); }
+__host__ __device__ inline long long img_plane_bytes(long long rows, int chunks) {
+    return (long long)img_rows_pad(rows) * IMG_ROW_B * chunks;
+}
+// total bytes of an image (hi plane then lo plane), 1024-aligned by construction
+__host__ __device__ inline long long img_bytes(long long rows, int chunks) {
+    return 2 * img_plane_bytes(rows, chunks);
+}
+inline Img img_view(void* base, long long rows, int chunks) {
+    Img v;
+    v.hi = reinterpret_cast<uint8_t*>(base);
+    v.lo = v.hi + img_plane_bytes(rows, chunks);
+    v.rows_pad = img_rows_pad(rows);
+    v.chunk_stride = (long long)v.rows_pad * IMG_ROW_B;
+    v.chunks = chunks;
+    return v;
+}
+// byte offset of the 16-byte unit holding columns [8*g, 8*g+8) of row r (g = global 8-group)
+__host__ __device__ __forceinline__ long long img_unit_off(long long chunk_stride, long long r, int g) {
+    const int chunk = g >> 3, u = g & 7, r7 = (int)(r & 7);
+    return (long long)chunk * chunk_stride + (r >> 3) * 1024 + r7 * 128 + ((u ^ r7) << 4);
+}
+// split 8 floats and store them as one 16-byte unit into both planes
+__device__ __forceinline__ void img_store8(const Img& im, long long r, int g, const float* x) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        tc::split_bf16(x[2 * j], h0, l0);
+        tc::split_bf16(x[2 * j + 1], h1, l1);
+        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    const long long off = img_unit_off(im.chunk_stride, r, g);
+    *reinterpret_cast<uint4*>(im.hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void img_store8_zero(const Img& im, long long r, int g) {
+    const long long off = img_unit_off(im.chunk_stride, r, g);
+    *reinterpret_cast<uint4*>(im.hi + off) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ---- fp32 row-major matrix -> image (weights; zero padded) -------------------------------------
+__global__ void img_pack_kernel(const float* __restrict__ src, int R, int C, int ld, Img im) {
+    const int groups = im.chunks * 8;
+    const long long total = (long long)im.rows_pad * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % groups);
+        const long long r = i / groups;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            x[j] = (r < R && c < C) ? __ldg(src + r * ld + c) : 0.f;
+        }
+        img_store8(im, r, g, x);
+    }
+}
+inline cudaError_t img_pack(const float* src, int R, int C, int ld, const Img& im, cudaStream_t s) {
+    const long long total = (long long)im.rows_pad * im.chunks * 8;
+    NRMS_LAUNCH("img_pack", s,
+                img_pack_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(src, R, C, ld, im));
+    return cudaGetLastError();
+}
+
+// ---- the GEMM ----------------------------------------------------------------------------------
+enum Epi { EPI_BIAS = 0, EPI_TANH_DOT = 1, EPI_ACCUM = 2, EPI_MASK = 3, EPI_PARTIAL = 4 };
+
+struct IgArgs {
+    Img A, B;
+    float* C;
+    int ldc;
+    long long c_split_stride;   // EPI_PARTIAL: partial of split s lives at C + s*c_split_stride
+    const float* bias;          // EPI_BIAS / EPI_TANH_DOT: [N]
+    const float* qv;            // EPI_TANH_DOT: [N]
+    float* dot_out;             // EPI_TANH_DOT: [M]  sum_n tanh(.)*qv[n]
+    const uint32_t* mask_bits;  // EPI_MASK: [M, mask_words] keep bits (bit n%32 of word n/32), or NULL
+    int mask_words;
+    float mask_scale;           // 1/(1-p)
+    int M, N;                   // valid output rows / columns
+    int m_tiles, n_tiles;       // work grid (tiles of 128 rows x N_T columns)
+    int k_chunks;               // 64-deep k chunks in total
+    int k_steps;                // UMMA K=16 steps in total (<= 4*k_chunks)
+    int splits;                 // k splits (weight gradient); 1 otherwise
+};
+
+constexpr int IG_THREADS = 192;
+
+__host__ __device__ constexpr int ig_stage_bytes(int n_t) { return 2 * A_TILE_B + 2 * n_t * IMG_ROW_B; }
+__host__ __device__ constexpr int ig_stages(int n_t) {
+    return (227 * 1024 - 1280) / ig_stage_bytes(n_t) >= 4 ? 4 : (227 * 1024 - 1280) / ig_stage_bytes(n_t);
+}
+// tail after the ring: 128 B of mbarriers + TMEM slot, then 2*N_T floats of epilogue staging
+// (bias / query vector; only the N_T <= 256 variants stage anything)
+__host__ __device__ constexpr int ig_tail_bytes(int n_t) { return n_t <= 256 ? 128 + 2 * 256 * 4 : 256; }
+__host__ __device__ constexpr int ig_smem_bytes(int n_t) {
+    return ig_stages(n_t) * ig_stage_bytes(n_t) + 1024 /*alignment slack*/ + ig_tail_bytes(n_t);
+}
+
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // MN-major: bytes between 64-wide blocks
+    d |= (uint64_t)(1024 >> 4) << 32;                   // SBO: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=F32, A=B=BF16; major bits: 0 = K-major, 1 = MN-major
+__host__ __device__ constexpr uint32_t make_idesc2(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+template <bool A_MN, bool B_MN, int N_T, int EPI>
+__global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) {
+    constexpr int STAGES = ig_stages(N_T);
+    constexpr int STAGE_B = ig_stage_bytes(N_T);
+    constexpr int B_PLANE_B = N_T * IMG_ROW_B;
+    constexpr bool DOUBLE_ACC = 2 * N_T <= 512 && !A_MN;
+    constexpr int ACC_STRIDE = 256;            // TMEM column offset of the second accumulator
+    constexpr int N1 = N_T > 256 ? 256 : N_T;  // first / second UMMA of a k-step (N <= 256 each)
+    constexpr int N2 = N_T - N1;
+    static_assert(STAGES >= 2, "need at least a double buffer");
+    static_assert(N_T % 16 == 0 && N1 % 16 == 0 && N2 % 16 == 0, "UMMA N granularity for M=128");
+    static_assert(!B_MN || N_T % 64 == 0, "MN-major operands come in 64-wide blocks");
+    static_assert(N_T <= 512, "TMEM has 512 columns");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_B);
+    // bars: [0,S) full | [S,2S) empty | [2S,2S+2) acc full | [2S+2,2S+4) acc empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* s_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_B + 128);   // [2][256] floats (N_T <= 256 only)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = tc::smem_u32(smem);
+    const uint32_t bar_base = tc::smem_u32(bars);
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+    auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(full_bar(s), 1);
+            tc::mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            tc::mbar_init(accf_bar(b), 1);
+            tc::mbar_init(acce_bar(b), 4);
+        }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<512>(tc::smem_u32(tmem_slot));
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_work = a.m_tiles * a.n_tiles * a.splits;
+    const int cps = ceil_div(a.k_chunks, a.splits);   // chunks per split
+
+    if (warp == 0) {
+        // =============================== loader ================================================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                const int tile = w % (a.m_tiles * a.n_tiles), split = w / (a.m_tiles * a.n_tiles);
+                const int m_tile = tile / a.n_tiles, n_tile = tile % a.n_tiles;
+                const int c0 = split * cps, c1 = min(a.k_chunks, c0 + cps);
+                for (int kc = c0; kc < c1; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    tc::mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
+                    const uint32_t dst = smem_base + s * STAGE_B;
+                    tc::mbar_arrive_expect_tx(full_bar(s), STAGE_B);
+                    if (A_MN) {
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            const long long off = (long long)(m_tile * 2 + b) * a.A.chunk_stride + (long long)kc * IMG_BLOCK_B;
+                            tc::bulk_g2s(dst + b * IMG_BLOCK_B, a.A.hi + off, IMG_BLOCK_B, full_bar(s));
+                            tc::bulk_g2s(dst + A_TILE_B + b * IMG_BLOCK_B, a.A.lo + off, IMG_BLOCK_B, full_bar(s));
+                        }
+                    } else {
+                        const long long off = (long long)kc * a.A.chunk_stride + (long long)m_tile * A_TILE_B;
+                        tc::bulk_g2s(dst, a.A.hi + off, A_TILE_B, full_bar(s));
+                        tc::bulk_g2s(dst + A_TILE_B, a.A.lo + off, A_TILE_B, full_bar(s));
+                    }
+                    const uint32_t dstb = dst + 2 * A_TILE_B;
+                    if (B_MN) {
+#pragma unroll
+                        for (int b = 0; b < N_T / 64; ++b) {
+                            const long long off = (long long)(n_tile * (N_T / 64) + b) * a.B.chunk_stride + (long long)kc * IMG_BLOCK_B;
+                            tc::bulk_g2s(dstb + b * IMG_BLOCK_B, a.B.hi + off, IMG_BLOCK_B, full_bar(s));
+                            tc::bulk_g2s(dstb + B_PLANE_B + b * IMG_BLOCK_B, a.B.lo + off, IMG_BLOCK_B, full_bar(s));
+                        }
+                    } else {
+                        const long long off = (long long)kc * a.B.chunk_stride + (long long)n_tile * B_PLANE_B;
+                        tc::bulk_g2s(dstb, a.B.hi + off, B_PLANE_B, full_bar(s));
+                        tc::bulk_g2s(dstb + B_PLANE_B, a.B.lo + off, B_PLANE_B, full_bar(s));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =============================== MMA issuer ============================================
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = make_idesc2(N1, A_MN, B_MN);
+            constexpr uint32_t idesc2 = make_idesc2(N2 > 0 ? N2 : 16, A_MN, B_MN);
+            constexpr uint32_t A_LBO = A_MN ? IMG_BLOCK_B : 16, B_LBO = B_MN ? IMG_BLOCK_B : 16;
+            constexpr uint32_t A_ADV = A_MN ? 2048 : 32, B_ADV = B_MN ? 2048 : 32;   // bytes per K=16 step
+            // second UMMA of a k-step covers columns [N1, N_T): its B rows/blocks start here
+            constexpr uint32_t B2_OFF = B_MN ? (N1 / 64) * IMG_BLOCK_B : N1 * IMG_ROW_B;
+            uint32_t it = 0, tile_it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
+                const int split = w / (a.m_tiles * a.n_tiles);
+                const int c0 = split * cps, c1 = min(a.k_chunks, c0 + cps);
+                const int buf = DOUBLE_ACC ? (int)(tile_it & 1u) : 0;
+                const uint32_t use = DOUBLE_ACC ? (tile_it >> 1) : tile_it;
+                tc::mbar_wait(acce_bar(buf), (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
+                for (int kc = c0; kc < c1; ++kc, ++it) {
+                    const int s = it % STAGES;
+                    tc::mbar_wait(full_bar(s), (it / STAGES) & 1u);
+                    tc::tc_fence_after();
+                    const uint32_t sa = smem_base + s * STAGE_B;
+                    const uint32_t sb = sa + 2 * A_TILE_B;
+                    const int steps = min(4, a.k_steps - 4 * kc);
+                    for (int j = 0; j < steps; ++j) {
+                        const uint64_t a_hi = make_sw128_desc(sa + j * A_ADV, A_LBO);
+                        const uint64_t a_lo = make_sw128_desc(sa + A_TILE_B + j * A_ADV, A_LBO);
+                        const uint64_t b_hi = make_sw128_desc(sb + j * B_ADV, B_LBO);
+                        const uint64_t b_lo = make_sw128_desc(sb + B_PLANE_B + j * B_ADV, B_LBO);
+                        const uint32_t acc = (kc > c0 || j > 0) ? 1u : 0u;
+                        tc::umma_bf16(d_tmem, a_hi, b_hi, idesc1, acc);
+                        tc::umma_bf16(d_tmem, a_lo, b_hi, idesc1, 1u);
+                        tc::umma_bf16(d_tmem, a_hi, b_lo, idesc1, 1u);
+                        if (N2 > 0) {
+                            const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
+                            const uint64_t b2_lo = make_sw128_desc(sb + B_PLANE_B + B2_OFF + j * B_ADV, B_LBO);
+                            tc::umma_bf16(d_tmem + N1, a_hi, b2_hi, idesc2, acc);
+                            tc::umma_bf16(d_tmem + N1, a_lo, b2_hi, idesc2, 1u);
+                            tc::umma_bf16(d_tmem + N1, a_hi, b2_lo, idesc2, 1u);
+                        }
+                    }
+                    tc::umma_commit(empty_bar(s));   // frees the stage when these MMAs retire
+                }
+                tc::umma_commit(accf_bar(buf));      // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // =============================== epilogue (warps 2..5) =================================
+        const int q = warp & 3;                       // TMEM lane quadrant this warp may read
+        const int et = (warp - 2) * 32 + lane;        // 0..127 within the epilogue group
+        static_assert(!(EPI == EPI_BIAS || EPI == EPI_TANH_DOT) || N_T <= 256, "epilogue staging holds 256 columns");
+        float* s_bias = s_epi;                        // [256]
+        float* s_qv = s_epi + 256;                    // [256] (EPI_TANH_DOT)
+        uint32_t tile_it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
+            const int tile = w % (a.m_tiles * a.n_tiles), split = w / (a.m_tiles * a.n_tiles);
+            const int m_tile = tile / a.n_tiles, n_tile = tile % a.n_tiles;
+            const int n0 = n_tile * N_T;
+            const int buf = DOUBLE_ACC ? (int)(tile_it & 1u) : 0;
+            const uint32_t use = DOUBLE_ACC ? (tile_it >> 1) : tile_it;
+            if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
+                for (int i = et; i < N_T; i += 128) {
+                    const int n = n0 + i;
+                    s_bias[i] = n < a.N ? __ldg(a.bias + n) : 0.f;
+                    if (EPI == EPI_TANH_DOT) s_qv[i] = n < a.N ? __ldg(a.qv + n) : 0.f;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            const int m = m_tile * 128 + q * 32 + lane;
+            const bool row_ok = m < a.M;
+            uint32_t mw[10];
+            if (EPI == EPI_MASK) {
+#pragma unroll
+                for (int i = 0; i < 10; ++i)
+                    mw[i] = (a.mask_bits && row_ok && i < a.mask_words) ? __ldg(a.mask_bits + (long long)m * a.mask_words + i)
+                                                                       : 0xffffffffu;
+            }
+            float* crow = a.C + (EPI == EPI_PARTIAL ? (long long)split * a.c_split_stride : 0ll) +
+                          (long long)m * a.ldc + n0;
+            tc::mbar_wait(accf_bar(buf), use & 1u);
+            tc::tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t)(buf * ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
+            float dot = 0.f;
+#pragma unroll 1
+            for (int cb = 0; cb < N_T; cb += 32) {
+                float v[32];
+                tc::tmem_ld32(t_row + (uint32_t)cb, v);
+                float4 old[8];
+                if (EPI == EPI_ACCUM) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int n = cb + 4 * g;
+                        old[g] = (row_ok && n < N_T && n0 + n < a.N) ? *reinterpret_cast<const float4*>(crow + n)
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    const int n = cb + 4 * g;
+                    if (n >= N_T) continue;
+                    float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                    if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT) {
+                        o.x += s_bias[n]; o.y += s_bias[n + 1]; o.z += s_bias[n + 2]; o.w += s_bias[n + 3];
+                    }
+                    if (EPI == EPI_TANH_DOT) {
+                        o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
+                        dot = fmaf(o.x, s_qv[n], dot); dot = fmaf(o.y, s_qv[n + 1], dot);
+                        dot = fmaf(o.z, s_qv[n + 2], dot); dot = fmaf(o.w, s_qv[n + 3], dot);
+                    }
+                    if (EPI == EPI_ACCUM) {
+                        o.x += old[g].x; o.y += old[g].y; o.z += old[g].z; o.w += old[g].w;
+                    }
+                    if (EPI == EPI_MASK) {
+                        const uint32_t bits = mw[(n0 + n) >> 5] >> ((n0 + n) & 31);
+                        o.x = (bits & 1u) ? o.x * a.mask_scale : 0.f;
+                        o.y = (bits & 2u) ? o.y * a.mask_scale : 0.f;
+                        o.z = (bits & 4u) ? o.z * a.mask_scale : 0.f;
+                        o.w = (bits & 8u) ? o.w * a.mask_scale : 0.f;
+                    }
+                    if (row_ok && n0 + n < a.N) *reinterpret_cast<float4*>(crow + n) = o;
+                }
+            }
+            if (EPI == EPI_TANH_DOT && row_ok) a.dot_out[m] = dot;
+            // release the accumulator
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acce_bar(buf));
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+}
+
+template <bool A_MN, bool B_MN, int N_T, int EPI>
+inline cudaError_t ig_launch(const IgArgs& a, cudaStream_t s, const char* name) {
+    constexpr int smem = ig_smem_bytes(N_T);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ig_gemm_kernel<A_MN, B_MN, N_T, EPI>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int total = a.m_tiles * a.n_tiles * a.splits;
+    const int grid = total < kNumSMs ? total : kNumSMs;
+    NRMS_LAUNCH(name, s, (ig_gemm_kernel<A_MN, B_MN, N_T, EPI><<<grid, IG_THREADS, smem, s>>>(a)));
+    return cudaGetLastError();
+}
+
+}  // namespace ig
+}  // namespace nrms

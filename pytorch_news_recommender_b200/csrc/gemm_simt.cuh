@@ -5,11 +5,12 @@
 //
 // Operand access is templated on which index is contiguous in memory so the same kernel
 // serves the three contraction shapes of an nn.Linear:
-//   forward   y = x W^T + b   : A K-contiguous (rows optionally GATHERED from the embedding
-//                               table, dropout applied on load), B K-contiguous (W is [N,K])
+//   forward   y = x W^T + b   : A K-contiguous, B K-contiguous (W is [N,K])
 //   data grad dx = dy W       : A K-contiguous, B N-contiguous (W is [K,N] for this product)
-//   weight grad dW = dy^T x   : A M-contiguous (dy^T), B N-contiguous (x, optionally gathered
-//                               + dropout), reduction split over blockIdx.z into partials.
+//   weight grad dW = dy^T x   : A M-contiguous (dy^T), B N-contiguous (x), reduction split over
+//                               blockIdx.z into partials.
+// The embedding gather and both dropouts happen in the producing kernels (gather.cuh,
+// attention.cuh); the data gradient w.r.t. the embedding rows applies the stored keep bits.
 // All contiguous extents are feature dims (300/900/200) => multiples of 4 => float4 access.
 #pragma once
 #include "common.cuh"
@@ -22,17 +23,15 @@ struct GemmArgs {
     const float* B;
     float* C;
     const float* bias;      // [N] or nullptr
-    const int64_t* a_rows;  // A_KC only: logical row m is stored at row a_rows[m] of A
-    const int64_t* b_rows;  // !B_KC only: logical k-row k is stored at row b_rows[k] of B
     int M, N, K;
     int lda, ldb, ldc;
     int k_chunk;               // reduction range per blockIdx.z (K when not split)
     long long c_split_stride;  // elements between per-z outputs
     int accumulate;            // C += result instead of C = result
     int epilogue;              // 0 none, 1 tanh
-    int drop_on;               // 0 none, 1 A elements (m*K+k), 2 B elements (k*N+n), 3 C (m*N+n)
-    uint32_t drop_sid;
-    Dropout drop;
+    const uint8_t* mask;       // optional keep bits of C [M, mask_bytes] (byte n/8, bit n%8)
+    int mask_bytes;
+    float mask_scale;          // 1/(1-p)
 };
 
 constexpr int GBM = 128, GBN = 128, GBK = 16, GTHREADS = 256, GPAD = 4;
@@ -60,12 +59,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_simt_kernel(const GemmArgs g
             a_i0[i] = idx >> 2;        // m_l
             a_i1[i] = (idx & 3) << 2;  // k_l (x4)
             const int m = m0 + a_i0[i];
-            if (m < g.M) {
-                const long long row = g.a_rows ? (long long)g.a_rows[m] : (long long)m;
-                a_ptr[i] = g.A + row * g.lda;
-            } else {
-                a_ptr[i] = nullptr;
-            }
+            a_ptr[i] = (m < g.M) ? g.A + (long long)m * g.lda : nullptr;
         } else {
             a_i0[i] = idx >> 5;        // k_l
             a_i1[i] = (idx & 31) << 2;  // m_l (x4)
@@ -89,14 +83,7 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_simt_kernel(const GemmArgs g
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (A_KC) {
                 const int k = k0 + a_i1[i];
-                if (a_ptr[i] && k < kend) {
-                    v = __ldg(reinterpret_cast<const float4*>(a_ptr[i] + k));
-                    if (g.drop_on == 1) {
-                        const float4 mk = g.drop.mult4(
-                            g.drop_sid, (uint64_t)(m0 + a_i0[i]) * (uint64_t)g.K + (uint64_t)k);
-                        v.x *= mk.x; v.y *= mk.y; v.z *= mk.z; v.w *= mk.w;
-                    }
-                }
+                if (a_ptr[i] && k < kend) v = __ldg(reinterpret_cast<const float4*>(a_ptr[i] + k));
             } else {
                 const int k = k0 + a_i0[i];
                 if (a_ptr[i] && k < kend)
@@ -109,15 +96,8 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_simt_kernel(const GemmArgs g
                 if (b_ptr[i] && k < kend) w = __ldg(reinterpret_cast<const float4*>(b_ptr[i] + k));
             } else {
                 const int k = k0 + b_i0[i];
-                if (b_ptr[i] && k < kend) {
-                    const long long row = g.b_rows ? (long long)g.b_rows[k] : (long long)k;
-                    w = __ldg(reinterpret_cast<const float4*>(b_ptr[i] + row * g.ldb));
-                    if (g.drop_on == 2) {
-                        const float4 mk = g.drop.mult4(
-                            g.drop_sid, (uint64_t)k * (uint64_t)g.N + (uint64_t)(n0 + b_i1[i]));
-                        w.x *= mk.x; w.y *= mk.y; w.z *= mk.z; w.w *= mk.w;
-                    }
-                }
+                if (b_ptr[i] && k < kend)
+                    w = __ldg(reinterpret_cast<const float4*>(b_ptr[i] + (long long)k * g.ldb));
             }
             rb[i] = w;
         }
@@ -198,10 +178,12 @@ __global__ void __launch_bounds__(GTHREADS, 2) gemm_simt_kernel(const GemmArgs g
             if (g.epilogue == 1) {
                 v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w);
             }
-            if (g.drop_on == 3) {
-                const float4 mk =
-                    g.drop.mult4(g.drop_sid, (uint64_t)m * (uint64_t)g.N + (uint64_t)n);
-                v.x *= mk.x; v.y *= mk.y; v.z *= mk.z; v.w *= mk.w;
+            if (g.mask) {
+                const uint32_t bits = (uint32_t)g.mask[(long long)m * g.mask_bytes + (n >> 3)] >> (n & 7);
+                v.x = (bits & 1u) ? v.x * g.mask_scale : 0.f;
+                v.y = (bits & 2u) ? v.y * g.mask_scale : 0.f;
+                v.z = (bits & 4u) ? v.z * g.mask_scale : 0.f;
+                v.w = (bits & 8u) ? v.w * g.mask_scale : 0.f;
             }
             float4* dst = reinterpret_cast<float4*>(C + (long long)m * g.ldc + n);
             if (g.accumulate) {

@@ -5,19 +5,23 @@
 //   out = sum_l w_l ctx_l
 #pragma once
 #include "common.cuh"
+#include "gemm_img.cuh"
 
 namespace nrms {
 
 struct PoolArgs {
-    const float* ctx;   // [M, D]
-    const float* t;     // [M, Q]
-    const float* q;     // [Q]
-    float* w;           // [n_seq, L]  fwd out / bwd in
-    float* out;         // [n_seq, D]  fwd out
-    const float* d_out; // [n_seq, D]  bwd in
-    float* d_ctx;       // [M, D]      bwd out: w_l * d_out (projection path is added by the GEMM)
-    float* d_pre;       // [M, Q]      bwd out: grad wrt pre-tanh activations
-    float* d_part;      // [n_seq, 2Q] bwd out: per-sequence partials of (d_b_a | d_q)
+    const float* ctx;    // [M, D]
+    const float* t;      // [M, Q]
+    const float* q;      // [Q]
+    const float* score;  // [M] a_l = t_l . q when the projection GEMM's epilogue already made it, else nullptr
+    float* w;            // [n_seq, L]  fwd out / bwd in
+    float* out;          // [n_seq, D]  fwd out
+    const float* d_out;  // [n_seq, D]  bwd in
+    float* d_ctx;        // [M, D]      bwd out: w_l * d_out (projection path is added by the GEMM)
+    float* d_pre;        // [M, Q]      bwd out (optional): grad wrt pre-tanh activations, fp32
+    ig::Img d_pre_img;   //             bwd out (optional): the same as a split-bf16 image
+    float* d_part;       // [n_seq, 2Q] bwd out: per-sequence partials of (d_b_a | d_q)
+    long long M;
     int L, D, Q;
 };
 
@@ -27,12 +31,16 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolArgs p) {
     const int seq = blockIdx.x, L = p.L, D = p.D, Q = p.Q;
     const long long row0 = (long long)seq * L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int l = warp; l < L; l += nw) {
-        const float* tr = p.t + (row0 + l) * Q;
-        float s = 0.f;
-        for (int j = lane; j < Q; j += 32) s = fmaf(__ldg(tr + j), __ldg(p.q + j), s);
-        s = warp_sum(s);
-        if (lane == 0) sw[l] = s;
+    if (p.score) {
+        for (int l = threadIdx.x; l < L; l += blockDim.x) sw[l] = p.score[row0 + l];
+    } else {
+        for (int l = warp; l < L; l += nw) {
+            const float* tr = p.t + (row0 + l) * Q;
+            float s = 0.f;
+            for (int j = lane; j < Q; j += 32) s = fmaf(__ldg(tr + j), __ldg(p.q + j), s);
+            s = warp_sum(s);
+            if (lane == 0) sw[l] = s;
+        }
     }
     __syncthreads();
     if (warp == 0) {
@@ -55,9 +63,14 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolArgs p) {
     }
     __syncthreads();
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float acc = 0.f;
-        for (int l = 0; l < L; ++l) acc = fmaf(sw[l], __ldg(p.ctx + (row0 + l) * D + d), acc);
-        p.out[(long long)seq * D + d] = acc;
+        float acc0 = 0.f, acc1 = 0.f;
+        int l = 0;
+        for (; l + 1 < L; l += 2) {
+            acc0 = fmaf(sw[l], __ldg(p.ctx + (row0 + l) * D + d), acc0);
+            acc1 = fmaf(sw[l + 1], __ldg(p.ctx + (row0 + l + 1) * D + d), acc1);
+        }
+        if (l < L) acc0 = fmaf(sw[l], __ldg(p.ctx + (row0 + l) * D + d), acc0);
+        p.out[(long long)seq * D + d] = acc0 + acc1;
     }
 }
 
@@ -95,20 +108,63 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
     for (int l = threadIdx.x; l < L; l += blockDim.x) sda[l] = sw[l] * (sda[l] - dot);
     __syncthreads();
     // d_ctx (pooling path)
-    for (int i = threadIdx.x; i < L * D; i += blockDim.x) {
-        const int l = i / D, d = i - l * D;
-        p.d_ctx[(row0 + l) * D + d] = sw[l] * __ldg(go + d);
+    {
+        const int d4n = D >> 2;
+        for (int i = threadIdx.x; i < L * d4n; i += blockDim.x) {
+            const int l = i / d4n, d = (i - l * d4n) << 2;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(go + d));
+            const float wl = sw[l];
+            *reinterpret_cast<float4*>(p.d_ctx + (row0 + l) * D + d) = make_float4(wl * g.x, wl * g.y, wl * g.z, wl * g.w);
+        }
     }
-    // d_pre and the bias / query-vector partials
+    // d_pre = da_l * q_j * (1 - t^2), coalesced 2-column units (fp32 and/or image)
+    const bool img = p.d_pre_img.hi != nullptr;
+    {
+        const int q2 = Q >> 1;
+        for (int i = threadIdx.x; i < L * q2; i += blockDim.x) {
+            const int l = i / q2, j = (i - l * q2) << 1;
+            const float2 tv = __ldg(reinterpret_cast<const float2*>(p.t + (row0 + l) * Q + j));
+            const float2 qv = __ldg(reinterpret_cast<const float2*>(p.q + j));
+            const float da = sda[l];
+            const float2 dp = make_float2(da * qv.x * (1.f - tv.x * tv.x), da * qv.y * (1.f - tv.y * tv.y));
+            if (p.d_pre) *reinterpret_cast<float2*>(p.d_pre + (row0 + l) * Q + j) = dp;
+            if (img) {
+                __nv_bfloat16 h0b, l0b, h1b, l1b;
+                tc::split_bf16(dp.x, h0b, l0b);
+                tc::split_bf16(dp.y, h1b, l1b);
+                const long long off = ig::img_unit_off(p.d_pre_img.chunk_stride, row0 + l, j >> 3) + (j & 7) * 2;
+                *reinterpret_cast<uint32_t*>(p.d_pre_img.hi + off) =
+                    (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+                *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) =
+                    (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+            }
+        }
+        if (img) {
+            // zero padding: columns [Q, 16*ceil(Q/16)) feed the data-gradient GEMM's last k-step,
+            // rows [M, rows_pad) the weight-gradient reduction
+            const int cpad = ceil_div(Q, 16) * 16 - Q;   // even (Q % 4 == 0)
+            for (int i = threadIdx.x; i < L * (cpad >> 1); i += blockDim.x) {
+                const int l = i / (cpad >> 1), j = Q + ((i - l * (cpad >> 1)) << 1);
+                const long long off = ig::img_unit_off(p.d_pre_img.chunk_stride, row0 + l, j >> 3) + (j & 7) * 2;
+                *reinterpret_cast<uint32_t*>(p.d_pre_img.hi + off) = 0u;
+                *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) = 0u;
+            }
+            if (seq == (int)gridDim.x - 1) {
+                const int groups = p.d_pre_img.chunks * 8;
+                const long long npad = p.d_pre_img.rows_pad - p.M;
+                for (long long i = threadIdx.x; i < npad * groups; i += blockDim.x)
+                    ig::img_store8_zero(p.d_pre_img, p.M + i / groups, (int)(i % groups));
+            }
+        }
+    }
+    // bias / query-vector partials (fixed summation order over l)
     for (int j = threadIdx.x; j < Q; j += blockDim.x) {
         const float qj = __ldg(p.q + j);
         float db = 0.f, dq = 0.f;
         for (int l = 0; l < L; ++l) {
             const float tv = __ldg(p.t + (row0 + l) * Q + j);
             const float da = sda[l];
-            const float dp = da * qj * (1.f - tv * tv);
-            p.d_pre[(row0 + l) * Q + j] = dp;
-            db += dp;
+            db += da * qj * (1.f - tv * tv);
             dq = fmaf(da, tv, dq);
         }
         p.d_part[(long long)seq * 2 * Q + j] = db;

@@ -348,10 +348,18 @@ __global__ void gather_rows_kernel(const T* __restrict__ src, long long n_src, i
     }
 }
 
-__global__ void dropout_mask_kernel(Dropout dr, uint32_t sid, long long n, float* out) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (long long)gridDim.x * blockDim.x)
-        out[i] = dr.enabled() ? dr.mult(sid, (uint64_t)i) : 1.f;
+// test hook: the multiplier (0 or 1/(1-p)) the encoder kernels apply to element (r, c)
+__global__ void dropout_mask_kernel(Dropout dr, uint32_t sid, long long n_rows, int n_cols, float* out) {
+    const int groups = ceil_div(n_cols, 8);
+    const long long total = n_rows * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int g = (int)(i - r * groups);
+        const uint32_t keep = dr.enabled() ? dr.keep8(sid, (uint64_t)r, (uint32_t)g) : 0xffu;
+        for (int j = 0; j < 8 && g * 8 + j < n_cols; ++j)
+            out[r * n_cols + g * 8 + j] = ((keep >> j) & 1u) ? dr.scale : 0.f;
+    }
 }
 
 __global__ void validate_ids_kernel(const int64_t* ids, long long n, long long vocab,

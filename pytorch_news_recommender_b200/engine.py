@@ -73,7 +73,7 @@ class NewsEncodeFn(torch.autograd.Function):
         shape = EncoderShape(n_seq, L, D, n_heads, Q, table.shape[0])
         flat = pack_params(params)
         # a private saved blob per call: several encoder calls may be alive in one graph
-        saved = torch.empty(ops.saved_bytes(shape), dtype=torch.uint8, device=table.device)
+        saved = torch.empty(ops.saved_bytes(shape, gemm_mode), dtype=torch.uint8, device=table.device)
         out = ops.news_encoder_fwd(shape, ids, table.detach(), flat, saved, dropout_p, seed, gemm_mode)
         ctx.shape, ctx.dropout_p, ctx.seed, ctx.gemm_mode = shape, dropout_p, seed, gemm_mode
         ctx.save_for_backward(ids, table, flat, saved)
@@ -85,7 +85,7 @@ class NewsEncodeFn(torch.autograd.Function):
         ids, table, flat, saved = ctx.saved_tensors
         shape = ctx.shape
         dev = table.device
-        scratch = _blobs.get("news_scratch", ops.scratch_bytes(shape), dev)
+        scratch = _blobs.get("news_scratch", ops.scratch_bytes(shape, ctx.gemm_mode), dev)
         d_flat = torch.empty_like(flat)
         M = shape.n_seq * shape.seq_len
         d_rows = torch.empty((M, shape.d_model), dtype=torch.float32, device=dev)
@@ -113,7 +113,7 @@ class UserEncodeFn(torch.autograd.Function):
         Q = params[8].numel()
         shape = EncoderShape(n_seq, L, D, n_heads, Q, 0)
         flat = pack_params(params)
-        saved = torch.empty(ops.saved_bytes(shape), dtype=torch.uint8, device=x.device)
+        saved = torch.empty(ops.saved_bytes(shape, gemm_mode), dtype=torch.uint8, device=x.device)
         out = ops.user_encoder_fwd(shape, x, flat, saved, gemm_mode)
         ctx.shape, ctx.gemm_mode = shape, gemm_mode
         ctx.save_for_backward(x, flat, saved)
@@ -124,7 +124,7 @@ class UserEncodeFn(torch.autograd.Function):
     def backward(ctx, d_out):
         x, flat, saved = ctx.saved_tensors
         shape = ctx.shape
-        scratch = _blobs.get("user_scratch", ops.scratch_bytes(shape), x.device)
+        scratch = _blobs.get("user_scratch", ops.scratch_bytes(shape, ctx.gemm_mode), x.device)
         d_flat = torch.empty_like(flat)
         d_x = torch.empty_like(x)
         ops.user_encoder_bwd(shape, x, flat, d_out.contiguous(), saved, scratch, d_flat, d_x,
@@ -264,10 +264,10 @@ class FusedTrainer:
         news_shape = EncoderShape(n_titles, T, D, h, Q, V)
         user_shape = EncoderShape(B, H, D, h, Q, 0)
         news_flat, user_flat = self.flat[:self.n_enc], self.flat[self.n_enc:]
-        news_saved = self.blobs.get("news_saved", ops.saved_bytes(news_shape), dev)
-        user_saved = self.blobs.get("user_saved", ops.saved_bytes(user_shape), dev)
-        news_scratch = self.blobs.get("scratch", max(ops.scratch_bytes(news_shape),
-                                                     ops.scratch_bytes(user_shape)), dev)
+        news_saved = self.blobs.get("news_saved", ops.saved_bytes(news_shape, gm), dev)
+        user_saved = self.blobs.get("user_saved", ops.saved_bytes(user_shape, gm), dev)
+        news_scratch = self.blobs.get("scratch", max(ops.scratch_bytes(news_shape, gm),
+                                                     ops.scratch_bytes(user_shape, gm)), dev)
         table = self.table.data
         # ---- forward ----------------------------------------------------------------------
         ops.news_encoder_fwd(news_shape, b["ids"], table, news_flat, news_saved, p, seed, gm,

@@ -53,15 +53,15 @@ def encoder_param_count(d_model: int, d_query: int) -> int:
     return int(_lib.load().nrms_encoder_param_count(d_model, d_query))
 
 
-def saved_bytes(shape: EncoderShape) -> int:
-    n = int(_lib.load().nrms_encoder_saved_bytes(shape.dims()))
+def saved_bytes(shape: EncoderShape, gemm_mode: int = 0) -> int:
+    n = int(_lib.load().nrms_encoder_saved_bytes(shape.dims(gemm_mode=gemm_mode)))
     if n < 0:
         check(-1, "nrms_encoder_saved_bytes")
     return n
 
 
-def scratch_bytes(shape: EncoderShape) -> int:
-    n = int(_lib.load().nrms_encoder_scratch_bytes(shape.dims()))
+def scratch_bytes(shape: EncoderShape, gemm_mode: int = 0) -> int:
+    n = int(_lib.load().nrms_encoder_scratch_bytes(shape.dims(gemm_mode=gemm_mode)))
     if n < 0:
         check(-1, "nrms_encoder_scratch_bytes")
     return n
@@ -219,10 +219,32 @@ def gather_rows(src, idx, base: int = 0):
     return out
 
 
-def dropout_mask(seed: int, stream_id: int, p: float, n: int, device) -> torch.Tensor:
-    out = torch.empty(n, dtype=torch.float32, device=device)
-    check(_lib.load().nrms_dropout_mask(int(seed) & (2**64 - 1), stream_id, float(p), n, ptr(out),
-                                        _stream()), "nrms_dropout_mask")
+def dropout_mask(seed: int, stream_id: int, p: float, n_rows: int, n_cols: int, device) -> torch.Tensor:
+    """The multipliers (0 or 1/(1-p)) the encoder kernels apply to a [n_rows, n_cols] activation."""
+    out = torch.empty((n_rows, n_cols), dtype=torch.float32, device=device)
+    check(_lib.load().nrms_dropout_mask(int(seed) & (2**64 - 1), stream_id, float(p), n_rows, n_cols,
+                                        ptr(out), _stream()), "nrms_dropout_mask")
+    return out
+
+
+def gemm_selftest(variant: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """tcgen05 GEMM layer self-test (see include/nrms_b200.h: nrms_gemm_selftest)."""
+    _require_cuda(A, B)
+    A, B = _cf32(A), _cf32(B)
+    if variant == 0:
+        (M, K), N = A.shape, B.shape[0]
+    elif variant == 1:
+        (M, K), N = A.shape, B.shape[1]
+    else:
+        (K, M), N = A.shape, B.shape[1]
+    lib = _lib.load()
+    nbytes = int(lib.nrms_gemm_selftest_bytes(variant, M, N, K))
+    if nbytes < 0:
+        raise NrmsError("nrms_gemm_selftest_bytes: bad shape")
+    work = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    check(lib.nrms_gemm_selftest(variant, ptr(A), ptr(B), ptr(out), M, N, K, ptr(work), nbytes, _stream()),
+          "nrms_gemm_selftest")
     return out
 
 

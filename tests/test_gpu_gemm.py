@@ -1,0 +1,41 @@
+"""GPU tests of the tcgen05 GEMM layer (gemm_img.cuh) through the C-ABI self-test hook: the three
+operand orientations of the path (forward, data gradient, weight gradient) against float64
+matmul, at the path's shapes and at ragged ones.  bf16x3 is fp32-grade: tolerance 2e-5 of the
+output scale (plain bf16 would sit near 4e-3)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(got, want, what):
+    scale = want.abs().max().item()
+    err = (got.double() - want).abs().max().item()
+    assert err <= 2e-5 * scale, f"{what}: max err {err:.3e} vs scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 240, 64), (300, 900, 300), (1000, 200, 300), (77, 60, 20), (4096, 900, 300)])
+def test_forward_orientation(M, N, K, built_lib):
+    from pytorch_news_recommender_b200 import ops
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    _check(ops.gemm_selftest(0, A, B), A.double() @ B.double().t(), f"NT {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 320, 64), (300, 300, 900), (1000, 300, 200), (77, 20, 60), (4096, 300, 900)])
+def test_data_gradient_orientation(M, N, K, built_lib):
+    from pytorch_news_recommender_b200 import ops
+    torch.manual_seed(M + N + K + 1)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(K, N, device="cuda")
+    _check(ops.gemm_selftest(1, A, B), A.double() @ B.double(), f"NN {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 320, 64), (900, 300, 3000), (200, 300, 3000), (60, 20, 130), (900, 300, 105600)])
+def test_weight_gradient_orientation(M, N, K, built_lib):
+    from pytorch_news_recommender_b200 import ops
+    torch.manual_seed(M + N + K + 2)
+    A = torch.randn(K, M, device="cuda")
+    B = torch.randn(K, N, device="cuda")
+    _check(ops.gemm_selftest(2, A, B), A.double().t() @ B.double(), f"TN {M}x{N}x{K}")

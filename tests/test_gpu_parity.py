@@ -104,9 +104,9 @@ def test_dropin_backward_matches_reference(name, gemm_mode, built_lib):
 
 def _kernel_masks(cfg, c, seed):
     from pytorch_news_recommender_b200 import ops
-    n = c.B * (c.C + c.H) * c.T * c.D
-    m1 = ops.dropout_mask(seed, ops.DROP_EMBEDDING, cfg.dropout, n, "cuda:0").view(-1, c.T, c.D).cpu()
-    m2 = ops.dropout_mask(seed, ops.DROP_CONTEXT, cfg.dropout, n, "cuda:0").view(-1, c.T, c.D).cpu()
+    n = c.B * (c.C + c.H) * c.T
+    m1 = ops.dropout_mask(seed, ops.DROP_EMBEDDING, cfg.dropout, n, c.D, "cuda:0").view(-1, c.T, c.D).cpu()
+    m2 = ops.dropout_mask(seed, ops.DROP_CONTEXT, cfg.dropout, n, c.D, "cuda:0").view(-1, c.T, c.D).cpu()
     return m1, m2
 
 
