@@ -50,28 +50,40 @@ __host__ __device__ inline size_t attn_bwd_smem_bytes(int L, int hpb) {
     return (size_t)4 * hpb * L * kRowStride * sizeof(float);
 }
 
-// Cooperative coalesced load of `ncol` columns starting at `col0` of rows [row0, row0+L) of a
+__device__ __forceinline__ void cp_async8(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Asynchronous (cp.async) load of `ncol` columns starting at `col0` of rows [row0, row0+L) of a
 // row-major matrix with leading dimension ld into dst[(hh*L + l)*kRowStride + d] (column c ->
-// head hh = c/dk, d = c%dk), scaled by mul, pad lanes d in [dk, 32) zeroed.  8-byte units when
-// VEC2 (dk, col0 and ld even), scalar otherwise.
+// head hh = c/dk, d = c%dk); pad lanes d in [dk, 32) are zeroed with plain stores.  A thread
+// owns a 2-column unit (8 bytes; 1 column when !VEC2) and walks the rows, so the copies of a
+// warp are coalesced, there is no per-element index arithmetic and nothing waits until
+// cp_async_wait_all().
 template <bool VEC2>
-__device__ __forceinline__ void load_heads(float* dst, const float* src, long long row0, int ld,
-                                           int col0, int L, int dk, int hpb, float mul) {
+__device__ __forceinline__ void load_heads_async(float* dst, const float* src, long long row0, int ld,
+                                                 int col0, int L, int dk, int hpb) {
     const int ncol = hpb * dk;
-    if (VEC2) {
-        const int n2 = ncol >> 1;
-        for (int i = threadIdx.x; i < L * n2; i += blockDim.x) {
-            const int l = i / n2, c = (i - l * n2) << 1;
-            const int hh = c / dk, d = c - hh * dk;
-            float2 v = __ldg(reinterpret_cast<const float2*>(src + (row0 + l) * ld + col0 + c));
-            v.x *= mul; v.y *= mul;
-            *reinterpret_cast<float2*>(dst + (hh * L + l) * kRowStride + d) = v;
-        }
-    } else {
-        for (int i = threadIdx.x; i < L * ncol; i += blockDim.x) {
-            const int l = i / ncol, c = i - l * ncol;
-            const int hh = c / dk, d = c - hh * dk;
-            dst[(hh * L + l) * kRowStride + d] = __ldg(src + (row0 + l) * ld + col0 + c) * mul;
+    const int nu = VEC2 ? ncol >> 1 : ncol;
+    for (int u = threadIdx.x; u < nu; u += blockDim.x) {
+        const int c = VEC2 ? u << 1 : u;
+        const int hh = c / dk, d = c - hh * dk;
+        const float* g = src + row0 * ld + col0 + c;
+        float* t = dst + (size_t)hh * L * kRowStride + d;
+#pragma unroll 4
+        for (int l = 0; l < L; ++l) {
+            if (VEC2) cp_async8(t + l * kRowStride, g + (long long)l * ld);
+            else cp_async4(t + l * kRowStride, g + (long long)l * ld);
         }
     }
     const int npad = kDkPad - dk;
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
     const int h0 = blockIdx.y * a.hpb;
     const int hpb = min(a.hpb, a.n_heads - h0);
     const size_t per = (size_t)a.hpb * L * kRowStride;
-    float* Qs = smem;   // scale*Q, later the normalised output O
+    float* Qs = smem;   // Q, later the normalised output O
     float* Ks = Qs + per;
     float* Vs = Ks + per;
     uint8_t* s_mask = reinterpret_cast<uint8_t*>(Vs + per);   // [L][64] keep bytes (dropout only)
@@ -116,9 +128,9 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
     const int ld = 3 * D;
     const int col0 = h0 * dk, ncol = hpb * dk;
 
-    load_heads<VEC2>(Qs, a.qkv, row0, ld, col0, L, dk, hpb, a.scale);
-    load_heads<VEC2>(Ks, a.qkv, row0, ld, D + col0, L, dk, hpb, 1.f);
-    load_heads<VEC2>(Vs, a.qkv, row0, ld, 2 * D + col0, L, dk, hpb, 1.f);
+    load_heads_async<VEC2>(Qs, a.qkv, row0, ld, col0, L, dk, hpb);
+    load_heads_async<VEC2>(Ks, a.qkv, row0, ld, D + col0, L, dk, hpb);
+    load_heads_async<VEC2>(Vs, a.qkv, row0, ld, 2 * D + col0, L, dk, hpb);
     if (a.drop.enabled()) {
         // keep bits of the 8-column groups overlapping this CTA's columns: one Philox call each
         const int g0 = col0 >> 3, g1 = (col0 + ncol + 7) >> 3;
@@ -131,6 +143,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
             if (a.cmask && g < a.mask_bytes) a.cmask[(row0 + l) * a.mask_bytes + g] = (uint8_t)keep;
         }
     }
+    cp_async_wait_all();
     __syncthreads();
 
     const int unit = threadIdx.x / U, ul = threadIdx.x % U;
@@ -144,7 +157,10 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
         load_row32(q0, Qs + (size_t)(hh * L + (act0 ? r0 : 0)) * kRowStride);
         load_row32(q1, Qs + (size_t)(hh * L + (act1 ? r1 : 0)) * kRowStride);
 #pragma unroll
-        for (int d = 0; d < kDkPad; ++d) { acc0[d] = 0.f; acc1[d] = 0.f; }
+        for (int d = 0; d < kDkPad; ++d) {
+            q0[d] *= a.scale; q1[d] *= a.scale;   // scores = (Q K^T) / sqrt(d_k)  (nrms_v0.py:14)
+            acc0[d] = 0.f; acc1[d] = 0.f;
+        }
         float m0 = -INFINITY, m1 = -INFINITY, den0 = 0.f, den1 = 0.f;
         const float* kbase = Ks + (size_t)hh * L * kRowStride;
         const float* vbase = Vs + (size_t)hh * L * kRowStride;
@@ -207,37 +223,40 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
     const bool img = a.ctx_img.hi != nullptr;
     const bool drop = a.drop.enabled();
     if (VEC2) {
-        const int n2 = ncol >> 1;
-        for (int i = threadIdx.x; i < L * n2; i += blockDim.x) {
-            const int l = i / n2, c = (i - l * n2) << 1;
+        for (int u = threadIdx.x; u < (ncol >> 1); u += blockDim.x) {
+            const int c = u << 1;
             const int hh = c / dk, d = c - hh * dk;
-            float2 v = *reinterpret_cast<const float2*>(Qs + (size_t)(hh * L + l) * kRowStride + d);
             const int col = col0 + c;
-            if (drop) {
-                const uint32_t keep = (uint32_t)s_mask[l * 64 + (col >> 3)] >> (col & 7);
-                v.x = (keep & 1u) ? v.x * a.drop.scale : 0.f;
-                v.y = (keep & 2u) ? v.y * a.drop.scale : 0.f;
-            }
-            *reinterpret_cast<float2*>(a.ctx + (row0 + l) * D + col) = v;
-            if (img) {
-                __nv_bfloat16 h0b, l0b, h1b, l1b;
-                tc::split_bf16(v.x, h0b, l0b);
-                tc::split_bf16(v.y, h1b, l1b);
-                const long long off = ig::img_unit_off(a.ctx_img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
-                *reinterpret_cast<uint32_t*>(a.ctx_img.hi + off) =
-                    (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-                *reinterpret_cast<uint32_t*>(a.ctx_img.lo + off) =
-                    (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+            const float* srow = Qs + (size_t)hh * L * kRowStride + d;
+            for (int l = 0; l < L; ++l) {
+                float2 v = *reinterpret_cast<const float2*>(srow + l * kRowStride);
+                if (drop) {
+                    const uint32_t keep = (uint32_t)s_mask[l * 64 + (col >> 3)] >> (col & 7);
+                    v.x = (keep & 1u) ? v.x * a.drop.scale : 0.f;
+                    v.y = (keep & 2u) ? v.y * a.drop.scale : 0.f;
+                }
+                *reinterpret_cast<float2*>(a.ctx + (row0 + l) * D + col) = v;
+                if (img) {
+                    __nv_bfloat16 h0b, l0b, h1b, l1b;
+                    tc::split_bf16(v.x, h0b, l0b);
+                    tc::split_bf16(v.y, h1b, l1b);
+                    const long long off = ig::img_unit_off(a.ctx_img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
+                    *reinterpret_cast<uint32_t*>(a.ctx_img.hi + off) =
+                        (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+                    *reinterpret_cast<uint32_t*>(a.ctx_img.lo + off) =
+                        (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+                }
             }
         }
     } else {
-        for (int i = threadIdx.x; i < L * ncol; i += blockDim.x) {
-            const int l = i / ncol, c = i - l * ncol;
+        for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
             const int hh = c / dk, d = c - hh * dk;
-            float v = Qs[(size_t)(hh * L + l) * kRowStride + d];
             const int col = col0 + c;
-            if (drop) v = ((s_mask[l * 64 + (col >> 3)] >> (col & 7)) & 1u) ? v * a.drop.scale : 0.f;
-            a.ctx[(row0 + l) * D + col] = v;
+            for (int l = 0; l < L; ++l) {
+                float v = Qs[(size_t)(hh * L + l) * kRowStride + d];
+                if (drop) v = ((s_mask[l * 64 + (col >> 3)] >> (col & 7)) & 1u) ? v * a.drop.scale : 0.f;
+                a.ctx[(row0 + l) * D + col] = v;
+            }
         }
     }
     if (img) {
@@ -273,7 +292,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
     const int h0 = blockIdx.y * a.hpb;
     const int hpb = min(a.hpb, a.n_heads - h0);
     const size_t per = (size_t)a.hpb * L * kRowStride;
-    float* Qs = smem;  // holds scale*Q
+    float* Qs = smem;  // Q (unscaled)
     float* Ks = Qs + per;
     float* Vs = Ks + per;
     float* Gs = Vs + per;  // dO (grad wrt pre-dropout context); spare columns 32,33: delta, lse
@@ -285,10 +304,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
     // phase 0: dO = d_ctx * mask -> Gs, post-dropout context -> Qs (temporarily), then
     // delta_i = sum_d dO_raw * O_raw = (sum_d dO * ctx_post) / drop.scale, one (head,row) per
     // thread in a fixed order (deterministic; no atomics)
-    load_heads<VEC2>(Ks, a.qkv, row0, ld, D + col0, L, dk, hpb, 1.f);
-    load_heads<VEC2>(Vs, a.qkv, row0, ld, 2 * D + col0, L, dk, hpb, 1.f);
-    load_heads<VEC2>(Qs, a.ctx, row0, D, col0, L, dk, hpb, 1.f);
-    load_heads<VEC2>(Gs, a.d_ctx, row0, D, col0, L, dk, hpb, 1.f);
+    load_heads_async<VEC2>(Ks, a.qkv, row0, ld, D + col0, L, dk, hpb);
+    load_heads_async<VEC2>(Vs, a.qkv, row0, ld, 2 * D + col0, L, dk, hpb);
+    load_heads_async<VEC2>(Qs, a.ctx, row0, D, col0, L, dk, hpb);
+    load_heads_async<VEC2>(Gs, a.d_ctx, row0, D, col0, L, dk, hpb);
+    cp_async_wait_all();
     __syncthreads();
     const float inv_drop = drop ? 1.f / a.drop.scale : 1.f;
     for (int i = threadIdx.x; i < hpb * L; i += blockDim.x) {
@@ -314,7 +334,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
         g[kDkPad + 1] = a.lse[(row0 + l) * a.n_heads + h0 + hh];
     }
     __syncthreads();
-    load_heads<VEC2>(Qs, a.qkv, row0, ld, col0, L, dk, hpb, a.scale);
+    load_heads_async<VEC2>(Qs, a.qkv, row0, ld, col0, L, dk, hpb);
+    cp_async_wait_all();
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,6 +359,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
         float q[kDkPad], go[kDkPad];
         load_row32(q, qb + ii * kRowStride);
         load_row32(go, gb + ii * kRowStride);
+#pragma unroll
+        for (int d = 0; d < kDkPad; ++d) q[d] *= a.scale;
         const float delta = gb[ii * kRowStride + kDkPad];
         const float lse = gb[ii * kRowStride + kDkPad + 1];
 #pragma unroll
@@ -378,7 +401,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
         if (has_task) {
 #pragma unroll 2
             for (int r = 0; r < L; ++r) {
-                const float* qr = qb + r * kRowStride;  // scale*Q_r
+                const float* qr = qb + r * kRowStride;  // Q_r (unscaled)
                 const float* gr = gb + r * kRowStride;
                 float s = 0.f, dp = 0.f;
                 float qreg[kDkPad], greg[kDkPad];
@@ -396,8 +419,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
                     dp = fmaf(gv.z, v[4 * c + 2], dp); dp = fmaf(gv.w, v[4 * c + 3], dp);
                 }
                 const float delta = gr[kDkPad], lse = gr[kDkPad + 1];
-                const float p = __expf(s - lse);
-                const float ds = p * (dp - delta);  // qreg already carries `scale`
+                const float p = __expf(s * a.scale - lse);
+                const float ds = p * (dp - delta) * a.scale;
 #pragma unroll
                 for (int d = 0; d < kDkPad; ++d) {
                     dvv[d] = fmaf(p, greg[d], dvv[d]);
@@ -413,17 +436,22 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
         store_row32(Vs + (size_t)(hh * L + i) * kRowStride, dvv, 1.f);
     }
     __syncthreads();
-    // coalesced write-out of dQ|dK|dV and the per-sequence column sums (bias gradients)
+    // write-out of dQ|dK|dV and the per-sequence column sums (bias gradients)
     const bool img = a.d_qkv_img.hi != nullptr;
-    for (int third = 0; third < 3; ++third) {
-        const float* src = smem + third * per;
-        if (VEC2) {
-            const int n2 = ncol >> 1;
-            for (int idx = threadIdx.x; idx < L * n2; idx += blockDim.x) {
-                const int l = idx / n2, c = (idx - l * n2) << 1;
-                const int h2 = c / dk, d = c - h2 * dk;
-                const float2 v = *reinterpret_cast<const float2*>(src + (size_t)(h2 * L + l) * kRowStride + d);
-                const int col = third * D + col0 + c;
+    // a thread owns a 2-column unit of one third and walks the rows: coalesced 8-byte stores, the
+    // bias partial (column sum over the sequence) falls out of the same walk in a fixed order
+    const int nu = VEC2 ? ncol >> 1 : ncol;
+    for (int u = threadIdx.x; u < 3 * nu; u += blockDim.x) {
+        const int third = u / nu;
+        const int c = VEC2 ? (u - third * nu) << 1 : (u - third * nu);
+        const int h2 = c / dk, d = c - h2 * dk;
+        const int col = third * D + col0 + c;
+        const float* srow = smem + third * per + (size_t)h2 * L * kRowStride + d;
+        float sum0 = 0.f, sum1 = 0.f;
+        for (int l = 0; l < L; ++l) {
+            if (VEC2) {
+                const float2 v = *reinterpret_cast<const float2*>(srow + l * kRowStride);
+                sum0 += v.x; sum1 += v.y;
                 if (a.d_qkv) *reinterpret_cast<float2*>(a.d_qkv + (row0 + l) * ld + col) = v;
                 if (img) {
                     __nv_bfloat16 h0b, l0b, h1b, l1b;
@@ -435,21 +463,14 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
                     *reinterpret_cast<uint32_t*>(a.d_qkv_img.lo + off) =
                         (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
                 }
-            }
-        } else {
-            for (int idx = threadIdx.x; idx < L * ncol; idx += blockDim.x) {
-                const int l = idx / ncol, c = idx - l * ncol;
-                const int h2 = c / dk, d = c - h2 * dk;
-                if (a.d_qkv)
-                    a.d_qkv[(row0 + l) * ld + third * D + col0 + c] = src[(size_t)(h2 * L + l) * kRowStride + d];
+            } else {
+                const float v = srow[l * kRowStride];
+                sum0 += v;
+                if (a.d_qkv) a.d_qkv[(row0 + l) * ld + col] = v;
             }
         }
-        for (int c = threadIdx.x; c < ncol; c += blockDim.x) {
-            const int h2 = c / dk, d = c - h2 * dk;
-            float sum = 0.f;
-            for (int l = 0; l < L; ++l) sum += src[(size_t)(h2 * L + l) * kRowStride + d];
-            a.d_bias_part[(long long)seq * ld + third * D + col0 + c] = sum;
-        }
+        a.d_bias_part[(long long)seq * ld + col] = sum0;
+        if (VEC2) a.d_bias_part[(long long)seq * ld + col + 1] = sum1;
     }
     if (img) {
         // image padding: columns [3D, 16*ceil(3D/16)) are read by the data-gradient GEMM's last
