@@ -689,7 +689,10 @@ int nrms_embedding_plan(const int64_t* ids, int64_t n_rows, int32_t vocab, void*
     PlanView v = plan_view(plan, n_rows, vocab);
     NRMS_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int32_t) * vocab, s));
     NRMS_LAUNCH("plan_hist", s, plan_hist_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.counts));
-    NRMS_LAUNCH("plan_scan", s, plan_scan_kernel<<<1, 1024, 0, s>>>(v.counts, v.offsets, v.cursor, v.n_valid, vocab));
+    const int scan_blocks = ceil_div(vocab, kScanBlock);
+    NRMS_LAUNCH("plan_scan", s, plan_block_totals_kernel<<<scan_blocks, kScanBlock, 0, s>>>(v.counts, v.block_tot, vocab));
+    NRMS_LAUNCH("plan_scan", s, plan_scan_kernel<<<scan_blocks, kScanBlock, 0, s>>>(v.counts, v.block_tot, v.offsets, v.cursor,
+                                                                              v.n_valid, vocab));
     NRMS_LAUNCH("plan_fill", s, plan_fill_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.offsets, v.cursor,
                                                           v.perm, v.sorted_id));
     NRMS_LAUNCH("plan_sort_segments", s, plan_sort_segments_kernel<<<grid_for((long long)vocab * 32, 256), 256, 0, s>>>(v.offsets, v.perm,

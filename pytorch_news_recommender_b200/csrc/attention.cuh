@@ -366,11 +366,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
 #pragma unroll
         for (int d = 0; d < kDkPad; ++d) dq[d] = 0.f;
         if (has_task) {
-#pragma unroll 2
+#pragma unroll 1
             for (int j = 0; j < L; ++j) {
                 const float* kr = kb + j * kRowStride;
                 const float* vr = vb + j * kRowStride;
-                float s = 0.f, dp = 0.f;
+                // four partial sums per dot product: dependent FMA chains of 8, not 32
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = s4;
                 float kreg[kDkPad];
 #pragma unroll
                 for (int c = 0; c < kDkPad / 4; ++c) {
@@ -378,11 +379,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
                     const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * c);
                     kreg[4 * c] = kv.x; kreg[4 * c + 1] = kv.y; kreg[4 * c + 2] = kv.z;
                     kreg[4 * c + 3] = kv.w;
-                    s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s);
-                    s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
-                    dp = fmaf(go[4 * c], vv.x, dp); dp = fmaf(go[4 * c + 1], vv.y, dp);
-                    dp = fmaf(go[4 * c + 2], vv.z, dp); dp = fmaf(go[4 * c + 3], vv.w, dp);
+                    s4.x = fmaf(q[4 * c], kv.x, s4.x); s4.y = fmaf(q[4 * c + 1], kv.y, s4.y);
+                    s4.z = fmaf(q[4 * c + 2], kv.z, s4.z); s4.w = fmaf(q[4 * c + 3], kv.w, s4.w);
+                    d4.x = fmaf(go[4 * c], vv.x, d4.x); d4.y = fmaf(go[4 * c + 1], vv.y, d4.y);
+                    d4.z = fmaf(go[4 * c + 2], vv.z, d4.z); d4.w = fmaf(go[4 * c + 3], vv.w, d4.w);
                 }
+                const float s = (s4.x + s4.y) + (s4.z + s4.w), dp = (d4.x + d4.y) + (d4.z + d4.w);
                 const float p = __expf(s - lse);
                 const float ds = p * (dp - delta) * a.scale;
 #pragma unroll
@@ -399,11 +401,11 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
 #pragma unroll
         for (int d = 0; d < kDkPad; ++d) { dkk[d] = 0.f; dvv[d] = 0.f; }
         if (has_task) {
-#pragma unroll 2
+#pragma unroll 1
             for (int r = 0; r < L; ++r) {
                 const float* qr = qb + r * kRowStride;  // Q_r (unscaled)
                 const float* gr = gb + r * kRowStride;
-                float s = 0.f, dp = 0.f;
+                float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f), d4 = s4;
                 float qreg[kDkPad], greg[kDkPad];
 #pragma unroll
                 for (int c = 0; c < kDkPad / 4; ++c) {
@@ -413,11 +415,12 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
                     qreg[4 * c + 3] = qv.w;
                     greg[4 * c] = gv.x; greg[4 * c + 1] = gv.y; greg[4 * c + 2] = gv.z;
                     greg[4 * c + 3] = gv.w;
-                    s = fmaf(qv.x, k[4 * c], s); s = fmaf(qv.y, k[4 * c + 1], s);
-                    s = fmaf(qv.z, k[4 * c + 2], s); s = fmaf(qv.w, k[4 * c + 3], s);
-                    dp = fmaf(gv.x, v[4 * c], dp); dp = fmaf(gv.y, v[4 * c + 1], dp);
-                    dp = fmaf(gv.z, v[4 * c + 2], dp); dp = fmaf(gv.w, v[4 * c + 3], dp);
+                    s4.x = fmaf(qv.x, k[4 * c], s4.x); s4.y = fmaf(qv.y, k[4 * c + 1], s4.y);
+                    s4.z = fmaf(qv.z, k[4 * c + 2], s4.z); s4.w = fmaf(qv.w, k[4 * c + 3], s4.w);
+                    d4.x = fmaf(gv.x, v[4 * c], d4.x); d4.y = fmaf(gv.y, v[4 * c + 1], d4.y);
+                    d4.z = fmaf(gv.z, v[4 * c + 2], d4.z); d4.w = fmaf(gv.w, v[4 * c + 3], d4.w);
                 }
+                const float s = (s4.x + s4.y) + (s4.z + s4.w), dp = (d4.x + d4.y) + (d4.z + d4.w);
                 const float delta = gr[kDkPad], lse = gr[kDkPad + 1];
                 const float p = __expf(s * a.scale - lse);
                 const float ds = p * (dp - delta) * a.scale;

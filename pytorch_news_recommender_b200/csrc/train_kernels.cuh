@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a) {
 // segmented reduction (one warp per 32 sorted rows) into the dense table gradient.
 // Replaces 55 x (zero-fill [V,D] + scatter + accumulate) of the reference.
 // plan blob: int32 counts[V] | int32 offsets[V+1] | int32 cursor[V] | int32 perm[n_rows]
-//            | int32 sorted_id[n_rows] | int32 n_valid
+//            | int32 sorted_id[n_rows] | int32 n_valid | int32 block_tot[ceil(V/1024)]
 // ---------------------------------------------------------------------------------------
 struct PlanView {
     int32_t* counts;
@@ -98,9 +98,10 @@ struct PlanView {
     int32_t* perm;
     int32_t* sorted_id;
     int32_t* n_valid;
+    int32_t* block_tot;
 };
 inline int64_t plan_bytes(int64_t n_rows, int32_t vocab) {
-    return align_up((int64_t)sizeof(int32_t) * (3ll * vocab + 1 + 2 * n_rows + 4), 256);
+    return align_up((int64_t)sizeof(int32_t) * (3ll * vocab + 1 + 2 * n_rows + 4 + (vocab + 1023) / 1024), 256);
 }
 inline PlanView plan_view(void* blob, int64_t n_rows, int32_t vocab) {
     PlanView v;
@@ -111,6 +112,7 @@ inline PlanView plan_view(void* blob, int64_t n_rows, int32_t vocab) {
     v.perm = v.cursor + vocab;
     v.sorted_id = v.perm + n_rows;
     v.n_valid = v.sorted_id + n_rows;
+    v.block_tot = v.n_valid + 1;
     return v;
 }
 
@@ -123,20 +125,14 @@ __global__ void plan_hist_kernel(const int64_t* __restrict__ ids, long long n, i
     }
 }
 
-// single-CTA exclusive scan of counts[V] -> offsets[V+1]; cursor = 0; n_valid = total
-__global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restrict__ counts,
-                                                         int32_t* __restrict__ offsets,
-                                                         int32_t* __restrict__ cursor,
-                                                         int32_t* __restrict__ n_valid,
-                                                         int vocab) {
-    __shared__ int32_t warp_tot[32];
-    __shared__ int32_t carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int per = ceil_div(vocab, 1024);
-    const int beg = tid * per, end = min(vocab, beg + per);
-    int32_t local = 0;
-    for (int i = beg; i < end; ++i) local += counts[i];
-    int32_t inc = local;
+// Exclusive scan of counts[V] -> offsets[V+1] in two small launches of ceil(V/1024) CTAs:
+// (1) per-CTA totals, (2) every CTA sums the totals of the CTAs before it (at most a few hundred
+// values) and scans its own 1024 counts.  cursor = 0; n_valid = total.
+constexpr int kScanBlock = 1024;
+
+__device__ __forceinline__ int32_t block_inclusive_scan(int32_t x, int32_t* warp_tot /*[32]*/, int32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t inc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const int32_t n = __shfl_up_sync(0xffffffffu, inc, o);
@@ -145,26 +141,55 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(const int32_t* __restri
     if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        int32_t w = warp_tot[lane];
+        const int32_t w = warp_tot[lane];
         int32_t winc = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int32_t n = __shfl_up_sync(0xffffffffu, winc, o);
             if (lane >= o) winc += n;
         }
-        warp_tot[lane] = winc - w;  // exclusive
-        if (lane == 31) carry_s = winc;
+        warp_tot[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) *total = winc;
     }
     __syncthreads();
-    int32_t run = warp_tot[warp] + inc - local;
-    for (int i = beg; i < end; ++i) {
-        offsets[i] = run;
+    return inc + warp_tot[warp];
+}
+
+__global__ void __launch_bounds__(kScanBlock) plan_block_totals_kernel(const int32_t* __restrict__ counts,
+                                                                      int32_t* __restrict__ block_tot, int vocab) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t total;
+    const int i = blockIdx.x * kScanBlock + threadIdx.x;
+    block_inclusive_scan(i < vocab ? counts[i] : 0, warp_tot, &total);
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanBlock) plan_scan_kernel(const int32_t* __restrict__ counts,
+                                                              const int32_t* __restrict__ block_tot,
+                                                              int32_t* __restrict__ offsets,
+                                                              int32_t* __restrict__ cursor,
+                                                              int32_t* __restrict__ n_valid, int vocab) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t total;
+    __shared__ int32_t base_s;
+    // sum of the totals of the CTAs before this one
+    int32_t part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanBlock) part += block_tot[b];
+    block_inclusive_scan(part, warp_tot, &total);
+    if (threadIdx.x == 0) base_s = total;
+    __syncthreads();
+    const int32_t base = base_s;
+    __syncthreads();
+    const int i = blockIdx.x * kScanBlock + threadIdx.x;
+    const int32_t c = i < vocab ? counts[i] : 0;
+    const int32_t inc = block_inclusive_scan(c, warp_tot, &total);
+    if (i < vocab) {
+        offsets[i] = base + inc - c;
         cursor[i] = 0;
-        run += counts[i];
     }
-    if (tid == 0) {
-        offsets[vocab] = carry_s;
-        *n_valid = carry_s;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        offsets[vocab] = base + total;
+        *n_valid = base + total;
     }
 }
 

@@ -21,6 +21,7 @@ import torch.distributed as dist
 from . import ops
 from ._lib import NrmsError
 from .ops import BlobCache, EncoderShape
+from .parallel import GradientExchange
 
 _ENC_PARAM_ORDER = ("W_Q.weight", "W_K.weight", "W_V.weight", "W_Q.bias", "W_K.bias", "W_V.bias",
                     "linear.weight", "linear.bias", "attention_query_vector")
@@ -176,7 +177,8 @@ class FusedTrainer:
         self.lr = float(cfg.learning_rate if lr is None else lr)
         self.betas, self.eps = betas, eps
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.exchange = GradientExchange(process_group)
+        self.world = self.exchange.world
         self.table_sync = table_sync
         self.step_count = 0
         self.table = model.news_encoder.word_embedding[0].weight
@@ -289,10 +291,8 @@ class FusedTrainer:
         plan = self.blobs.get("plan", ops.embedding_plan_bytes(M, V), dev)
         ops.embedding_plan(b["ids"], V, plan)
         ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
-        # ---- gradient exchange (data parallel) ----------------------------------------------
-        if self.world > 1:
-            dist.all_reduce(self.flat_grad, group=self.pg)
-            dist.all_reduce(self.table_grad, group=self.pg)
+        # ---- gradient exchange (data parallel): SUM-allreduce, gradients already carry 1/B_global
+        self.exchange.allreduce([self.table_grad, self.flat_grad])
         # ---- Adam ---------------------------------------------------------------------------
         b1, b2 = self.betas
         ops.adam_step(self.flat, self.flat_grad, self.flat_m, self.flat_v, self.step_count, self.lr,
