@@ -349,13 +349,14 @@ def main():
 
     # ---- per-kernel breakdown (separate profiled pass, CUDA events per launch) ---------------
     roofline, breakdown = None, {}
+    nprof = min(K, 5)
+    if rank == 0:
+        lib.nrms_profile_enable(1)
+    for i in range(nprof):          # every rank steps: the step contains the gradient allreduce
+        step_resident(i)
+    sync_all()
     if rank == 0:
         peaks = load_peaks()
-        lib.nrms_profile_enable(1)
-        nprof = min(K, 5)
-        for i in range(nprof):
-            step_resident(i)
-        torch.cuda.synchronize()
         import ctypes
         buf = ctypes.create_string_buffer(1 << 16)
         lib.nrms_profile_collect(buf, len(buf))
