@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "attention.cuh"
+#include "attention_tile.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gather.cuh"
@@ -355,27 +356,36 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = news ? drop : make_dropout(0.f, 0);
-        const AttnCfg c = attn_fwd_cfg(L, h);
-        a.hpb = c.hpb;
-        const bool vec2 = (dk % 2 == 0);
-        const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
-        if (a.drop.enabled() && c.hpb < h && ((c.hpb * dk) % 8))
-            ;  // groups straddling head groups are written twice with identical bits: fine
-        if (c.unit == 16) {
-            if (vec2) {
-                if ((rc = set_smem(attn_fwd_kernel<16, true>, c.smem))) return rc;
-                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<16, true><<<grid, c.threads, c.smem, s>>>(a)));
-            } else {
-                if ((rc = set_smem(attn_fwd_kernel<16, false>, c.smem))) return rc;
-                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<16, false><<<grid, c.threads, c.smem, s>>>(a)));
-            }
+        if (L <= kTile && dk % 2 == 0) {
+            // register-tiled kernel: one warp per (sequence, head)
+            int hpb = h;
+            while (hpb > 1 && attn_tile_fwd_smem_bytes(hpb) > 75 * 1024) --hpb;   // 3 CTAs per SM
+            hpb = ceil_div(h, ceil_div(h, hpb));
+            a.hpb = hpb;
+            const size_t smem = attn_tile_fwd_smem_bytes(hpb);
+            if ((rc = set_smem(attn_tile_fwd_kernel, smem))) return rc;
+            NRMS_LAUNCH("attn_fwd", s, (attn_tile_fwd_kernel<<<dim3(d.n_seq, ceil_div(h, hpb)), hpb * 32, smem, s>>>(a)));
         } else {
-            if (vec2) {
-                if ((rc = set_smem(attn_fwd_kernel<32, true>, c.smem))) return rc;
-                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<32, true><<<grid, c.threads, c.smem, s>>>(a)));
+            const AttnCfg c = attn_fwd_cfg(L, h);
+            a.hpb = c.hpb;
+            const bool vec2 = (dk % 2 == 0);
+            const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
+            if (c.unit == 16) {
+                if (vec2) {
+                    if ((rc = set_smem(attn_fwd_kernel<16, true>, c.smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<16, true><<<grid, c.threads, c.smem, s>>>(a)));
+                } else {
+                    if ((rc = set_smem(attn_fwd_kernel<16, false>, c.smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<16, false><<<grid, c.threads, c.smem, s>>>(a)));
+                }
             } else {
-                if ((rc = set_smem(attn_fwd_kernel<32, false>, c.smem))) return rc;
-                NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<32, false><<<grid, c.threads, c.smem, s>>>(a)));
+                if (vec2) {
+                    if ((rc = set_smem(attn_fwd_kernel<32, true>, c.smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<32, true><<<grid, c.threads, c.smem, s>>>(a)));
+                } else {
+                    if ((rc = set_smem(attn_fwd_kernel<32, false>, c.smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_fwd_kernel<32, false><<<grid, c.threads, c.smem, s>>>(a)));
+                }
             }
         }
         NRMS_CHECK_CUDA(cudaGetLastError());
@@ -486,15 +496,25 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = drop;
-        const AttnCfg c = attn_bwd_cfg(L, h);
-        a.hpb = c.hpb;
-        const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
-        if (dk % 2 == 0) {
-            if ((rc = set_smem(attn_bwd_kernel<true>, c.smem))) return rc;
-            NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<true><<<grid, c.threads, c.smem, s>>>(a)));
+        if (L <= kTile && dk % 2 == 0) {
+            int hpb = h;
+            while (hpb > 1 && attn_tile_bwd_smem_bytes(hpb) > 113 * 1024) --hpb;  // 2 CTAs per SM
+            hpb = ceil_div(h, ceil_div(h, hpb));
+            a.hpb = hpb;
+            const size_t smem = attn_tile_bwd_smem_bytes(hpb);
+            if ((rc = set_smem(attn_tile_bwd_kernel, smem))) return rc;
+            NRMS_LAUNCH("attn_bwd", s, (attn_tile_bwd_kernel<<<dim3(d.n_seq, ceil_div(h, hpb)), hpb * 32, smem, s>>>(a)));
         } else {
-            if ((rc = set_smem(attn_bwd_kernel<false>, c.smem))) return rc;
-            NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<false><<<grid, c.threads, c.smem, s>>>(a)));
+            const AttnCfg c = attn_bwd_cfg(L, h);
+            a.hpb = c.hpb;
+            const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
+            if (dk % 2 == 0) {
+                if ((rc = set_smem(attn_bwd_kernel<true>, c.smem))) return rc;
+                NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<true><<<grid, c.threads, c.smem, s>>>(a)));
+            } else {
+                if ((rc = set_smem(attn_bwd_kernel<false>, c.smem))) return rc;
+                NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<false><<<grid, c.threads, c.smem, s>>>(a)));
+            }
         }
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
