@@ -357,14 +357,11 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = news ? drop : make_dropout(0.f, 0);
         if (L <= kTile && dk % 2 == 0) {
-            // register-tiled kernel: one warp per (sequence, head)
-            int hpb = h;
-            while (hpb > 1 && attn_tile_fwd_smem_bytes(hpb) > 75 * 1024) --hpb;   // 3 CTAs per SM
-            hpb = ceil_div(h, ceil_div(h, hpb));
-            a.hpb = hpb;
-            const size_t smem = attn_tile_fwd_smem_bytes(hpb);
+            // register-tiled kernel: one independent warp per (sequence, head)
+            const long long items = (long long)d.n_seq * h;
+            const size_t smem = attn_tile_fwd_smem_bytes();
             if ((rc = set_smem(attn_tile_fwd_kernel, smem))) return rc;
-            NRMS_LAUNCH("attn_fwd", s, (attn_tile_fwd_kernel<<<dim3(d.n_seq, ceil_div(h, hpb)), hpb * 32, smem, s>>>(a)));
+            NRMS_LAUNCH("attn_fwd", s, (attn_tile_fwd_kernel<<<(unsigned)ceil_div64(items, kTileWarps), kTileWarps * 32, smem, s>>>(a, items)));
         } else {
             const AttnCfg c = attn_fwd_cfg(L, h);
             a.hpb = c.hpb;
@@ -497,13 +494,10 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = drop;
         if (L <= kTile && dk % 2 == 0) {
-            int hpb = h;
-            while (hpb > 1 && attn_tile_bwd_smem_bytes(hpb) > 113 * 1024) --hpb;  // 2 CTAs per SM
-            hpb = ceil_div(h, ceil_div(h, hpb));
-            a.hpb = hpb;
-            const size_t smem = attn_tile_bwd_smem_bytes(hpb);
+            const long long items = (long long)d.n_seq * h;
+            const size_t smem = attn_tile_bwd_smem_bytes();
             if ((rc = set_smem(attn_tile_bwd_kernel, smem))) return rc;
-            NRMS_LAUNCH("attn_bwd", s, (attn_tile_bwd_kernel<<<dim3(d.n_seq, ceil_div(h, hpb)), hpb * 32, smem, s>>>(a)));
+            NRMS_LAUNCH("attn_bwd", s, (attn_tile_bwd_kernel<<<(unsigned)ceil_div64(items, kTileWarps), kTileWarps * 32, smem, s>>>(a, items)));
         } else {
             const AttnCfg c = attn_bwd_cfg(L, h);
             a.hpb = c.hpb;
