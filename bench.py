@@ -245,7 +245,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("NRMS_GEMM_MODE", "0")))
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("NRMS_GEMM_MODE", "1")),
+                    help="1 = tcgen05 split-bf16 GEMMs (default), 0 = exact-fp32 CUDA-core GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--zipf", action="store_true", help="Zipf(1.0) token distribution instead of uniform")
     args = ap.parse_args()

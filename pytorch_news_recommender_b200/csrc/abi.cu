@@ -440,8 +440,8 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     {
         PoolArgs p{};
         p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.d_out = d_out;
-        p.d_ctx = sc.d_ctx; p.d_part = sc.part_q;
-        if (tcm) p.d_pre_img = sc.d_pre_img; else p.d_pre = sc.d_pre;
+        p.d_part = sc.part_q;
+        if (tcm) p.d_pre_img = sc.d_pre_img; else { p.d_pre = sc.d_pre; p.d_ctx = sc.d_ctx; }
         p.M = M; p.L = L; p.D = D; p.Q = Q;
         NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
@@ -450,12 +450,14 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     rc = reduce_rows(sc.part_q, gv.ba, d.n_seq, 2 * Q, 2 * Q, 1.f, sc.red_tmp, s);
     if (rc) return rc;
     const int tok_tiles = ig::img_rows_pad(M) / 128;
-    // 2. d_ctx += d_pre W_a        3. dW_a = d_pre^T ctx (split over the token rows)
+    // 2. d_ctx = pool path + d_pre W_a        3. dW_a = d_pre^T ctx (split over the token rows)
     if (tcm) {
+        // d_ctx = w_l * d_out (pooling path, formed in the epilogue) + d_pre W_a
         ig::IgArgs g = ig_args(sc.d_pre_img, sv.wa_img, sc.d_ctx, D, M, D);
         g.m_tiles = tok_tiles; g.n_tiles = 1;
         g.k_steps = ceil_div(Q, 16); g.k_chunks = ceil_div(g.k_steps, 4);
-        NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_ACCUM>(g, s, "gemm_dgrad_additive")));
+        g.row_w = sv.w; g.seq_vec = d_out; g.seq_len = L;
+        NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_POOLADD>(g, s, "gemm_dgrad_additive")));
 
         ig::IgArgs w = ig_args(sc.d_pre_img, sv.ctx_img, sc.wpart, D, Q, D);
         w.m_tiles = ceil_div(Q, 128); w.n_tiles = 1;

@@ -123,7 +123,7 @@ inline cudaError_t img_pack(const float* src, int R, int C, int ld, const Img& i
 }
 
 // ---- the GEMM ----------------------------------------------------------------------------------
-enum Epi { EPI_BIAS = 0, EPI_TANH_DOT = 1, EPI_ACCUM = 2, EPI_MASK = 3, EPI_PARTIAL = 4 };
+enum Epi { EPI_BIAS = 0, EPI_TANH_DOT = 1, EPI_ACCUM = 2, EPI_MASK = 3, EPI_PARTIAL = 4, EPI_POOLADD = 5 };
 
 struct IgArgs {
     Img A, B;
@@ -136,6 +136,9 @@ struct IgArgs {
     const uint32_t* mask_bits;  // EPI_MASK: [M, mask_words] keep bits (bit n%32 of word n/32), or NULL
     int mask_words;
     float mask_scale;           // 1/(1-p)
+    const float* row_w;         // EPI_POOLADD: [M] pooling weight of each token row
+    const float* seq_vec;       // EPI_POOLADD: [M / seq_len, N] upstream gradient of each sequence
+    int seq_len;                // EPI_POOLADD: C[m,n] = acc + row_w[m] * seq_vec[m / seq_len, n]
     int M, N;                   // valid output rows / columns
     int m_tiles, n_tiles;       // work grid (tiles of 128 rows x N_T columns)
     int k_chunks;               // 64-deep k chunks in total
@@ -342,6 +345,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                     mw[i] = (a.mask_bits && row_ok && i < a.mask_words) ? __ldg(a.mask_bits + (long long)m * a.mask_words + i)
                                                                        : 0xffffffffu;
             }
+            float rw = 0.f;
+            const float* svec = nullptr;
+            if (EPI == EPI_POOLADD && row_ok) {
+                rw = __ldg(a.row_w + m);
+                svec = a.seq_vec + (long long)(m / a.seq_len) * a.N + n0;
+            }
             float* crow = a.C + (EPI == EPI_PARTIAL ? (long long)split * a.c_split_stride : 0ll) +
                           (long long)m * a.ldc + n0;
             tc::mbar_wait(accf_bar(buf), use & 1u);
@@ -353,12 +362,16 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                 float v[32];
                 tc::tmem_ld32(t_row + (uint32_t)cb, v);
                 float4 old[8];
-                if (EPI == EPI_ACCUM) {
+                if (EPI == EPI_ACCUM || EPI == EPI_POOLADD) {
+                    // batched, independent loads (issued together, consumed below)
 #pragma unroll
                     for (int g = 0; g < 8; ++g) {
                         const int n = cb + 4 * g;
-                        old[g] = (row_ok && n < N_T && n0 + n < a.N) ? *reinterpret_cast<const float4*>(crow + n)
-                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const bool ok = row_ok && n < N_T && n0 + n < a.N;
+                        if (EPI == EPI_ACCUM)
+                            old[g] = ok ? *reinterpret_cast<const float4*>(crow + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        else
+                            old[g] = ok ? __ldg(reinterpret_cast<const float4*>(svec + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
 #pragma unroll
@@ -376,6 +389,10 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                     }
                     if (EPI == EPI_ACCUM) {
                         o.x += old[g].x; o.y += old[g].y; o.z += old[g].z; o.w += old[g].w;
+                    }
+                    if (EPI == EPI_POOLADD) {
+                        o.x = fmaf(rw, old[g].x, o.x); o.y = fmaf(rw, old[g].y, o.y);
+                        o.z = fmaf(rw, old[g].z, o.z); o.w = fmaf(rw, old[g].w, o.w);
                     }
                     if (EPI == EPI_MASK) {
                         const uint32_t bits = mw[(n0 + n) >> 5] >> ((n0 + n) & 31);

@@ -17,7 +17,8 @@ struct PoolArgs {
     float* w;            // [n_seq, L]  fwd out / bwd in
     float* out;          // [n_seq, D]  fwd out
     const float* d_out;  // [n_seq, D]  bwd in
-    float* d_ctx;        // [M, D]      bwd out: w_l * d_out (projection path is added by the GEMM)
+    float* d_ctx;        // [M, D]      bwd out (optional): w_l * d_out; the projection path is added by the
+                         //             data-gradient GEMM, whose tcgen05 epilogue forms this term itself
     float* d_pre;        // [M, Q]      bwd out (optional): grad wrt pre-tanh activations, fp32
     ig::Img d_pre_img;   //             bwd out (optional): the same as a split-bf16 image
     float* d_part;       // [n_seq, 2Q] bwd out: per-sequence partials of (d_b_a | d_q)
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
     for (int l = threadIdx.x; l < L; l += blockDim.x) sda[l] = sw[l] * (sda[l] - dot);
     __syncthreads();
     // d_ctx (pooling path)
-    {
+    if (p.d_ctx) {
         const int d4n = D >> 2;
         for (int i = threadIdx.x; i < L * d4n; i += blockDim.x) {
             const int l = i / d4n, d = (i - l * d4n) << 2;

@@ -255,7 +255,8 @@ class FusedTrainer:
         cfg, dev = self.cfg, self.device
         D, V = self.table.shape[1], self.table.shape[0]
         h, Q = cfg.num_attention_heads, cfg.query_vector_dim
-        gm = int(getattr(cfg, "gemm_mode", 0))
+        from .model.nrms_v0 import _gemm_mode
+        gm = _gemm_mode(cfg)
         training = self.model.training
         p = float(cfg.dropout) if training else 0.0
         self.step_count += 1

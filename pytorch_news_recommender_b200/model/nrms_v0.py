@@ -53,7 +53,14 @@ class AdditiveAttention(nn.Module):
 
 
 def _gemm_mode(config) -> int:
-    return int(getattr(config, "gemm_mode", 0))
+    """config.gemm_mode when set; otherwise the tcgen05 path (1) whenever its tile shapes cover
+    the model dims (include/nrms_b200.h), else the exact-fp32 CUDA-core GEMMs (0).  Both are
+    implementations of the same contractions on the GPU — neither is a fallback off the device."""
+    gm = getattr(config, "gemm_mode", None)
+    if gm is not None:
+        return int(gm)
+    d, q, h = config.word_embed_size, config.query_vector_dim, config.num_attention_heads
+    return 1 if (d <= 320 and q <= 208 and (d // h) % 2 == 0) else 0
 
 
 class NewsEncoder(nn.Module):
