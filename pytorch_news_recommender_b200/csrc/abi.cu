@@ -9,6 +9,7 @@
 
 #include "attention.cuh"
 #include "attention_tile.cuh"
+#include "attention_mma.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gather.cuh"
@@ -357,11 +358,11 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = news ? drop : make_dropout(0.f, 0);
         if (L <= kTile && dk % 2 == 0) {
-            // register-tiled kernel: one independent warp per (sequence, head)
+            // one independent warp per (sequence, head), products on mma.sync (attention_mma.cuh)
             const long long items = (long long)d.n_seq * h;
-            const size_t smem = attn_tile_fwd_smem_bytes();
-            if ((rc = set_smem(attn_tile_fwd_kernel, smem))) return rc;
-            NRMS_LAUNCH("attn_fwd", s, (attn_tile_fwd_kernel<<<(unsigned)ceil_div64(items, kTileWarps), kTileWarps * 32, smem, s>>>(a, items)));
+            const size_t smem = attn_mma_fwd_smem_bytes();
+            if ((rc = set_smem(attn_mma_fwd_kernel, smem))) return rc;
+            NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<<<(unsigned)ceil_div64(items, kMmaWarps), kMmaWarps * 32, smem, s>>>(a, items)));
         } else {
             const AttnCfg c = attn_fwd_cfg(L, h);
             a.hpb = c.hpb;
@@ -497,9 +498,9 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.drop = drop;
         if (L <= kTile && dk % 2 == 0) {
             const long long items = (long long)d.n_seq * h;
-            const size_t smem = attn_tile_bwd_smem_bytes();
-            if ((rc = set_smem(attn_tile_bwd_kernel, smem))) return rc;
-            NRMS_LAUNCH("attn_bwd", s, (attn_tile_bwd_kernel<<<(unsigned)ceil_div64(items, kTileWarps), kTileWarps * 32, smem, s>>>(a, items)));
+            const size_t smem = attn_mma_bwd_smem_bytes();
+            if ((rc = set_smem(attn_mma_bwd_kernel, smem))) return rc;
+            NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<<<(unsigned)ceil_div64(items, kMmaWarps), kMmaWarps * 32, smem, s>>>(a, items)));
         } else {
             const AttnCfg c = attn_bwd_cfg(L, h);
             a.hpb = c.hpb;

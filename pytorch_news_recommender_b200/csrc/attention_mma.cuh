@@ -1,0 +1,383 @@
+// attention_mma.cuh — self-attention for sequences of up to 32 tokens (the title encoder) with the
+// per-head 32x32x32 products on the tensor cores, forward and backward.  Same math and I/O
+// contract as attention.cuh / attention_tile.cuh (reference nrms_v0.py:13-23, 46-76, 171-173).
+//
+// Why: with CUDA-core FMAs a head's products are bound by shared-memory bandwidth (each lane
+// re-reads its operands for every k: 3 x 16-byte reads per 32 FMAs, 4 wavefronts each).  With
+// warp-level mma.sync.m16n8k16 every operand element is read from shared memory ONCE per product
+// into a register fragment, and the math runs on the tensor pipe.  These are tiny batched
+// products (30x30x30 per head, 35,200 heads per step), not GEMM tiles: tcgen05's 128-row tiles
+// and TMEM round trips do not fit them, the warp-level instruction does.
+//
+// Precision: the same 3-term bf16 split as the projections (gemm_img.cuh): x = hi + lo,
+// A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo, fp32 accumulate — fp32-grade.
+//
+// One WARP owns one (sequence, head) and never synchronises with another warp.  Operands arrive
+// by cp.async into warp-private 32x40 fp32 slots (rows >= L, columns >= d_k zero).  The score
+// tile stays in the accumulator fragment layout (row g / g+8, columns 2t, 2t+1 of each 8-wide
+// tile; g = lane/4, t = lane%4): the row softmax is two shuffles over a quad, and P / dS feed the
+// next product as A fragments straight from registers (the accumulator layout of m16n8 IS the A
+// layout of m16n8k16).  P^T / dS^T for the backward's transposed products go through a dead slot.
+#pragma once
+#include "attention_tile.cuh"
+
+namespace nrms {
+
+constexpr int kMS = 40;                 // slot row stride: 8-byte fragment reads of rows g..g+3 hit 32 distinct banks
+constexpr int kMSlot = kTile * kMS;     // floats per 32x40 slot
+constexpr int kMmaWarps = 4;
+
+__host__ __device__ inline size_t attn_mma_fwd_smem_bytes() {
+    return (size_t)kMmaWarps * (3 * kMSlot * sizeof(float) + kTile * 8);
+}
+__host__ __device__ inline size_t attn_mma_bwd_smem_bytes() {
+    return (size_t)kMmaWarps * 4 * kMSlot * sizeof(float);
+}
+
+// (x, y) -> packed bf16 pairs: hi = {bf16(x) low, bf16(y) high}, lo = the same of the residuals
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+    const float hx = __uint_as_float(hi << 16), hy = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(y - hy), "f"(x - hx));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// c += A*B with the 3-term split
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
+                                     const uint32_t (&bhi)[2], const uint32_t (&blo)[2]) {
+    mma_bf16(c, alo, bhi[0], bhi[1]);
+    mma_bf16(c, ahi, blo[0], blo[1]);
+    mma_bf16(c, ahi, bhi[0], bhi[1]);
+}
+
+// A fragments (hi/lo) of the 16x16 block (rows 16mt.., k 16ks..) of a row-major [row][k] slot
+__device__ __forceinline__ void load_a_frag(uint32_t (&hi)[4], uint32_t (&lo)[4], const float* A, int mt, int ks,
+                                            int g, int t) {
+    const float* p = A + (16 * mt + g) * kMS + 16 * ks + 2 * t;
+    const float2 v0 = *reinterpret_cast<const float2*>(p);
+    const float2 v1 = *reinterpret_cast<const float2*>(p + 8 * kMS);
+    const float2 v2 = *reinterpret_cast<const float2*>(p + 8);
+    const float2 v3 = *reinterpret_cast<const float2*>(p + 8 * kMS + 8);
+    split_pair(v0.x, v0.y, hi[0], lo[0]);
+    split_pair(v1.x, v1.y, hi[1], lo[1]);
+    split_pair(v2.x, v2.y, hi[2], lo[2]);
+    split_pair(v3.x, v3.y, hi[3], lo[3]);
+}
+// B fragments of the 16(k) x 8(n) block from a slot holding B as [n][k] (k contiguous)
+__device__ __forceinline__ void load_b_frag_nk(uint32_t (&hi)[2], uint32_t (&lo)[2], const float* B, int nt, int ks,
+                                               int g, int t) {
+    const float* p = B + (8 * nt + g) * kMS + 16 * ks + 2 * t;
+    const float2 v0 = *reinterpret_cast<const float2*>(p);
+    const float2 v1 = *reinterpret_cast<const float2*>(p + 8);
+    split_pair(v0.x, v0.y, hi[0], lo[0]);
+    split_pair(v1.x, v1.y, hi[1], lo[1]);
+}
+// B fragments of the 16(k) x 8(n) block from a slot holding B as [k][n] (n contiguous)
+__device__ __forceinline__ void load_b_frag_kn(uint32_t (&hi)[2], uint32_t (&lo)[2], const float* B, int nt, int ks,
+                                               int g, int t) {
+    const float* p = B + (16 * ks + 2 * t) * kMS + 8 * nt + g;
+    split_pair(p[0], p[kMS], hi[0], lo[0]);
+    split_pair(p[8 * kMS], p[9 * kMS], hi[1], lo[1]);
+}
+
+// c[mt][nt] += A[32 x 32k] * B^T, both slots row-major over k:  S = Q K^T,  dP = dO V^T
+__device__ __forceinline__ void mma_abt(float (&c)[2][4][4], const float* A, const float* B, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) load_a_frag(ahi[mt], alo[mt], A, mt, ks, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bhi[2], blo[2];
+            load_b_frag_nk(bhi, blo, B, nt, ks, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma3(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
+        }
+    }
+}
+// c[mt][nt] += P * B with P in the accumulator layout (registers) and B a [k][n] slot:
+// O = P V,  dQ = dS K
+__device__ __forceinline__ void mma_regA_b(float (&c)[2][4][4], const float (&p)[2][4][4], const float* B, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            split_pair(p[mt][2 * ks][0], p[mt][2 * ks][1], ahi[mt][0], alo[mt][0]);          // row g,   k 2t..
+            split_pair(p[mt][2 * ks][2], p[mt][2 * ks][3], ahi[mt][1], alo[mt][1]);          // row g+8
+            split_pair(p[mt][2 * ks + 1][0], p[mt][2 * ks + 1][1], ahi[mt][2], alo[mt][2]);  // row g,   k 2t+8..
+            split_pair(p[mt][2 * ks + 1][2], p[mt][2 * ks + 1][3], ahi[mt][3], alo[mt][3]);  // row g+8
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bhi[2], blo[2];
+            load_b_frag_kn(bhi, blo, B, nt, ks, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma3(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
+        }
+    }
+}
+// c[mt][nt] += AT * B with AT a slot holding A^T as [m][k] and B a [k][n] slot:
+// dV = P^T dO (AT = P^T[key][row]),  dK = dS^T Q
+__device__ __forceinline__ void mma_a_b(float (&c)[2][4][4], const float* AT, const float* B, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) load_a_frag(ahi[mt], alo[mt], AT, mt, ks, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bhi[2], blo[2];
+            load_b_frag_kn(bhi, blo, B, nt, ks, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma3(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
+        }
+    }
+}
+__device__ __forceinline__ void zero_frag(float (&c)[2][4][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[mt][nt][i] = 0.f;
+}
+// accumulator layout -> slot[row][col] (row-major), rows scaled by mul[mt][half]
+__device__ __forceinline__ void store_frag(float* slot, const float (&c)[2][4][4], const float (&mul)[2][2], int g, int t) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float* p = slot + (16 * mt + g) * kMS + 8 * nt + 2 * t;
+            *reinterpret_cast<float2*>(p) = make_float2(c[mt][nt][0] * mul[mt][0], c[mt][nt][1] * mul[mt][0]);
+            *reinterpret_cast<float2*>(p + 8 * kMS) = make_float2(c[mt][nt][2] * mul[mt][1], c[mt][nt][3] * mul[mt][1]);
+        }
+}
+// accumulator layout -> slot[col][row] (transposed)
+__device__ __forceinline__ void store_frag_t(float* slot, const float (&c)[2][4][4], int g, int t) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            float* p = slot + (8 * nt + 2 * t) * kMS + 16 * mt + g;
+            p[0] = c[mt][nt][0];
+            p[kMS] = c[mt][nt][1];
+            p[8] = c[mt][nt][2];
+            p[kMS + 8] = c[mt][nt][3];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const AttnArgs a, long long n_items) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kMmaWarps + warp;
+    if (item >= n_items) return;
+    const int L = a.L, D = a.D, dk = a.dk;
+    const long long seq = item / a.n_heads;
+    const int h = (int)(item - seq * a.n_heads);
+    float* Qh = smem + (size_t)warp * 3 * kMSlot;
+    float* Kh = Qh + kMSlot;       // K, later the output staging
+    float* Vh = Kh + kMSlot;
+    uint8_t* smask = reinterpret_cast<uint8_t*>(smem + (size_t)kMmaWarps * 3 * kMSlot) + warp * kTile * 8;
+    const long long row0 = seq * L;
+    const int ld = 3 * D, col = h * dk;
+    const int g = lane >> 2, t = lane & 3;
+
+    load_slot_async<kMS>(Qh, a.qkv, row0, ld, col, L, dk, lane);
+    load_slot_async<kMS>(Kh, a.qkv, row0, ld, D + col, L, dk, lane);
+    load_slot_async<kMS>(Vh, a.qkv, row0, ld, 2 * D + col, L, dk, lane);
+    const int g0 = col >> 3;
+    const bool drop = a.drop.enabled();
+    if (drop) {
+        const int ng = ((col + dk + 7) >> 3) - g0;
+        for (int it = lane; it < L * 8; it += 32) {
+            const int l = it >> 3, gi = it & 7;
+            if (gi < ng) {
+                const uint32_t keep = a.drop.keep8(kDropContext, (uint64_t)(row0 + l), (uint32_t)(g0 + gi));
+                smask[l * 8 + gi] = (uint8_t)keep;
+                if (a.cmask && g0 + gi < a.mask_bytes) a.cmask[(row0 + l) * a.mask_bytes + g0 + gi] = (uint8_t)keep;
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    float s[2][4][4];
+    zero_frag(s);
+    mma_abt(s, Qh, Kh, g, t);
+    // softmax over the keys: a row lives in the 4 lanes of a quad
+    float inv[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float& x = s[mt][nt][2 * hf + e];
+                    x = (8 * nt + 2 * t + e < L) ? x * a.scale : -INFINITY;   // scores / sqrt(d_k); no key >= L
+                    m = fmaxf(m, x);
+                }
+            m = quad_max(m);
+            float sum = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float& x = s[mt][nt][2 * hf + e];
+                    x = __expf(x - m);
+                    sum += x;
+                }
+            sum = quad_sum(sum);
+            inv[mt][hf] = 1.f / sum;
+            const int r = 16 * mt + 8 * hf + g;
+            if (t == 0 && r < L) a.lse[(row0 + r) * a.n_heads + h] = m + __logf(sum);
+        }
+    float o[2][4][4];
+    zero_frag(o);
+    mma_regA_b(o, s, Vh, g, t);          // unnormalised P straight from registers
+    __syncwarp();                        // all reads of K (scores) are long done; V reads done
+    store_frag(Kh, o, inv, g, t);        // O = P V / rowsum over the dead K slot
+    __syncwarp();
+    warp_write_slot<false, kMS>(Kh, L, dk, row0, col, a.ctx, D, a.ctx_img, drop ? smask : nullptr, g0, a.drop.scale,
+                                nullptr, lane);
+    if (a.ctx_img.hi != nullptr)
+        pad_image(a.ctx_img, row0, L, D, a.ctx_img.chunks * 64, h == a.n_heads - 1, item == n_items - 1, a.M, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+//   P = exp(scale*Q K^T - lse) ; dP = dO V^T ; dS = scale * P o (dP - delta) ; delta = rowsum(dO o O)
+//   dV = P^T dO ; dK = dS^T Q ; dQ = dS K
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const AttnArgs a, long long n_items) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * kMmaWarps + warp;
+    if (item >= n_items) return;
+    const int L = a.L, D = a.D, dk = a.dk;
+    const long long seq = item / a.n_heads;
+    const int h = (int)(item - seq * a.n_heads);
+    float* Qh = smem + (size_t)warp * 4 * kMSlot;   // Q  -> dK staging
+    float* Kh = Qh + kMSlot;                        // K  -> dQ staging
+    float* Vh = Kh + kMSlot;                        // V  -> P^T -> dV staging
+    float* Gh = Vh + kMSlot;                        // dO -> dS^T
+    const long long row0 = seq * L;
+    const int ld = 3 * D, col = h * dk;
+    const int g = lane >> 2, t = lane & 3;
+    const bool drop = a.drop.enabled() && a.cmask != nullptr;
+
+    load_slot_async<kMS>(Qh, a.qkv, row0, ld, col, L, dk, lane);
+    load_slot_async<kMS>(Kh, a.qkv, row0, ld, D + col, L, dk, lane);
+    load_slot_async<kMS>(Vh, a.qkv, row0, ld, 2 * D + col, L, dk, lane);
+    load_slot_async<kMS>(Gh, a.d_ctx, row0, D, col, L, dk, lane);
+    // rows of this lane in the accumulator layout: r(mt,hf) = 16mt + 8hf + g ; the quad splits a
+    // row's 32 columns into 8-column pieces for delta_i = sum_d d_ctx * ctx (post-dropout both)
+    float2 ov[2][2][4];
+    float lse[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int r = 16 * mt + 8 * hf + g;
+            lse[mt][hf] = r < L ? a.lse[(row0 + r) * a.n_heads + h] : 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int d = 8 * t + 2 * c;
+                ov[mt][hf][c] = (r < L && d < dk) ? __ldg(reinterpret_cast<const float2*>(a.ctx + (row0 + r) * D + col + d))
+                                                  : make_float2(0.f, 0.f);
+            }
+        }
+    cp_async_wait_all();
+    __syncwarp();
+
+    float delta[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const float* gp = Gh + (16 * mt + 8 * hf + g) * kMS + 8 * t;
+            const float4 g0v = *reinterpret_cast<const float4*>(gp), g1v = *reinterpret_cast<const float4*>(gp + 4);
+            float dl = g0v.x * ov[mt][hf][0].x;
+            dl = fmaf(g0v.y, ov[mt][hf][0].y, dl); dl = fmaf(g0v.z, ov[mt][hf][1].x, dl); dl = fmaf(g0v.w, ov[mt][hf][1].y, dl);
+            dl = fmaf(g1v.x, ov[mt][hf][2].x, dl); dl = fmaf(g1v.y, ov[mt][hf][2].y, dl);
+            dl = fmaf(g1v.z, ov[mt][hf][3].x, dl); dl = fmaf(g1v.w, ov[mt][hf][3].y, dl);
+            delta[mt][hf] = quad_sum(dl);
+        }
+    if (drop) {
+        // dO = d_ctx * keep/(1-p), in place: 16 lanes per row, two rows per pass
+        __syncwarp();
+        const int half = dk >> 1;
+        for (int l0 = 0; l0 < L; l0 += 2) {
+            const int l = l0 + (lane >> 4), pp = lane & 15;
+            if (l < L && pp < half) {
+                const int d = pp << 1;
+                const int c = col + d;
+                const uint32_t keep = (uint32_t)a.cmask[(row0 + l) * a.mask_bytes + (c >> 3)] >> (c & 7);
+                float2* p = reinterpret_cast<float2*>(Gh + l * kMS + d);
+                float2 gv = *p;
+                gv.x = (keep & 1u) ? gv.x * a.drop.scale : 0.f;
+                gv.y = (keep & 2u) ? gv.y * a.drop.scale : 0.f;
+                *p = gv;
+            }
+        }
+        __syncwarp();
+    }
+    float p[2][4][4], ds[2][4][4];
+    zero_frag(p);
+    zero_frag(ds);
+    mma_abt(p, Qh, Kh, g, t);            // S
+    mma_abt(ds, Gh, Vh, g, t);           // dP
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int hf = i >> 1;
+                const bool ok = (16 * mt + 8 * hf + g < L) && (8 * nt + 2 * t + (i & 1) < L);
+                const float pv = ok ? __expf(p[mt][nt][i] * a.scale - lse[mt][hf]) : 0.f;
+                p[mt][nt][i] = pv;
+                ds[mt][nt][i] = ok ? pv * (ds[mt][nt][i] - delta[mt][hf]) * a.scale : 0.f;
+            }
+    __syncwarp();                        // all reads of V (dP) are done
+    store_frag_t(Vh, p, g, t);           // P^T[key][row] over V
+    __syncwarp();
+    const float one[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
+    const ig::Img& im = a.d_qkv_img;
+    float* sums = a.d_bias_part + seq * ld;
+    float acc[2][4][4];
+    zero_frag(acc);
+    mma_a_b(acc, Vh, Gh, g, t);          // dV[key][d] = sum_row P^T[key][row] dO[row][d]
+    __syncwarp();                        // all reads of P^T and dO are done
+    store_frag(Vh, acc, one, g, t);      // dV over P^T
+    store_frag_t(Gh, ds, g, t);          // dS^T[key][row] over dO
+    __syncwarp();
+    warp_write_slot<true, kMS>(Vh, L, dk, row0, 2 * D + col, a.d_qkv, ld, im, nullptr, 0, 1.f, sums, lane);
+    zero_frag(acc);
+    mma_a_b(acc, Gh, Qh, g, t);          // dK[key][d] = sum_row dS^T[key][row] Q[row][d]
+    __syncwarp();                        // all reads of Q are done
+    store_frag(Qh, acc, one, g, t);      // dK over Q
+    __syncwarp();
+    warp_write_slot<true, kMS>(Qh, L, dk, row0, D + col, a.d_qkv, ld, im, nullptr, 0, 1.f, sums, lane);
+    zero_frag(acc);
+    mma_regA_b(acc, ds, Kh, g, t);       // dQ[row][d] = sum_key dS[row][key] K[key][d], dS from registers
+    __syncwarp();                        // all reads of K are done
+    store_frag(Kh, acc, one, g, t);      // dQ over K
+    __syncwarp();
+    warp_write_slot<true, kMS>(Kh, L, dk, row0, col, a.d_qkv, ld, im, nullptr, 0, 1.f, sums, lane);
+    if (im.hi != nullptr)
+        pad_image(im, row0, L, 3 * D, ceil_div(3 * D, 16) * 16, h == a.n_heads - 1, item == n_items - 1, a.M, lane);
+}
+
+}  // namespace nrms

@@ -33,25 +33,26 @@ __host__ __device__ inline size_t attn_tile_bwd_smem_bytes() {
 // Warp-private cp.async load of columns [col, col+dk) of rows [row0, row0+L) into one 32x36
 // slot; rows >= L and columns in [dk, 36) are zero-filled with plain stores.  16 lanes walk the
 // even rows, 16 the odd rows, each lane owning one 2-column unit.
+template <int RS = kRowStride>
 __device__ __forceinline__ void load_slot_async(float* slot, const float* src, long long row0, int ld,
                                                 int col, int L, int dk, int lane) {
     const int pp = lane & 15, par = lane >> 4;
     if (2 * pp < dk) {
         const float* g = src + (row0 + par) * ld + col + 2 * pp;
-        uint32_t t = (uint32_t)__cvta_generic_to_shared(slot + par * kRowStride + 2 * pp);
+        uint32_t t = (uint32_t)__cvta_generic_to_shared(slot + par * RS + 2 * pp);
         for (int l = par; l < L; l += 2) {
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(t), "l"(g) : "memory");
-            t += 2 * kRowStride * 4;
+            t += 2 * RS * 4;
             g += 2 * ld;
         }
     }
     {
-        float* row = slot + lane * kRowStride;      // lane = slot row
+        float* row = slot + lane * RS;      // lane = slot row
         if (lane < L) {
-            for (int d = dk; d < kRowStride; d += 2) *reinterpret_cast<float2*>(row + d) = make_float2(0.f, 0.f);
+            for (int d = dk; d < RS; d += 2) *reinterpret_cast<float2*>(row + d) = make_float2(0.f, 0.f);
         } else {
 #pragma unroll
-            for (int d = 0; d < kRowStride; d += 4) *reinterpret_cast<float4*>(row + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int d = 0; d < RS; d += 4) *reinterpret_cast<float4*>(row + d) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
 }
@@ -61,7 +62,7 @@ __device__ __forceinline__ void load_slot_async(float* slot, const float* src, l
 // bits smask[row*8 + (col>>3) - g0]; SUMS adds the per-sequence column sums (bias partials).
 // 16 lanes per row (one 2-column unit each), two rows per pass of a ROLLED loop: the code stays
 // small (the kernels are instruction-fetch sensitive) and every store is coalesced.
-template <bool SUMS>
+template <bool SUMS, int RS = kRowStride>
 __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk, long long row0, int gcol0, float* out,
                                                 int ld, const ig::Img& img, const uint8_t* smask, int g0,
                                                 float drop_scale, float* sums, int lane) {
@@ -73,7 +74,7 @@ __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk
 #pragma unroll 1
     for (int l = par; l < L; l += 2) {
         if (!active) continue;
-        float2 v = *reinterpret_cast<const float2*>(slot + l * kRowStride + c);
+        float2 v = *reinterpret_cast<const float2*>(slot + l * RS + c);
         if (smask) {
             const uint32_t keep = (uint32_t)smask[l * 8 + g - g0] >> (col & 7);
             v.x = (keep & 1u) ? v.x * drop_scale : 0.f;
@@ -97,10 +98,10 @@ __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
         for (int l = 0; l + 1 < L; l += 2) {
-            s0 += slot[l * kRowStride + lane];
-            s1 += slot[(l + 1) * kRowStride + lane];
+            s0 += slot[l * RS + lane];
+            s1 += slot[(l + 1) * RS + lane];
         }
-        if (L & 1) s0 += slot[(L - 1) * kRowStride + lane];
+        if (L & 1) s0 += slot[(L - 1) * RS + lane];
         sums[gcol0 + lane] = s0 + s1;
     }
 }

@@ -99,7 +99,9 @@ def test_dropin_backward_matches_reference(name, gemm_mode, built_lib):
         for k, g in grads.items():
             gold = c.z[f"evalgrad/full/{k}"]
             scale = max(float(np.abs(gold).max()), 1e-6)
-            np.testing.assert_allclose(g.cpu().numpy(), gold, rtol=2e-3, atol=2e-4 * scale + 1e-7)
+            # + 1e-6: noise floor of tensors that are mathematically zero (the W_K bias gradient:
+            # row sums of dS vanish), where only split-bf16 rounding noise is left
+            np.testing.assert_allclose(g.cpu().numpy(), gold, rtol=2e-3, atol=2e-4 * scale + 1e-6)
 
 
 def _kernel_masks(cfg, c, seed):
