@@ -187,8 +187,8 @@ Scratch scratch_layout(void* blob, const nrms_encoder_dims& d) {
         s.d_pre_img = ig::img_view(take_bytes(ig::img_bytes(M, kPreChunks)), M, kPreChunks);
         s.d_qkv_img = ig::img_view(take_bytes(ig::img_bytes(M, kQkvChunks)), M, kQkvChunks);
         const int kch = ig::img_rows_pad(M) / 64;
-        const int64_t a = (int64_t)wgrad_splits_tc(ceil_div((int)(3 * D), 128), kch) * 3 * D * D;
-        const int64_t b = (int64_t)wgrad_splits_tc(ceil_div((int)Q, 128), kch) * Q * D;
+        const int64_t a = (int64_t)wgrad_splits_tc(ceil_div((int)(3 * D), 128), kch) * 3 * D * (D + 4);
+        const int64_t b = (int64_t)wgrad_splits_tc(ceil_div((int)Q, 128), kch) * Q * (D + 4);
         wpart = a > b ? a : b;
     } else {
         s.d_pre = take(M * Q);
@@ -227,8 +227,8 @@ int check_dims(const nrms_encoder_dims* d, bool news) {
         return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode=%d unknown", d->gemm_mode);
     if (d->gemm_mode == 1) {
         // tile shapes of the tcgen05 path (gemm_img.cuh): N tiles of 240 / 208 / 320 columns
-        if (d->d_model > 320 || d->d_query > 208)
-            return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode 1 supports d_model <= 320 and d_query <= 208 "
+        if (d->d_model > 316 || d->d_query > 208)
+            return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode 1 supports d_model <= 316 and d_query <= 208 "
                         "(got %d, %d); use gemm_mode 0", d->d_model, d->d_query);
         if ((d->d_model / d->n_heads) % 2)
             return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode 1 needs an even head dim (got %d); use gemm_mode 0",
@@ -447,8 +447,11 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
-    // [d_b_a | d_query] are adjacent in the flat block, as in part_q
-    rc = reduce_rows(sc.part_q, gv.ba, d.n_seq, 2 * Q, 2 * Q, 1.f, sc.red_tmp, s);
+    // [d_b_a | d_query] are adjacent in the flat block, as in part_q; with the tcgen05 GEMMs d_b_a
+    // comes out of the weight-gradient GEMM (ones column of the context image) and only d_query
+    // is reduced here
+    rc = tcm ? reduce_rows(sc.part_q + Q, gv.qv, d.n_seq, Q, 2 * Q, 1.f, sc.red_tmp, s)
+             : reduce_rows(sc.part_q, gv.ba, d.n_seq, 2 * Q, 2 * Q, 1.f, sc.red_tmp, s);
     if (rc) return rc;
     const int tok_tiles = ig::img_rows_pad(M) / 128;
     // 2. d_ctx = pool path + d_pre W_a        3. dW_a = d_pre^T ctx (split over the token rows)
@@ -460,14 +463,16 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.row_w = sv.w; g.seq_vec = d_out; g.seq_len = L;
         NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_POOLADD>(g, s, "gemm_dgrad_additive")));
 
-        ig::IgArgs w = ig_args(sc.d_pre_img, sv.ctx_img, sc.wpart, D, Q, D);
+        // columns [0,D) = dW_a, column D = d_b_a (ones column of the context image)
+        ig::IgArgs w = ig_args(sc.d_pre_img, sv.ctx_img, sc.wpart, D + 4, Q, D + 4);
         w.m_tiles = ceil_div(Q, 128); w.n_tiles = 1;
         w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
         w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
-        w.c_split_stride = (long long)Q * D;
+        w.c_split_stride = (long long)Q * (D + 4);
         NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_additive")));
-        rc = reduce_rows(sc.wpart, gv.Wa, w.splits, (long long)Q * D, (long long)Q * D, 1.f, nullptr, s);
-        if (rc) return rc;
+        NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)Q * (D + 1), 256), 256, 0, s>>>(
+            sc.wpart, w.splits, Q, D + 4, D, gv.Wa, gv.ba));
+        NRMS_CHECK_CUDA(cudaGetLastError());
     } else {
         GemmArgs g{};
         g.A = sc.d_pre; g.B = pv.Wa; g.C = sc.d_ctx;
@@ -492,7 +497,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.qkv = sv.qkv; a.ctx = sv.ctx; a.lse = sv.lse; a.d_ctx = sc.d_ctx;
         a.cmask = sv.cmask; a.mask_bytes = mb;
         if (tcm) a.d_qkv_img = sc.d_qkv_img; else a.d_qkv = sc.d_qkv;
-        a.d_bias_part = sc.part_b;
+        a.d_bias_part = tcm ? nullptr : sc.part_b;   // tcgen05 path: bias gradient = column D of dW_qkv
         a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = drop;
@@ -515,18 +520,22 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         }
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
-    rc = reduce_rows(sc.part_b, gv.bqkv, d.n_seq, 3 * D, 3 * D, 1.f, sc.red_tmp, s);
-    if (rc) return rc;
+    if (!tcm) {
+        rc = reduce_rows(sc.part_b, gv.bqkv, d.n_seq, 3 * D, 3 * D, 1.f, sc.red_tmp, s);
+        if (rc) return rc;
+    }
     // 5. dW_qkv = d_qkv^T x        6. d_x = d_qkv W_qkv (x the embedding dropout mask)
     if (tcm) {
-        ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D, 3 * D, D);
+        // columns [0,D) = dW_qkv, column D = d_b_qkv (ones column of the input image)
+        ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D + 4, 3 * D, D + 4);
         w.m_tiles = ceil_div(3 * D, 128); w.n_tiles = 1;
         w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
         w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
-        w.c_split_stride = 3ll * D * D;
+        w.c_split_stride = 3ll * D * (D + 4);
         NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_qkv")));
-        rc = reduce_rows(sc.wpart, gv.Wqkv, w.splits, 3ll * D * D, 3ll * D * D, 1.f, nullptr, s);
-        if (rc) return rc;
+        NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for(3ll * D * (D + 1), 256), 256, 0, s>>>(
+            sc.wpart, w.splits, 3 * D, D + 4, D, gv.Wqkv, gv.bqkv));
+        NRMS_CHECK_CUDA(cudaGetLastError());
         if (d_x) {
             ig::IgArgs g = ig_args(sc.d_qkv_img, sv.wqkv_img, d_x, D, M, D);
             g.m_tiles = tok_tiles; g.n_tiles = 1;

@@ -36,7 +36,7 @@ struct AttnArgs {
     const float* d_ctx;  // bwd: grad wrt post-dropout context [M, D]
     float* d_qkv;        // bwd out (optional) fp32 [M, 3D]
     ig::Img d_qkv_img;   // bwd out (optional) image of [M, 3D]
-    float* d_bias_part;  // bwd out [n_seq, 3D]: per-sequence column sums of d_qkv
+    float* d_bias_part;  // bwd out (optional) [n_seq, 3D]: per-sequence column sums of d_qkv
     long long M;         // total token rows (n_seq * L)
     int L, D, n_heads, dk, hpb, mask_bytes;
     float scale;         // 1/sqrt(dk)
@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
             for (int i = threadIdx.x; i < L * (cpad >> 1); i += blockDim.x) {
                 const int l = i / (cpad >> 1), col = D + ((i - l * (cpad >> 1)) << 1);
                 const long long off = ig::img_unit_off(a.ctx_img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
-                *reinterpret_cast<uint32_t*>(a.ctx_img.hi + off) = 0u;
+                // column D = 1.0 (bf16 {1.0, 0.0}): the weight-gradient GEMM's bias column (gather.cuh)
+                *reinterpret_cast<uint32_t*>(a.ctx_img.hi + off) = col == D ? 0x00003F80u : 0u;
                 *reinterpret_cast<uint32_t*>(a.ctx_img.lo + off) = 0u;
             }
         }
@@ -472,8 +473,10 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnArgs a) {
                 if (a.d_qkv) a.d_qkv[(row0 + l) * ld + col] = v;
             }
         }
-        a.d_bias_part[(long long)seq * ld + col] = sum0;
-        if (VEC2) a.d_bias_part[(long long)seq * ld + col + 1] = sum1;
+        if (a.d_bias_part) {
+            a.d_bias_part[(long long)seq * ld + col] = sum0;
+            if (VEC2) a.d_bias_part[(long long)seq * ld + col + 1] = sum1;
+        }
     }
     if (img) {
         // image padding: columns [3D, 16*ceil(3D/16)) are read by the data-gradient GEMM's last

@@ -23,7 +23,7 @@
 
 namespace nrms {
 
-constexpr int kMS = 40;                 // slot row stride: 8-byte fragment reads of rows g..g+3 hit 32 distinct banks
+constexpr int kMS = 36;                 // slot row stride (floats): 3 CTAs of 4 warps fit an SM in the backward
 constexpr int kMSlot = kTile * kMS;     // floats per 32x40 slot
 constexpr int kMmaWarps = 4;
 
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const Attn
     warp_write_slot<false, kMS>(Kh, L, dk, row0, col, a.ctx, D, a.ctx_img, drop ? smask : nullptr, g0, a.drop.scale,
                                 nullptr, lane);
     if (a.ctx_img.hi != nullptr)
-        pad_image(a.ctx_img, row0, L, D, a.ctx_img.chunks * 64, h == a.n_heads - 1, item == n_items - 1, a.M, lane);
+        pad_image(a.ctx_img, row0, L, D, a.ctx_img.chunks * 64, h == a.n_heads - 1, item == n_items - 1, a.M, lane, true);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const Attn
     __syncwarp();
     const float one[2][2] = {{1.f, 1.f}, {1.f, 1.f}};
     const ig::Img& im = a.d_qkv_img;
-    float* sums = a.d_bias_part + seq * ld;
+    float* sums = a.d_bias_part ? a.d_bias_part + seq * ld : nullptr;   // null: the weight-gradient GEMM makes them
     float acc[2][4][4];
     zero_frag(acc);
     mma_a_b(acc, Vh, Gh, g, t);          // dV[key][d] = sum_row P^T[key][row] dO[row][d]

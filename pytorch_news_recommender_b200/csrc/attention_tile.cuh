@@ -94,7 +94,7 @@ __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk
                 (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
         }
     }
-    if (SUMS && lane < dk) {
+    if (SUMS && sums != nullptr && lane < dk) {
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll 1
         for (int l = 0; l + 1 < L; l += 2) {
@@ -105,16 +105,17 @@ __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk
         sums[gcol0 + lane] = s0 + s1;
     }
 }
-// zero padding of an image the kernel fills: columns [c0, c1) of this sequence's rows by the
-// warp of the last head, rows [M, rows_pad) by the very last warp of the grid
+// padding of an image the kernel fills: columns [c0, c1) of this sequence's rows by the warp of
+// the last head (zero; with `ones_col` column c0 is 1.0 so that the weight-gradient GEMM yields
+// the bias gradient as its column c0), rows [M, rows_pad) by the very last warp of the grid
 __device__ __forceinline__ void pad_image(const ig::Img& img, long long row0, int L, int c0, int c1, bool last_head,
-                                          bool last_item, long long M, int lane) {
+                                          bool last_item, long long M, int lane, bool ones_col = false) {
     if (last_head) {
         const int np = (c1 - c0) >> 1;
         for (int i = lane; i < L * np; i += 32) {
             const int l = i / np, col = c0 + ((i - l * np) << 1);
             const long long off = ig::img_unit_off(img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
-            *reinterpret_cast<uint32_t*>(img.hi + off) = 0u;
+            *reinterpret_cast<uint32_t*>(img.hi + off) = (ones_col && col == c0) ? 0x00003F80u : 0u;   // bf16 {1.0, 0.0}
             *reinterpret_cast<uint32_t*>(img.lo + off) = 0u;
         }
     }

@@ -60,6 +60,13 @@ __global__ void __launch_bounds__(256) gather_rows_img_kernel(const GatherArgs a
                 for (int j = 0; j < 8; ++j) x[j] = ((keep >> j) & 1u) ? x[j] * a.drop.scale : 0.f;
                 if (a.mask && g < a.mask_bytes) a.mask[m * a.mask_bytes + g] = (uint8_t)keep;
             }
+            // image column D carries 1.0: the weight-gradient GEMM then yields the bias gradient as
+            // its column D (sum_t dY[t,j] * 1); the forward GEMM's weight image is zero there
+            if (img && c <= a.D && a.D < c + 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (c + j == a.D) x[j] = 1.f;
+            }
             if (a.x_f32) {
                 if (c < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c) = make_float4(x[0], x[1], x[2], x[3]);
                 if (c + 4 < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c + 4) = make_float4(x[4], x[5], x[6], x[7]);

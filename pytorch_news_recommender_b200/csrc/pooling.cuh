@@ -194,6 +194,29 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
     out[c] = accumulate ? out[c] + s : s;
 }
 
+// Sum of split-K weight-gradient partials whose column `cols` carries the bias gradient (the
+// activation image has a ones column, gather.cuh): part [splits][rows][ldp] ->
+// dW[r, c] (c < cols, contiguous [rows, cols]) and db[r].  Fixed summation order over the splits.
+__global__ void reduce_wgrad_kernel(const float* __restrict__ part, int splits, int rows, int ldp, int cols,
+                                    float* __restrict__ dW, float* __restrict__ db) {
+    const long long per = (long long)rows * ldp;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * (cols + 1);
+         i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / (cols + 1)), c = (int)(i - (long long)r * (cols + 1));
+        const float* p = part + (long long)r * ldp + c;
+        float s0 = 0.f, s1 = 0.f;
+        int s = 0;
+        for (; s + 1 < splits; s += 2) {
+            s0 += p[s * per];
+            s1 += p[(s + 1) * per];
+        }
+        if (s < splits) s0 += p[s * per];
+        const float v = s0 + s1;
+        if (c < cols) dW[(long long)r * cols + c] = v;
+        else db[r] = v;
+    }
+}
+
 // first level of the two-level column sum: slice y sums rows [y*per, (y+1)*per) into tmp[y, :]
 __global__ void reduce_rows_sliced_kernel(const float* __restrict__ in, float* __restrict__ tmp,
                                           long long R, long long n, long long ld, long long per) {

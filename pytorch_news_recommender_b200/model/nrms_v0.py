@@ -60,7 +60,7 @@ def _gemm_mode(config) -> int:
     if gm is not None:
         return int(gm)
     d, q, h = config.word_embed_size, config.query_vector_dim, config.num_attention_heads
-    return 1 if (d <= 320 and q <= 208 and (d // h) % 2 == 0) else 0
+    return 1 if (d <= 316 and q <= 208 and (d // h) % 2 == 0) else 0
 
 
 class NewsEncoder(nn.Module):
