@@ -92,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)],
+                                          "-lms", "25", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -210,6 +210,17 @@ def algorithmic_counts():
                 adam_bytes_per_step=adam_bytes, titles_per_impr=N)
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of `kernel` per step, from the committed ncu
+    capture of this workload (profiles/ncu_traffic.json, written by scripts/ncu_traffic.py); None
+    when the capture has no entry for it."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    rec = json.load(open(p)).get("kernels", {}).get(kernel)
+    return rec["dram_bytes_per_step"] if rec else None
+
+
 KERNEL_WORK = {
     # kernel name -> (bound, algorithmic work per LAUNCH for n_seq sequences of length L)
     # flops for GEMMs (2*M*N*K), bytes for HBM-bound kernels
@@ -242,7 +253,7 @@ def kernel_work(name, B):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("NRMS_GEMM_MODE", "1")),
@@ -322,15 +333,16 @@ def main():
     def step_resident(i):
         trainer.step(resident[i % len(resident)])
 
-    for i in range(warmup):
-        step_resident(i)
+    # clocks are sampled from the warm-up to the end of the end-to-end region (the device is under
+    # load throughout; the timed regions alone can be shorter than one nvidia-smi sample)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(warmup):
+        step_resident(i)
     n0 = lib.nrms_launch_count()
     ms = timed(step_resident, K)
     launches = int(lib.nrms_launch_count() - n0)
-    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / K
     value = world * B * K / (ms / 1e3)
 
@@ -347,6 +359,7 @@ def main():
     e2e_value = world * B * K / (ms_e2e / 1e3)
     h2d = sum(pinned[0][k].numel() * pinned[0][k].element_size()
               for k in ("candidate_titles", "browsed_titles", "candidate_mask"))
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel breakdown (separate profiled pass, CUDA events per launch) ---------------
     roofline, breakdown = None, {}
@@ -378,7 +391,7 @@ def main():
             else:
                 achieved, peak, unit = work / sec / 1e9, peaks["hbm_gbs"], "GB/s"
             roofline = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                        "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] +
+                        "frac": achieved / peak, "traffic": ncu_traffic(name), "peak_source": peaks["source"] +
                         (" sustained bf16 (kernel timed inside the step)" if bound == "tensor" else " copy bandwidth"),
                         "share_of_step": rec["ms_per_step"] / total if total else None,
                         "ms_per_launch_group": rec["ms_per_step"]}

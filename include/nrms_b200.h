@@ -57,8 +57,10 @@ typedef struct nrms_encoder_dims {
     int32_t d_query;    /* config.query_vector_dim (200) */
     int32_t vocab;      /* rows of the word-embedding table (news encoder); 0 for user */
     float dropout_p;    /* config.dropout when training, 0 in eval (nrms_v0.py:137,171-173) */
-    int32_t gemm_mode;  /* 0 = fp32 CUDA-core GEMMs, 1 = tcgen05 split-bf16 (bf16x3, fp32-grade);
-                           mode 1 needs d_model <= 316, d_query <= 208 and an even head dim */
+    int32_t gemm_mode;  /* 0 = fp32 CUDA-core GEMMs, 1 = tcgen05 split-bf16 (bf16x3, fp32-grade),
+                           2 = tcgen05 plain bf16 (hi planes only: the "bf16" configs of BASELINE.json,
+                           looser parity bound); modes 1/2 need d_model <= 316, d_query <= 208 and
+                           an even head dim */
     uint64_t seed;      /* Philox key of this step's dropout masks */
 } nrms_encoder_dims;
 

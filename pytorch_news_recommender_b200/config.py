@@ -52,7 +52,7 @@ _NRMS_KNOBS = dict(
 
 # additions of this implementation ----------------------------------------------------------------
 _B200_KNOBS = dict(
-    gemm_mode=1,       # 1: tcgen05 split-bf16 (bf16x3, fp32-grade) GEMMs; 0: exact-fp32 CUDA-core GEMMs
+    gemm_mode=1,       # 1: tcgen05 split-bf16 (bf16x3, fp32-grade); 2: tcgen05 plain bf16; 0: fp32 CUDA-core GEMMs
     dropout_seed=0,    # base Philox key; training step t uses dropout_seed + t
 )
 

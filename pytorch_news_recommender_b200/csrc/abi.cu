@@ -127,7 +127,7 @@ Saved saved_layout(void* blob, const nrms_encoder_dims& d) {
     const int mb = mask_bytes_for(D);
     s.xmask = reinterpret_cast<uint8_t*>(take_bytes(M * mb));
     s.cmask = reinterpret_cast<uint8_t*>(take_bytes(M * mb));
-    if (d.gemm_mode == 1) {
+    if (d.gemm_mode >= 1) {
         s.x_img = ig::img_view(take_bytes(ig::img_bytes(M, kXChunks)), M, kXChunks);
         s.ctx_img = ig::img_view(take_bytes(ig::img_bytes(M, kXChunks)), M, kXChunks);
         s.wqkv_img = ig::img_view(take_bytes(ig::img_bytes(kWqkvRows, kXChunks)), kWqkvRows, kXChunks);
@@ -183,7 +183,7 @@ Scratch scratch_layout(void* blob, const nrms_encoder_dims& d) {
     Scratch s{};
     s.d_ctx = take(M * D);
     int64_t wpart;
-    if (d.gemm_mode == 1) {
+    if (d.gemm_mode >= 1) {
         s.d_pre_img = ig::img_view(take_bytes(ig::img_bytes(M, kPreChunks)), M, kPreChunks);
         s.d_qkv_img = ig::img_view(take_bytes(ig::img_bytes(M, kQkvChunks)), M, kQkvChunks);
         const int kch = ig::img_rows_pad(M) / 64;
@@ -223,9 +223,9 @@ int check_dims(const nrms_encoder_dims* d, bool news) {
         return fail(NRMS_ERR_BAD_SHAPE, "dropout_p=%f outside [0,1)", (double)d->dropout_p);
     if ((int64_t)d->n_seq * d->seq_len > 0x7fffffffll / 4)
         return fail(NRMS_ERR_BAD_SHAPE, "n_seq*seq_len too large");
-    if (d->gemm_mode != 0 && d->gemm_mode != 1)
+    if (d->gemm_mode < 0 || d->gemm_mode > 2)
         return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode=%d unknown", d->gemm_mode);
-    if (d->gemm_mode == 1) {
+    if (d->gemm_mode >= 1) {
         // tile shapes of the tcgen05 path (gemm_img.cuh): N tiles of 240 / 208 / 320 columns
         if (d->d_model > 316 || d->d_query > 208)
             return fail(NRMS_ERR_BAD_SHAPE, "gemm_mode 1 supports d_model <= 316 and d_query <= 208 "
@@ -300,6 +300,7 @@ ig::IgArgs ig_args(const ig::Img& A, const ig::Img& B, float* C, int ldc, int M,
     ig::IgArgs g{};
     g.A = A; g.B = B; g.C = C; g.ldc = ldc; g.M = M; g.N = N;
     g.splits = 1;
+    g.terms = 3;
     g.mask_scale = 1.f;
     return g;
 }
@@ -313,7 +314,8 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     (long long)sv.bytes);
     const int D = d.d_model, Q = d.d_query, L = d.seq_len, h = d.n_heads, dk = D / h;
     const int M = d.n_seq * L;
-    const bool tcm = d.gemm_mode == 1;
+    const bool tcm = d.gemm_mode >= 1;
+    const int terms = d.gemm_mode == 2 ? 1 : 3;   // mode 2: plain bf16 tensor-core products
     const ParamView pv = param_view<ParamView>(params, D, Q);
     const Dropout drop = make_dropout(d.dropout_p, d.seed);
     const int mb = mask_bytes_for(D);
@@ -339,6 +341,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         NRMS_CHECK_CUDA(ig::img_pack(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, s));
         NRMS_CHECK_CUDA(ig::img_pack(pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, sv.qkv, 3 * D, M, 3 * D);
+        g.terms = terms;
         g.bias = pv.bqkv;
         g.m_tiles = sv.x_img.rows_pad / 128; g.n_tiles = ceil_div(3 * D, 240);
         g.k_steps = ceil_div(D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
@@ -361,8 +364,14 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             // one independent warp per (sequence, head), products on mma.sync (attention_mma.cuh)
             const long long items = (long long)d.n_seq * h;
             const size_t smem = attn_mma_fwd_smem_bytes();
-            if ((rc = set_smem(attn_mma_fwd_kernel, smem))) return rc;
-            NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<<<(unsigned)ceil_div64(items, kMmaWarps), kMmaWarps * 32, smem, s>>>(a, items)));
+            const unsigned grid = (unsigned)ceil_div64(items, kMmaWarps);
+            if (terms == 3) {
+                if ((rc = set_smem(attn_mma_fwd_kernel<3>, smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<3><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+            } else {
+                if ((rc = set_smem(attn_mma_fwd_kernel<1>, smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<1><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+            }
         } else {
             const AttnCfg c = attn_fwd_cfg(L, h);
             a.hpb = c.hpb;
@@ -392,6 +401,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     //    epilogue also reduces a_l = t_l . q (nrms_v0.py:110)
     if (tcm) {
         ig::IgArgs g = ig_args(sv.ctx_img, sv.wa_img, sv.t, Q, M, Q);
+        g.terms = terms;
         g.bias = pv.ba; g.qv = pv.qv; g.dot_out = sv.score;
         g.m_tiles = sv.ctx_img.rows_pad / 128; g.n_tiles = 1;
         g.k_steps = ceil_div(D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
@@ -429,7 +439,8 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     (long long)sc.bytes);
     const int D = d.d_model, Q = d.d_query, L = d.seq_len, h = d.n_heads, dk = D / h;
     const int M = d.n_seq * L;
-    const bool tcm = d.gemm_mode == 1;
+    const bool tcm = d.gemm_mode >= 1;
+    const int terms = d.gemm_mode == 2 ? 1 : 3;
     const ParamView pv = param_view<ParamView>(params, D, Q);
     const GradView gv = param_view<GradView>(d_params, D, Q);
     const Dropout drop = make_dropout(news ? d.dropout_p : 0.f, d.seed);
@@ -458,6 +469,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     if (tcm) {
         // d_ctx = w_l * d_out (pooling path, formed in the epilogue) + d_pre W_a
         ig::IgArgs g = ig_args(sc.d_pre_img, sv.wa_img, sc.d_ctx, D, M, D);
+        g.terms = terms;
         g.m_tiles = tok_tiles; g.n_tiles = 1;
         g.k_steps = ceil_div(Q, 16); g.k_chunks = ceil_div(g.k_steps, 4);
         g.row_w = sv.w; g.seq_vec = d_out; g.seq_len = L;
@@ -465,6 +477,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
 
         // columns [0,D) = dW_a, column D = d_b_a (ones column of the context image)
         ig::IgArgs w = ig_args(sc.d_pre_img, sv.ctx_img, sc.wpart, D + 4, Q, D + 4);
+        w.terms = terms;
         w.m_tiles = ceil_div(Q, 128); w.n_tiles = 1;
         w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
         w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
@@ -504,8 +517,14 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         if (L <= kTile && dk % 2 == 0) {
             const long long items = (long long)d.n_seq * h;
             const size_t smem = attn_mma_bwd_smem_bytes();
-            if ((rc = set_smem(attn_mma_bwd_kernel, smem))) return rc;
-            NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<<<(unsigned)ceil_div64(items, kMmaWarps), kMmaWarps * 32, smem, s>>>(a, items)));
+            const unsigned grid = (unsigned)ceil_div64(items, kMmaWarps);
+            if (terms == 3) {
+                if ((rc = set_smem(attn_mma_bwd_kernel<3>, smem))) return rc;
+                NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<3><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+            } else {
+                if ((rc = set_smem(attn_mma_bwd_kernel<1>, smem))) return rc;
+                NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<1><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+            }
         } else {
             const AttnCfg c = attn_bwd_cfg(L, h);
             a.hpb = c.hpb;
@@ -528,6 +547,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     if (tcm) {
         // columns [0,D) = dW_qkv, column D = d_b_qkv (ones column of the input image)
         ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D + 4, 3 * D, D + 4);
+        w.terms = terms;
         w.m_tiles = ceil_div(3 * D, 128); w.n_tiles = 1;
         w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
         w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
@@ -538,6 +558,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         NRMS_CHECK_CUDA(cudaGetLastError());
         if (d_x) {
             ig::IgArgs g = ig_args(sc.d_qkv_img, sv.wqkv_img, d_x, D, M, D);
+            g.terms = terms;
             g.m_tiles = tok_tiles; g.n_tiles = 1;
             g.k_steps = ceil_div(3 * D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
             if (drop.enabled()) {

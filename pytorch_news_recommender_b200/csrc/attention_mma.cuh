@@ -13,7 +13,7 @@
 // A*B ~= Ahi*Bhi + Alo*Bhi + Ahi*Blo, fp32 accumulate — fp32-grade.
 //
 // One WARP owns one (sequence, head) and never synchronises with another warp.  Operands arrive
-// by cp.async into warp-private 32x40 fp32 slots (rows >= L, columns >= d_k zero).  The score
+// by cp.async into warp-private 32x36 fp32 slots (rows >= L, columns >= d_k zero).  The score
 // tile stays in the accumulator fragment layout (row g / g+8, columns 2t, 2t+1 of each 8-wide
 // tile; g = lane/4, t = lane%4): the row softmax is two shuffles over a quad, and P / dS feed the
 // next product as A fragments straight from registers (the accumulator layout of m16n8 IS the A
@@ -24,7 +24,7 @@
 namespace nrms {
 
 constexpr int kMS = 36;                 // slot row stride (floats): 3 CTAs of 4 warps fit an SM in the backward
-constexpr int kMSlot = kTile * kMS;     // floats per 32x40 slot
+constexpr int kMSlot = kTile * kMS;     // floats per slot
 constexpr int kMmaWarps = 4;
 
 __host__ __device__ inline size_t attn_mma_fwd_smem_bytes() {
@@ -46,11 +46,14 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// c += A*B with the 3-term split
+// c += A*B: TERMS = 3 with the 3-term split (fp32-grade), TERMS = 1 plain bf16 (gemm_mode 2)
+template <int TERMS>
 __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
                                      const uint32_t (&bhi)[2], const uint32_t (&blo)[2]) {
-    mma_bf16(c, alo, bhi[0], bhi[1]);
-    mma_bf16(c, ahi, blo[0], blo[1]);
+    if (TERMS == 3) {
+        mma_bf16(c, alo, bhi[0], bhi[1]);
+        mma_bf16(c, ahi, blo[0], blo[1]);
+    }
     mma_bf16(c, ahi, bhi[0], bhi[1]);
 }
 
@@ -85,6 +88,7 @@ __device__ __forceinline__ void load_b_frag_kn(uint32_t (&hi)[2], uint32_t (&lo)
 }
 
 // c[mt][nt] += A[32 x 32k] * B^T, both slots row-major over k:  S = Q K^T,  dP = dO V^T
+template <int TERMS>
 __device__ __forceinline__ void mma_abt(float (&c)[2][4][4], const float* A, const float* B, int g, int t) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -96,12 +100,13 @@ __device__ __forceinline__ void mma_abt(float (&c)[2][4][4], const float* A, con
             uint32_t bhi[2], blo[2];
             load_b_frag_nk(bhi, blo, B, nt, ks, g, t);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma3(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
+            for (int mt = 0; mt < 2; ++mt) mma3<TERMS>(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
         }
     }
 }
 // c[mt][nt] += P * B with P in the accumulator layout (registers) and B a [k][n] slot:
 // O = P V,  dQ = dS K
+template <int TERMS>
 __device__ __forceinline__ void mma_regA_b(float (&c)[2][4][4], const float (&p)[2][4][4], const float* B, int g, int t) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -118,12 +123,13 @@ __device__ __forceinline__ void mma_regA_b(float (&c)[2][4][4], const float (&p)
             uint32_t bhi[2], blo[2];
             load_b_frag_kn(bhi, blo, B, nt, ks, g, t);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma3(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
+            for (int mt = 0; mt < 2; ++mt) mma3<TERMS>(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
         }
     }
 }
 // c[mt][nt] += AT * B with AT a slot holding A^T as [m][k] and B a [k][n] slot:
 // dV = P^T dO (AT = P^T[key][row]),  dK = dS^T Q
+template <int TERMS>
 __device__ __forceinline__ void mma_a_b(float (&c)[2][4][4], const float* AT, const float* B, int g, int t) {
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
@@ -135,7 +141,7 @@ __device__ __forceinline__ void mma_a_b(float (&c)[2][4][4], const float* AT, co
             uint32_t bhi[2], blo[2];
             load_b_frag_kn(bhi, blo, B, nt, ks, g, t);
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) mma3(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
+            for (int mt = 0; mt < 2; ++mt) mma3<TERMS>(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
         }
     }
 }
@@ -175,6 +181,7 @@ __device__ __forceinline__ void store_frag_t(float* slot, const float (&c)[2][4]
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+template <int TERMS>
 __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const AttnArgs a, long long n_items) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -212,7 +219,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const Attn
 
     float s[2][4][4];
     zero_frag(s);
-    mma_abt(s, Qh, Kh, g, t);
+    mma_abt<TERMS>(s, Qh, Kh, g, t);
     // softmax over the keys: a row lives in the 4 lanes of a quad
     float inv[2][2];
 #pragma unroll
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const Attn
         }
     float o[2][4][4];
     zero_frag(o);
-    mma_regA_b(o, s, Vh, g, t);          // unnormalised P straight from registers
+    mma_regA_b<TERMS>(o, s, Vh, g, t);          // unnormalised P straight from registers
     __syncwarp();                        // all reads of K (scores) are long done; V reads done
     store_frag(Kh, o, inv, g, t);        // O = P V / rowsum over the dead K slot
     __syncwarp();
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const Attn
 //   P = exp(scale*Q K^T - lse) ; dP = dO V^T ; dS = scale * P o (dP - delta) ; delta = rowsum(dO o O)
 //   dV = P^T dO ; dK = dS^T Q ; dQ = dS K
 // ------------------------------------------------------------------------------------------------
+template <int TERMS>
 __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const AttnArgs a, long long n_items) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -336,8 +344,8 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const Attn
     float p[2][4][4], ds[2][4][4];
     zero_frag(p);
     zero_frag(ds);
-    mma_abt(p, Qh, Kh, g, t);            // S
-    mma_abt(ds, Gh, Vh, g, t);           // dP
+    mma_abt<TERMS>(p, Qh, Kh, g, t);            // S
+    mma_abt<TERMS>(ds, Gh, Vh, g, t);           // dP
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -358,20 +366,20 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const Attn
     float* sums = a.d_bias_part ? a.d_bias_part + seq * ld : nullptr;   // null: the weight-gradient GEMM makes them
     float acc[2][4][4];
     zero_frag(acc);
-    mma_a_b(acc, Vh, Gh, g, t);          // dV[key][d] = sum_row P^T[key][row] dO[row][d]
+    mma_a_b<TERMS>(acc, Vh, Gh, g, t);          // dV[key][d] = sum_row P^T[key][row] dO[row][d]
     __syncwarp();                        // all reads of P^T and dO are done
     store_frag(Vh, acc, one, g, t);      // dV over P^T
     store_frag_t(Gh, ds, g, t);          // dS^T[key][row] over dO
     __syncwarp();
     warp_write_slot<true, kMS>(Vh, L, dk, row0, 2 * D + col, a.d_qkv, ld, im, nullptr, 0, 1.f, sums, lane);
     zero_frag(acc);
-    mma_a_b(acc, Gh, Qh, g, t);          // dK[key][d] = sum_row dS^T[key][row] Q[row][d]
+    mma_a_b<TERMS>(acc, Gh, Qh, g, t);          // dK[key][d] = sum_row dS^T[key][row] Q[row][d]
     __syncwarp();                        // all reads of Q are done
     store_frag(Qh, acc, one, g, t);      // dK over Q
     __syncwarp();
     warp_write_slot<true, kMS>(Qh, L, dk, row0, D + col, a.d_qkv, ld, im, nullptr, 0, 1.f, sums, lane);
     zero_frag(acc);
-    mma_regA_b(acc, ds, Kh, g, t);       // dQ[row][d] = sum_key dS[row][key] K[key][d], dS from registers
+    mma_regA_b<TERMS>(acc, ds, Kh, g, t);       // dQ[row][d] = sum_key dS[row][key] K[key][d], dS from registers
     __syncwarp();                        // all reads of K are done
     store_frag(Kh, acc, one, g, t);      // dQ over K
     __syncwarp();

@@ -144,6 +144,7 @@ struct IgArgs {
     int k_chunks;               // 64-deep k chunks in total
     int k_steps;                // UMMA K=16 steps in total (<= 4*k_chunks)
     int splits;                 // k splits (weight gradient); 1 otherwise
+    int terms;                  // 3 = bf16x3 (fp32-grade), 1 = plain bf16 (hi planes only)
 };
 
 constexpr int IG_THREADS = 192;
@@ -154,7 +155,11 @@ __host__ __device__ constexpr int ig_stages(int n_t) {
 }
 // tail after the ring: 128 B of mbarriers + TMEM slot, then 2*N_T floats of epilogue staging
 // (bias / query vector; only the N_T <= 256 variants stage anything)
-__host__ __device__ constexpr int ig_tail_bytes(int n_t) { return n_t <= 256 ? 128 + 2 * 256 * 4 : 256; }
+// + (N_T <= 256 only: the 320-column variants have no shared memory left) one 32x36-float
+// transposition buffer per epilogue warp for coalesced stores
+constexpr int IG_XPOSE_STRIDE = 36;
+constexpr int IG_XPOSE_BYTES = 32 * IG_XPOSE_STRIDE * 4;
+__host__ __device__ constexpr int ig_tail_bytes(int n_t) { return n_t <= 256 ? 128 + 2 * 256 * 4 + 4 * IG_XPOSE_BYTES : 256; }
 __host__ __device__ constexpr int ig_smem_bytes(int n_t) {
     return ig_stages(n_t) * ig_stage_bytes(n_t) + 1024 /*alignment slack*/ + ig_tail_bytes(n_t);
 }
@@ -194,6 +199,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
     // bars: [0,S) full | [S,2S) empty | [2S,2S+2) acc full | [2S+2,2S+4) acc empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     float* s_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_B + 128);   // [2][256] floats (N_T <= 256 only)
+    constexpr bool XPOSE = N_T <= 256;   // stage the tile through shared memory for full-line stores
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = tc::smem_u32(smem);
@@ -235,18 +241,19 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                     const int s = it % STAGES;
                     tc::mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
                     const uint32_t dst = smem_base + s * STAGE_B;
-                    tc::mbar_arrive_expect_tx(full_bar(s), STAGE_B);
+                    const bool lo = a.terms == 3;     // plain-bf16 mode streams the hi planes only
+                    tc::mbar_arrive_expect_tx(full_bar(s), lo ? STAGE_B : STAGE_B / 2);
                     if (A_MN) {
 #pragma unroll
                         for (int b = 0; b < 2; ++b) {
                             const long long off = (long long)(m_tile * 2 + b) * a.A.chunk_stride + (long long)kc * IMG_BLOCK_B;
                             tc::bulk_g2s(dst + b * IMG_BLOCK_B, a.A.hi + off, IMG_BLOCK_B, full_bar(s));
-                            tc::bulk_g2s(dst + A_TILE_B + b * IMG_BLOCK_B, a.A.lo + off, IMG_BLOCK_B, full_bar(s));
+                            if (lo) tc::bulk_g2s(dst + A_TILE_B + b * IMG_BLOCK_B, a.A.lo + off, IMG_BLOCK_B, full_bar(s));
                         }
                     } else {
                         const long long off = (long long)kc * a.A.chunk_stride + (long long)m_tile * A_TILE_B;
                         tc::bulk_g2s(dst, a.A.hi + off, A_TILE_B, full_bar(s));
-                        tc::bulk_g2s(dst + A_TILE_B, a.A.lo + off, A_TILE_B, full_bar(s));
+                        if (lo) tc::bulk_g2s(dst + A_TILE_B, a.A.lo + off, A_TILE_B, full_bar(s));
                     }
                     const uint32_t dstb = dst + 2 * A_TILE_B;
                     if (B_MN) {
@@ -254,12 +261,12 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                         for (int b = 0; b < N_T / 64; ++b) {
                             const long long off = (long long)(n_tile * (N_T / 64) + b) * a.B.chunk_stride + (long long)kc * IMG_BLOCK_B;
                             tc::bulk_g2s(dstb + b * IMG_BLOCK_B, a.B.hi + off, IMG_BLOCK_B, full_bar(s));
-                            tc::bulk_g2s(dstb + B_PLANE_B + b * IMG_BLOCK_B, a.B.lo + off, IMG_BLOCK_B, full_bar(s));
+                            if (lo) tc::bulk_g2s(dstb + B_PLANE_B + b * IMG_BLOCK_B, a.B.lo + off, IMG_BLOCK_B, full_bar(s));
                         }
                     } else {
                         const long long off = (long long)kc * a.B.chunk_stride + (long long)n_tile * B_PLANE_B;
                         tc::bulk_g2s(dstb, a.B.hi + off, B_PLANE_B, full_bar(s));
-                        tc::bulk_g2s(dstb + B_PLANE_B, a.B.lo + off, B_PLANE_B, full_bar(s));
+                        if (lo) tc::bulk_g2s(dstb + B_PLANE_B, a.B.lo + off, B_PLANE_B, full_bar(s));
                     }
                 }
             }
@@ -297,14 +304,18 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                         const uint64_t b_lo = make_sw128_desc(sb + B_PLANE_B + j * B_ADV, B_LBO);
                         const uint32_t acc = (kc > c0 || j > 0) ? 1u : 0u;
                         tc::umma_bf16(d_tmem, a_hi, b_hi, idesc1, acc);
-                        tc::umma_bf16(d_tmem, a_lo, b_hi, idesc1, 1u);
-                        tc::umma_bf16(d_tmem, a_hi, b_lo, idesc1, 1u);
+                        if (a.terms == 3) {
+                            tc::umma_bf16(d_tmem, a_lo, b_hi, idesc1, 1u);
+                            tc::umma_bf16(d_tmem, a_hi, b_lo, idesc1, 1u);
+                        }
                         if (N2 > 0) {
                             const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
                             const uint64_t b2_lo = make_sw128_desc(sb + B_PLANE_B + B2_OFF + j * B_ADV, B_LBO);
                             tc::umma_bf16(d_tmem + N1, a_hi, b2_hi, idesc2, acc);
-                            tc::umma_bf16(d_tmem + N1, a_lo, b2_hi, idesc2, 1u);
-                            tc::umma_bf16(d_tmem + N1, a_hi, b2_lo, idesc2, 1u);
+                            if (a.terms == 3) {
+                                tc::umma_bf16(d_tmem + N1, a_lo, b2_hi, idesc2, 1u);
+                                tc::umma_bf16(d_tmem + N1, a_hi, b2_lo, idesc2, 1u);
+                            }
                         }
                     }
                     tc::umma_commit(empty_bar(s));   // frees the stage when these MMAs retire
@@ -351,8 +362,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                 rw = __ldg(a.row_w + m);
                 svec = a.seq_vec + (long long)(m / a.seq_len) * a.N + n0;
             }
-            float* crow = a.C + (EPI == EPI_PARTIAL ? (long long)split * a.c_split_stride : 0ll) +
-                          (long long)m * a.ldc + n0;
+            float* cbase = a.C + (EPI == EPI_PARTIAL ? (long long)split * a.c_split_stride : 0ll);
+            float* crow = cbase + (long long)m * a.ldc + n0;
+            float* s_x = s_epi + 2 * 256 + (warp - 2) * (IG_XPOSE_BYTES / 4);
             tc::mbar_wait(accf_bar(buf), use & 1u);
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(buf * ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
@@ -401,7 +413,30 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                         o.z = (bits & 4u) ? o.z * a.mask_scale : 0.f;
                         o.w = (bits & 8u) ? o.w * a.mask_scale : 0.f;
                     }
-                    if (row_ok && n0 + n < a.N) *reinterpret_cast<float4*>(crow + n) = o;
+                    if (XPOSE) {
+                        *reinterpret_cast<float4*>(s_x + lane * IG_XPOSE_STRIDE + 4 * g) = o;
+                    } else {
+                        if (row_ok && n0 + n < a.N) *reinterpret_cast<float4*>(crow + n) = o;
+                    }
+                }
+                if (XPOSE) {
+                    // TMEM gives a lane one ROW; a direct store would touch 32 lines per instruction.
+                    // Through the warp's 32x36 buffer a store instruction writes 4 rows x 128 B.
+                    __syncwarp();
+                    const int cc = lane & 7;
+                    const int n = cb + 4 * cc;
+                    if (n < N_T && n0 + n < a.N) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = 4 * i + (lane >> 3);
+                            const int mm = m_tile * 128 + q * 32 + rr;
+                            if (mm < a.M) {
+                                const float4 v = *reinterpret_cast<const float4*>(s_x + rr * IG_XPOSE_STRIDE + 4 * cc);
+                                *reinterpret_cast<float4*>(cbase + (long long)mm * a.ldc + n0 + n) = v;
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
             if (EPI == EPI_TANH_DOT && row_ok) a.dot_out[m] = dot;
