@@ -100,6 +100,18 @@ int nrms_news_encoder_bwd(const nrms_encoder_dims* d, const int64_t* ids, const 
                           int64_t saved_bytes, void* scratch, int64_t scratch_bytes,
                           float* d_params, float* d_rows, nrms_stream_t stream);
 
+/* The same backward in two calls, for data-parallel training: NRMS_BWD_DATA runs the
+ * data-gradient path (d_out -> d_rows, everything the embedding-table gradient needs),
+ * NRMS_BWD_PARAMS the weight/bias/query-vector gradients (d_params) from the scratch the first
+ * call left.  The table gradient's all-reduce is started between the two and overlaps the
+ * second (engine.FusedTrainer).  DATA must precede PARAMS on the same stream and blobs. */
+#define NRMS_BWD_DATA 1
+#define NRMS_BWD_PARAMS 2
+int nrms_news_encoder_bwd_phase(const nrms_encoder_dims* d, const int64_t* ids, const float* table,
+                                const float* params, const float* d_out, const void* saved,
+                                int64_t saved_bytes, void* scratch, int64_t scratch_bytes,
+                                float* d_params, float* d_rows, int32_t phase, nrms_stream_t stream);
+
 /* UserEncoder.forward (nrms_v0.py:188-199): x [n_seq, seq_len, d_model] -> out [n_seq, d_model] */
 int nrms_user_encoder_fwd(const nrms_encoder_dims* d, const float* x, const float* params,
                           float* out, void* saved, int64_t saved_bytes, nrms_stream_t stream);

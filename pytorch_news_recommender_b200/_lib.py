@@ -52,6 +52,7 @@ SIGNATURES = {
     "nrms_encoder_scratch_bytes": (_I64, [_DIMS]),
     "nrms_news_encoder_fwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P]),
     "nrms_news_encoder_bwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P]),
+    "nrms_news_encoder_bwd_phase": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I32, _P]),
     "nrms_user_encoder_fwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P]),
     "nrms_user_encoder_bwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P]),
     "nrms_score_fwd": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P]),

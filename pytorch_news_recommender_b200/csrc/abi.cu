@@ -8,7 +8,6 @@
 #include <cstring>
 
 #include "attention.cuh"
-#include "attention_tile.cuh"
 #include "attention_mma.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -427,7 +426,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
 int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_or_table,
                 const float* params, const float* d_out, const void* saved_blob,
                 int64_t saved_bytes, void* scratch_blob, int64_t scratch_bytes, float* d_params,
-                float* d_x, bool news, cudaStream_t s) {
+                float* d_x, bool news, int phases, cudaStream_t s) {
     (void)ids;
     const Saved sv = saved_layout(const_cast<void*>(saved_blob), d);
     if (saved_bytes < sv.bytes)
@@ -448,146 +447,161 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     const float* x_f32 = news ? sv.x_f32 : x_or_table;   // mode 0 operand of dW_qkv
     int rc;
 
-    // 1. pooling backward: d_ctx (pool path), d_pre, partials of d_b_a and d_query
-    {
-        PoolArgs p{};
-        p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.d_out = d_out;
-        p.d_part = sc.part_q;
-        if (tcm) p.d_pre_img = sc.d_pre_img; else { p.d_pre = sc.d_pre; p.d_ctx = sc.d_ctx; }
-        p.M = M; p.L = L; p.D = D; p.Q = Q;
-        NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
-        NRMS_CHECK_CUDA(cudaGetLastError());
-    }
-    // [d_b_a | d_query] are adjacent in the flat block, as in part_q; with the tcgen05 GEMMs d_b_a
-    // comes out of the weight-gradient GEMM (ones column of the context image) and only d_query
-    // is reduced here
-    rc = tcm ? reduce_rows(sc.part_q + Q, gv.qv, d.n_seq, Q, 2 * Q, 1.f, sc.red_tmp, s)
-             : reduce_rows(sc.part_q, gv.ba, d.n_seq, 2 * Q, 2 * Q, 1.f, sc.red_tmp, s);
-    if (rc) return rc;
     const int tok_tiles = ig::img_rows_pad(M) / 128;
-    // 2. d_ctx = pool path + d_pre W_a        3. dW_a = d_pre^T ctx (split over the token rows)
-    if (tcm) {
-        // d_ctx = w_l * d_out (pooling path, formed in the epilogue) + d_pre W_a
-        ig::IgArgs g = ig_args(sc.d_pre_img, sv.wa_img, sc.d_ctx, D, M, D);
-        g.terms = terms;
-        g.m_tiles = tok_tiles; g.n_tiles = 1;
-        g.k_steps = ceil_div(Q, 16); g.k_chunks = ceil_div(g.k_steps, 4);
-        g.row_w = sv.w; g.seq_vec = d_out; g.seq_len = L;
-        NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_POOLADD>(g, s, "gemm_dgrad_additive")));
+    const bool do_data = (phases & 1) != 0, do_params = (phases & 2) != 0;
 
-        // columns [0,D) = dW_a, column D = d_b_a (ones column of the context image)
-        ig::IgArgs w = ig_args(sc.d_pre_img, sv.ctx_img, sc.wpart, D + 4, Q, D + 4);
-        w.terms = terms;
-        w.m_tiles = ceil_div(Q, 128); w.n_tiles = 1;
-        w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
-        w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
-        w.c_split_stride = (long long)Q * (D + 4);
-        NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_additive")));
-        NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)Q * (D + 1), 256), 256, 0, s>>>(
-            sc.wpart, w.splits, Q, D + 4, D, gv.Wa, gv.ba));
-        NRMS_CHECK_CUDA(cudaGetLastError());
-    } else {
-        GemmArgs g{};
-        g.A = sc.d_pre; g.B = pv.Wa; g.C = sc.d_ctx;
-        g.M = M; g.N = D; g.K = Q; g.lda = Q; g.ldb = D; g.ldc = D;
-        g.k_chunk = Q; g.accumulate = 1;
-        NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_additive"));
-
-        const int splits = wgrad_splits_simt(Q, D, M);
-        GemmArgs w{};
-        w.A = sc.d_pre; w.B = sv.ctx; w.C = sc.wpart;
-        w.M = Q; w.N = D; w.K = M; w.lda = Q; w.ldb = D; w.ldc = D;
-        w.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
-        w.c_split_stride = (long long)Q * D;
-        NRMS_CHECK_CUDA(launch_gemm_simt(w, false, false, ceil_div(M, w.k_chunk), s, "gemm_wgrad_additive"));
-        rc = reduce_rows(sc.wpart, gv.Wa, ceil_div(M, w.k_chunk), (long long)Q * D,
-                         (long long)Q * D, 1.f, nullptr, s);
-        if (rc) return rc;
-    }
-    // 4. attention backward -> d_qkv and bias partials
-    {
-        AttnArgs a{};
-        a.qkv = sv.qkv; a.ctx = sv.ctx; a.lse = sv.lse; a.d_ctx = sc.d_ctx;
-        a.cmask = sv.cmask; a.mask_bytes = mb;
-        if (tcm) a.d_qkv_img = sc.d_qkv_img; else a.d_qkv = sc.d_qkv;
-        a.d_bias_part = tcm ? nullptr : sc.part_b;   // tcgen05 path: bias gradient = column D of dW_qkv
-        a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
-        a.scale = 1.f / sqrtf((float)dk);
-        a.drop = drop;
-        if (L <= kTile && dk % 2 == 0) {
-            const long long items = (long long)d.n_seq * h;
-            const size_t smem = attn_mma_bwd_smem_bytes();
-            const unsigned grid = (unsigned)ceil_div64(items, kMmaWarps);
-            if (terms == 3) {
-                if ((rc = set_smem(attn_mma_bwd_kernel<3>, smem))) return rc;
-                NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<3><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
-            } else {
-                if ((rc = set_smem(attn_mma_bwd_kernel<1>, smem))) return rc;
-                NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<1><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
-            }
-        } else {
-            const AttnCfg c = attn_bwd_cfg(L, h);
-            a.hpb = c.hpb;
-            const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
-            if (dk % 2 == 0) {
-                if ((rc = set_smem(attn_bwd_kernel<true>, c.smem))) return rc;
-                NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<true><<<grid, c.threads, c.smem, s>>>(a)));
-            } else {
-                if ((rc = set_smem(attn_bwd_kernel<false>, c.smem))) return rc;
-                NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<false><<<grid, c.threads, c.smem, s>>>(a)));
-            }
+    // ================= data-gradient path: d_out -> d_x (everything the caller's next step needs)
+    if (do_data) {
+        // 1. pooling backward: d_ctx (pool path), d_pre, partials of d_b_a and d_query
+        {
+            PoolArgs p{};
+            p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.d_out = d_out;
+            p.d_part = sc.part_q;
+            if (tcm) p.d_pre_img = sc.d_pre_img; else { p.d_pre = sc.d_pre; p.d_ctx = sc.d_ctx; }
+            p.M = M; p.L = L; p.D = D; p.Q = Q;
+            NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
+            NRMS_CHECK_CUDA(cudaGetLastError());
         }
-        NRMS_CHECK_CUDA(cudaGetLastError());
-    }
-    if (!tcm) {
-        rc = reduce_rows(sc.part_b, gv.bqkv, d.n_seq, 3 * D, 3 * D, 1.f, sc.red_tmp, s);
-        if (rc) return rc;
-    }
-    // 5. dW_qkv = d_qkv^T x        6. d_x = d_qkv W_qkv (x the embedding dropout mask)
-    if (tcm) {
-        // columns [0,D) = dW_qkv, column D = d_b_qkv (ones column of the input image)
-        ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D + 4, 3 * D, D + 4);
-        w.terms = terms;
-        w.m_tiles = ceil_div(3 * D, 128); w.n_tiles = 1;
-        w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
-        w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
-        w.c_split_stride = 3ll * D * (D + 4);
-        NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_qkv")));
-        NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for(3ll * D * (D + 1), 256), 256, 0, s>>>(
-            sc.wpart, w.splits, 3 * D, D + 4, D, gv.Wqkv, gv.bqkv));
-        NRMS_CHECK_CUDA(cudaGetLastError());
-        if (d_x) {
-            ig::IgArgs g = ig_args(sc.d_qkv_img, sv.wqkv_img, d_x, D, M, D);
+        // 2. d_ctx = pool path + d_pre W_a
+        if (tcm) {
+            // d_ctx = w_l * d_out (pooling path, formed in the epilogue) + d_pre W_a
+            ig::IgArgs g = ig_args(sc.d_pre_img, sv.wa_img, sc.d_ctx, D, M, D);
             g.terms = terms;
             g.m_tiles = tok_tiles; g.n_tiles = 1;
-            g.k_steps = ceil_div(3 * D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
-            if (drop.enabled()) {
-                g.mask_bits = reinterpret_cast<const uint32_t*>(sv.xmask);
-                g.mask_words = mb / 4;
-                g.mask_scale = drop.scale;
-            }
-            NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_MASK>(g, s, "gemm_dgrad_qkv")));
-        }
-    } else {
-        const int splits = wgrad_splits_simt(3 * D, D, M);
-        GemmArgs w{};
-        w.A = sc.d_qkv; w.B = x_f32; w.C = sc.wpart;
-        w.M = 3 * D; w.N = D; w.K = M; w.lda = 3 * D; w.ldb = D; w.ldc = D;
-        w.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
-        w.c_split_stride = 3ll * D * D;
-        NRMS_CHECK_CUDA(launch_gemm_simt(w, false, false, ceil_div(M, w.k_chunk), s, "gemm_wgrad_qkv"));
-        rc = reduce_rows(sc.wpart, gv.Wqkv, ceil_div(M, w.k_chunk), 3ll * D * D, 3ll * D * D, 1.f,
-                         nullptr, s);
-        if (rc) return rc;
-        if (d_x) {
+            g.k_steps = ceil_div(Q, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+            g.row_w = sv.w; g.seq_vec = d_out; g.seq_len = L;
+            NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_POOLADD>(g, s, "gemm_dgrad_additive")));
+        } else {
             GemmArgs g{};
-            g.A = sc.d_qkv; g.B = pv.Wqkv; g.C = d_x;
-            g.M = M; g.N = D; g.K = 3 * D; g.lda = 3 * D; g.ldb = D; g.ldc = D;
-            g.k_chunk = 3 * D;
-            if (drop.enabled()) {
-                g.mask = sv.xmask; g.mask_bytes = mb; g.mask_scale = drop.scale;
+            g.A = sc.d_pre; g.B = pv.Wa; g.C = sc.d_ctx;
+            g.M = M; g.N = D; g.K = Q; g.lda = Q; g.ldb = D; g.ldc = D;
+            g.k_chunk = Q; g.accumulate = 1;
+            NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_additive"));
+        }
+        // 4. attention backward -> d_qkv and bias partials
+        {
+            AttnArgs a{};
+            a.qkv = sv.qkv; a.ctx = sv.ctx; a.lse = sv.lse; a.d_ctx = sc.d_ctx;
+            a.cmask = sv.cmask; a.mask_bytes = mb;
+            if (tcm) a.d_qkv_img = sc.d_qkv_img; else a.d_qkv = sc.d_qkv;
+            a.d_bias_part = tcm ? nullptr : sc.part_b;   // tcgen05 path: bias gradient = column D of dW_qkv
+            a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
+            a.scale = 1.f / sqrtf((float)dk);
+            a.drop = drop;
+            if (L <= kTile && dk % 2 == 0) {
+                const long long items = (long long)d.n_seq * h;
+                const size_t smem = attn_mma_bwd_smem_bytes();
+                const unsigned grid = (unsigned)ceil_div64(items, kMmaWarps);
+                if (terms == 3) {
+                    if ((rc = set_smem(attn_mma_bwd_kernel<3>, smem))) return rc;
+                    NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<3><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+                } else {
+                    if ((rc = set_smem(attn_mma_bwd_kernel<1>, smem))) return rc;
+                    NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<1><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+                }
+            } else {
+                const AttnCfg c = attn_bwd_cfg(L, h);
+                a.hpb = c.hpb;
+                const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
+                if (dk % 2 == 0) {
+                    if ((rc = set_smem(attn_bwd_kernel<true>, c.smem))) return rc;
+                    NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<true><<<grid, c.threads, c.smem, s>>>(a)));
+                } else {
+                    if ((rc = set_smem(attn_bwd_kernel<false>, c.smem))) return rc;
+                    NRMS_LAUNCH("attn_bwd", s, (attn_bwd_kernel<false><<<grid, c.threads, c.smem, s>>>(a)));
+                }
             }
-            NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_qkv"));
+            NRMS_CHECK_CUDA(cudaGetLastError());
+        }
+        // 6. d_x = d_qkv W_qkv (x the embedding dropout mask)
+        if (tcm) {
+            if (d_x) {
+                ig::IgArgs g = ig_args(sc.d_qkv_img, sv.wqkv_img, d_x, D, M, D);
+                g.terms = terms;
+                g.m_tiles = tok_tiles; g.n_tiles = 1;
+                g.k_steps = ceil_div(3 * D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+                if (drop.enabled()) {
+                    g.mask_bits = reinterpret_cast<const uint32_t*>(sv.xmask);
+                    g.mask_words = mb / 4;
+                    g.mask_scale = drop.scale;
+                }
+                NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_MASK>(g, s, "gemm_dgrad_qkv")));
+            }
+        } else {
+            if (d_x) {
+                GemmArgs g{};
+                g.A = sc.d_qkv; g.B = pv.Wqkv; g.C = d_x;
+                g.M = M; g.N = D; g.K = 3 * D; g.lda = 3 * D; g.ldb = D; g.ldc = D;
+                g.k_chunk = 3 * D;
+                if (drop.enabled()) {
+                    g.mask = sv.xmask; g.mask_bytes = mb; g.mask_scale = drop.scale;
+                }
+                NRMS_CHECK_CUDA(launch_gemm_simt(g, true, false, 1, s, "gemm_dgrad_qkv"));
+            }
+        }
+    }
+    // ================= parameter gradients (off the data path: a data-parallel caller overlaps
+    // them with the all-reduce of the embedding-table gradient)
+    if (do_params) {
+        // [d_b_a | d_query] are adjacent in the flat block, as in part_q; with the tcgen05 GEMMs d_b_a
+        // comes out of the weight-gradient GEMM (ones column of the context image) and only d_query
+        // is reduced here
+        rc = tcm ? reduce_rows(sc.part_q + Q, gv.qv, d.n_seq, Q, 2 * Q, 1.f, sc.red_tmp, s)
+                 : reduce_rows(sc.part_q, gv.ba, d.n_seq, 2 * Q, 2 * Q, 1.f, sc.red_tmp, s);
+        if (rc) return rc;
+        // 3. dW_a = d_pre^T ctx (split over the token rows)
+        if (tcm) {
+            // columns [0,D) = dW_a, column D = d_b_a (ones column of the context image)
+            ig::IgArgs w = ig_args(sc.d_pre_img, sv.ctx_img, sc.wpart, D + 4, Q, D + 4);
+            w.terms = terms;
+            w.m_tiles = ceil_div(Q, 128); w.n_tiles = 1;
+            w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
+            w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
+            w.c_split_stride = (long long)Q * (D + 4);
+            NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_additive")));
+            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)Q * (D + 1), 256), 256, 0, s>>>(
+                sc.wpart, w.splits, Q, D + 4, D, gv.Wa, gv.ba));
+            NRMS_CHECK_CUDA(cudaGetLastError());
+        } else {
+            const int splits = wgrad_splits_simt(Q, D, M);
+            GemmArgs w{};
+            w.A = sc.d_pre; w.B = sv.ctx; w.C = sc.wpart;
+            w.M = Q; w.N = D; w.K = M; w.lda = Q; w.ldb = D; w.ldc = D;
+            w.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
+            w.c_split_stride = (long long)Q * D;
+            NRMS_CHECK_CUDA(launch_gemm_simt(w, false, false, ceil_div(M, w.k_chunk), s, "gemm_wgrad_additive"));
+            rc = reduce_rows(sc.wpart, gv.Wa, ceil_div(M, w.k_chunk), (long long)Q * D,
+                             (long long)Q * D, 1.f, nullptr, s);
+            if (rc) return rc;
+        }
+        if (!tcm) {
+            rc = reduce_rows(sc.part_b, gv.bqkv, d.n_seq, 3 * D, 3 * D, 1.f, sc.red_tmp, s);
+            if (rc) return rc;
+        }
+        // 5. dW_qkv = d_qkv^T x
+        if (tcm) {
+            // columns [0,D) = dW_qkv, column D = d_b_qkv (ones column of the input image)
+            ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D + 4, 3 * D, D + 4);
+            w.terms = terms;
+            w.m_tiles = ceil_div(3 * D, 128); w.n_tiles = 1;
+            w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
+            w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
+            w.c_split_stride = 3ll * D * (D + 4);
+            NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_qkv")));
+            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for(3ll * D * (D + 1), 256), 256, 0, s>>>(
+                sc.wpart, w.splits, 3 * D, D + 4, D, gv.Wqkv, gv.bqkv));
+            NRMS_CHECK_CUDA(cudaGetLastError());
+        } else {
+            const int splits = wgrad_splits_simt(3 * D, D, M);
+            GemmArgs w{};
+            w.A = sc.d_qkv; w.B = x_f32; w.C = sc.wpart;
+            w.M = 3 * D; w.N = D; w.K = M; w.lda = 3 * D; w.ldb = D; w.ldc = D;
+            w.k_chunk = (int)align_up(ceil_div(M, splits), GBK);
+            w.c_split_stride = 3ll * D * D;
+            NRMS_CHECK_CUDA(launch_gemm_simt(w, false, false, ceil_div(M, w.k_chunk), s, "gemm_wgrad_qkv"));
+            rc = reduce_rows(sc.wpart, gv.Wqkv, ceil_div(M, w.k_chunk), 3ll * D * D, 3ll * D * D, 1.f,
+                             nullptr, s);
+            if (rc) return rc;
         }
     }
     return NRMS_OK;
@@ -643,7 +657,21 @@ int nrms_news_encoder_bwd(const nrms_encoder_dims* d, const int64_t* ids, const 
     NRMS_REQUIRE_PTR(d_out); NRMS_REQUIRE_PTR(saved); NRMS_REQUIRE_PTR(scratch);
     NRMS_REQUIRE_PTR(d_params); NRMS_REQUIRE_PTR(d_rows);
     return encoder_bwd(*d, ids, table, params, d_out, saved, saved_bytes, scratch, scratch_bytes,
-                       d_params, d_rows, true, (cudaStream_t)stream);
+                       d_params, d_rows, true, 3, (cudaStream_t)stream);
+}
+int nrms_news_encoder_bwd_phase(const nrms_encoder_dims* d, const int64_t* ids, const float* table,
+                                const float* params, const float* d_out, const void* saved,
+                                int64_t saved_bytes, void* scratch, int64_t scratch_bytes,
+                                float* d_params, float* d_rows, int32_t phase, nrms_stream_t stream) {
+    int rc = check_dims(d, true);
+    if (rc) return rc;
+    if (phase != NRMS_BWD_DATA && phase != NRMS_BWD_PARAMS)
+        return fail(NRMS_ERR_BAD_SHAPE, "phase=%d (expected NRMS_BWD_DATA or NRMS_BWD_PARAMS)", phase);
+    NRMS_REQUIRE_PTR(ids); NRMS_REQUIRE_PTR(table); NRMS_REQUIRE_PTR(params);
+    NRMS_REQUIRE_PTR(d_out); NRMS_REQUIRE_PTR(saved); NRMS_REQUIRE_PTR(scratch);
+    NRMS_REQUIRE_PTR(d_params); NRMS_REQUIRE_PTR(d_rows);
+    return encoder_bwd(*d, ids, table, params, d_out, saved, saved_bytes, scratch, scratch_bytes,
+                       d_params, d_rows, true, phase, (cudaStream_t)stream);
 }
 int nrms_user_encoder_fwd(const nrms_encoder_dims* d, const float* x, const float* params,
                           float* out, void* saved, int64_t saved_bytes, nrms_stream_t stream) {
@@ -667,7 +695,7 @@ int nrms_user_encoder_bwd(const nrms_encoder_dims* d, const float* x, const floa
     nrms_encoder_dims dd = *d;
     dd.dropout_p = 0.f;
     return encoder_bwd(dd, nullptr, x, params, d_out, saved, saved_bytes, scratch, scratch_bytes,
-                       d_params, d_x, false, (cudaStream_t)stream);
+                       d_params, d_x, false, 3, (cudaStream_t)stream);
 }
 
 static int score_check(int32_t B, int32_t C, int32_t D) {

@@ -1,6 +1,6 @@
 // attention_mma.cuh — self-attention for sequences of up to 32 tokens (the title encoder) with the
 // per-head 32x32x32 products on the tensor cores, forward and backward.  Same math and I/O
-// contract as attention.cuh / attention_tile.cuh (reference nrms_v0.py:13-23, 46-76, 171-173).
+// contract as attention.cuh (reference nrms_v0.py:13-23, 46-76, 171-173).
 //
 // Why: with CUDA-core FMAs a head's products are bound by shared-memory bandwidth (each lane
 // re-reads its operands for every k: 3 x 16-byte reads per 32 FMAs, 4 wavefronts each).  With
@@ -19,9 +19,116 @@
 // next product as A fragments straight from registers (the accumulator layout of m16n8 IS the A
 // layout of m16n8k16).  P^T / dS^T for the backward's transposed products go through a dead slot.
 #pragma once
-#include "attention_tile.cuh"
+#include "attention.cuh"
 
 namespace nrms {
+
+constexpr int kTile = 32;               // rows / columns of a head's score tile
+
+// Warp-private cp.async load of columns [col, col+dk) of rows [row0, row0+L) into one 32x36
+// slot; rows >= L and columns in [dk, 36) are zero-filled with plain stores.  16 lanes walk the
+// even rows, 16 the odd rows, each lane owning one 2-column unit.
+template <int RS = kRowStride>
+__device__ __forceinline__ void load_slot_async(float* slot, const float* src, long long row0, int ld,
+                                                int col, int L, int dk, int lane) {
+    const int pp = lane & 15, par = lane >> 4;
+    if (2 * pp < dk) {
+        const float* g = src + (row0 + par) * ld + col + 2 * pp;
+        uint32_t t = (uint32_t)__cvta_generic_to_shared(slot + par * RS + 2 * pp);
+        for (int l = par; l < L; l += 2) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(t), "l"(g) : "memory");
+            t += 2 * RS * 4;
+            g += 2 * ld;
+        }
+    }
+    {
+        float* row = slot + lane * RS;      // lane = slot row
+        if (lane < L) {
+            for (int d = dk; d < RS; d += 2) *reinterpret_cast<float2*>(row + d) = make_float2(0.f, 0.f);
+        } else {
+#pragma unroll
+            for (int d = 0; d < RS; d += 4) *reinterpret_cast<float4*>(row + d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// Warp-level write-out of a finished 32x36 slot (rows [0,L), columns [0,dk)) to global column
+// gcol0 + c of an fp32 matrix (may be null) and/or a split-bf16 image; optional dropout keep
+// bits smask[row*8 + (col>>3) - g0]; SUMS adds the per-sequence column sums (bias partials).
+// 16 lanes per row (one 2-column unit each), two rows per pass of a ROLLED loop: the code stays
+// small (the kernels are instruction-fetch sensitive) and every store is coalesced.
+template <bool SUMS, int RS = kRowStride>
+__device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk, long long row0, int gcol0, float* out,
+                                                int ld, const ig::Img& img, const uint8_t* smask, int g0,
+                                                float drop_scale, float* sums, int lane) {
+    const int c = (lane & 15) << 1, par = lane >> 4;
+    const bool active = c < dk;
+    const int col = gcol0 + c, g = col >> 3, gu = g & 7;
+    const bool has_img = img.hi != nullptr;
+    const long long choff = has_img ? (long long)(g >> 3) * img.chunk_stride + (col & 7) * 2 : 0;
+#pragma unroll 1
+    for (int l = par; l < L; l += 2) {
+        if (!active) continue;
+        float2 v = *reinterpret_cast<const float2*>(slot + l * RS + c);
+        if (smask) {
+            const uint32_t keep = (uint32_t)smask[l * 8 + g - g0] >> (col & 7);
+            v.x = (keep & 1u) ? v.x * drop_scale : 0.f;
+            v.y = (keep & 2u) ? v.y * drop_scale : 0.f;
+        }
+        const long long r = row0 + l;
+        if (out) *reinterpret_cast<float2*>(out + r * ld + col) = v;
+        if (has_img) {
+            __nv_bfloat16 h0b, l0b, h1b, l1b;
+            tc::split_bf16(v.x, h0b, l0b);
+            tc::split_bf16(v.y, h1b, l1b);
+            const int r7 = (int)(r & 7);
+            const long long off = choff + (r >> 3) * 1024 + r7 * 128 + ((gu ^ r7) << 4);
+            *reinterpret_cast<uint32_t*>(img.hi + off) =
+                (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
+            *reinterpret_cast<uint32_t*>(img.lo + off) =
+                (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+        }
+    }
+    if (SUMS && sums != nullptr && lane < dk) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+        for (int l = 0; l + 1 < L; l += 2) {
+            s0 += slot[l * RS + lane];
+            s1 += slot[(l + 1) * RS + lane];
+        }
+        if (L & 1) s0 += slot[(L - 1) * RS + lane];
+        sums[gcol0 + lane] = s0 + s1;
+    }
+}
+// padding of an image the kernel fills: columns [c0, c1) of this sequence's rows by the warp of
+// the last head (zero; with `ones_col` column c0 is 1.0 so that the weight-gradient GEMM yields
+// the bias gradient as its column c0), rows [M, rows_pad) by the very last warp of the grid
+__device__ __forceinline__ void pad_image(const ig::Img& img, long long row0, int L, int c0, int c1, bool last_head,
+                                          bool last_item, long long M, int lane, bool ones_col = false) {
+    if (last_head) {
+        const int np = (c1 - c0) >> 1;
+        for (int i = lane; i < L * np; i += 32) {
+            const int l = i / np, col = c0 + ((i - l * np) << 1);
+            const long long off = ig::img_unit_off(img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
+            *reinterpret_cast<uint32_t*>(img.hi + off) = (ones_col && col == c0) ? 0x00003F80u : 0u;   // bf16 {1.0, 0.0}
+            *reinterpret_cast<uint32_t*>(img.lo + off) = 0u;
+        }
+    }
+    if (last_item) {
+        const int groups = img.chunks * 8;
+        const long long npad = img.rows_pad - M;
+        for (long long i = lane; i < npad * groups; i += 32) ig::img_store8_zero(img, M + i / groups, (int)(i % groups));
+    }
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+    return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
 
 constexpr int kMS = 36;                 // slot row stride (floats): 3 CTAs of 4 warps fit an SM in the backward
 constexpr int kMSlot = kTile * kMS;     // floats per slot

@@ -98,14 +98,23 @@ def news_encoder_fwd(shape: EncoderShape, ids, table, params, saved, dropout_p=0
     return out
 
 
+BWD_DATA, BWD_PARAMS = 1, 2
+
+
 def news_encoder_bwd(shape: EncoderShape, ids, table, params, d_out, saved, scratch, d_params,
-                     d_rows, dropout_p=0.0, seed=0, gemm_mode=0):
+                     d_rows, dropout_p=0.0, seed=0, gemm_mode=0, phase: Optional[int] = None):
+    """phase None: the whole backward; BWD_DATA / BWD_PARAMS: its two halves (include/nrms_b200.h)."""
     _require_cuda(ids, table, params, d_out, saved, scratch, d_params, d_rows)
     d = shape.dims(dropout_p, seed, gemm_mode)
-    check(_lib.load().nrms_news_encoder_bwd(d, ptr(ids), ptr(table), ptr(params), ptr(d_out),
-                                            ptr(saved), saved.numel(), ptr(scratch),
-                                            scratch.numel(), ptr(d_params), ptr(d_rows), _stream()),
-          "nrms_news_encoder_bwd")
+    lib = _lib.load()
+    if phase is None:
+        check(lib.nrms_news_encoder_bwd(d, ptr(ids), ptr(table), ptr(params), ptr(d_out), ptr(saved),
+                                        saved.numel(), ptr(scratch), scratch.numel(), ptr(d_params),
+                                        ptr(d_rows), _stream()), "nrms_news_encoder_bwd")
+    else:
+        check(lib.nrms_news_encoder_bwd_phase(d, ptr(ids), ptr(table), ptr(params), ptr(d_out), ptr(saved),
+                                              saved.numel(), ptr(scratch), scratch.numel(), ptr(d_params),
+                                              ptr(d_rows), int(phase), _stream()), "nrms_news_encoder_bwd_phase")
 
 
 def user_encoder_fwd(shape: EncoderShape, x, params, saved, gemm_mode=0, out=None):
