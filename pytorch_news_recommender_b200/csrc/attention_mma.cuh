@@ -396,9 +396,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const Attn
     load_slot_async<kMS>(Kh, a.qkv, row0, ld, D + col, L, dk, lane);
     load_slot_async<kMS>(Vh, a.qkv, row0, ld, 2 * D + col, L, dk, lane);
     load_slot_async<kMS>(Gh, a.d_ctx, row0, D, col, L, dk, lane);
-    // rows of this lane in the accumulator layout: r(mt,hf) = 16mt + 8hf + g ; the quad splits a
-    // row's 32 columns into 8-column pieces for delta_i = sum_d d_ctx * ctx (post-dropout both)
-    float2 ov[2][2][4];
+    // rows of this lane in the accumulator layout: r(mt,hf) = 16mt + 8hf + g
     float lse[2][2];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -406,29 +404,10 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const Attn
         for (int hf = 0; hf < 2; ++hf) {
             const int r = 16 * mt + 8 * hf + g;
             lse[mt][hf] = r < L ? a.lse[(row0 + r) * a.n_heads + h] : 0.f;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int d = 8 * t + 2 * c;
-                ov[mt][hf][c] = (r < L && d < dk) ? __ldg(reinterpret_cast<const float2*>(a.ctx + (row0 + r) * D + col + d))
-                                                  : make_float2(0.f, 0.f);
-            }
         }
     cp_async_wait_all();
     __syncwarp();
 
-    float delta[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            const float* gp = Gh + (16 * mt + 8 * hf + g) * kMS + 8 * t;
-            const float4 g0v = *reinterpret_cast<const float4*>(gp), g1v = *reinterpret_cast<const float4*>(gp + 4);
-            float dl = g0v.x * ov[mt][hf][0].x;
-            dl = fmaf(g0v.y, ov[mt][hf][0].y, dl); dl = fmaf(g0v.z, ov[mt][hf][1].x, dl); dl = fmaf(g0v.w, ov[mt][hf][1].y, dl);
-            dl = fmaf(g1v.x, ov[mt][hf][2].x, dl); dl = fmaf(g1v.y, ov[mt][hf][2].y, dl);
-            dl = fmaf(g1v.z, ov[mt][hf][3].x, dl); dl = fmaf(g1v.w, ov[mt][hf][3].y, dl);
-            delta[mt][hf] = quad_sum(dl);
-        }
     if (drop) {
         // dO = d_ctx * keep/(1-p), in place: 16 lanes per row, two rows per pass
         __syncwarp();
@@ -453,6 +432,9 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const Attn
     zero_frag(ds);
     mma_abt<TERMS>(p, Qh, Kh, g, t);            // S
     mma_abt<TERMS>(ds, Gh, Vh, g, t);           // dP
+    // P, then delta_i = sum_d dO_id O_id = sum_j P_ij dP_ij (O = P V): a row sum over the quad, no
+    // extra operand; then dS = scale * P o (dP - delta)
+    float delta[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
@@ -463,8 +445,18 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_bwd_kernel(const Attn
                 const bool ok = (16 * mt + 8 * hf + g < L) && (8 * nt + 2 * t + (i & 1) < L);
                 const float pv = ok ? __expf(p[mt][nt][i] * a.scale - lse[mt][hf]) : 0.f;
                 p[mt][nt][i] = pv;
-                ds[mt][nt][i] = ok ? pv * (ds[mt][nt][i] - delta[mt][hf]) * a.scale : 0.f;
+                delta[mt][hf] = fmaf(pv, ds[mt][nt][i], delta[mt][hf]);
             }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) delta[mt][hf] = quad_sum(delta[mt][hf]);
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ds[mt][nt][i] = p[mt][nt][i] * (ds[mt][nt][i] - delta[mt][i >> 1]) * a.scale;
     __syncwarp();                        // all reads of V (dP) are done
     store_frag_t(Vh, p, g, t);           // P^T[key][row] over V
     __syncwarp();
