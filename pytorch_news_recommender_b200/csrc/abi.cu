@@ -363,13 +363,13 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             // one independent warp per (sequence, head), products on mma.sync (attention_mma.cuh)
             const long long items = (long long)d.n_seq * h;
             const size_t smem = attn_mma_fwd_smem_bytes();
-            const unsigned grid = (unsigned)ceil_div64(items, kMmaWarps);
+            const unsigned grid = (unsigned)ceil_div64(items, kMmaWarpsFwd);
             if (terms == 3) {
                 if ((rc = set_smem(attn_mma_fwd_kernel<3>, smem))) return rc;
-                NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<3><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+                NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<3><<<grid, kMmaWarpsFwd * 32, smem, s>>>(a, items)));
             } else {
                 if ((rc = set_smem(attn_mma_fwd_kernel<1>, smem))) return rc;
-                NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<1><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
+                NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<1><<<grid, kMmaWarpsFwd * 32, smem, s>>>(a, items)));
             }
         } else {
             const AttnCfg c = attn_fwd_cfg(L, h);

@@ -25,6 +25,12 @@ namespace nrms {
 
 constexpr int kTile = 32;               // rows / columns of a head's score tile
 
+// (x, y) -> packed bf16 pairs: hi = {bf16(x) low, bf16(y) high}, lo = the same of the residuals
+__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+    const float hx = __uint_as_float(hi << 16), hy = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(y - hy), "f"(x - hx));
+}
 // Warp-private cp.async load of columns [col, col+dk) of rows [row0, row0+L) into one 32x36
 // slot; rows >= L and columns in [dk, 36) are zero-filled with plain stores.  16 lanes walk the
 // even rows, 16 the odd rows, each lane owning one 2-column unit.
@@ -52,41 +58,54 @@ __device__ __forceinline__ void load_slot_async(float* slot, const float* src, l
     }
 }
 
-// Warp-level write-out of a finished 32x36 slot (rows [0,L), columns [0,dk)) to global column
-// gcol0 + c of an fp32 matrix (may be null) and/or a split-bf16 image; optional dropout keep
-// bits smask[row*8 + (col>>3) - g0]; SUMS adds the per-sequence column sums (bias partials).
-// 16 lanes per row (one 2-column unit each), two rows per pass of a ROLLED loop: the code stays
-// small (the kernels are instruction-fetch sensitive) and every store is coalesced.
+// Warp-level write-out of a finished slot (rows [0,L), columns [0,dk)) to global column gcol0 + c
+// of an fp32 matrix (may be null) and/or a split-bf16 image; optional dropout keep bits
+// smask[row*8 + (col>>3) - g0]; SUMS adds the per-sequence column sums (bias partials).
+// 8 lanes per row (one 16-byte / 4-column read each), four rows per pass of a ROLLED loop: the
+// code stays small (the kernels are instruction-fetch sensitive) and every store is coalesced.
+// gcol0 and dk are even, so a lane's four columns are two aligned 2-column pairs.
 template <bool SUMS, int RS = kRowStride>
 __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk, long long row0, int gcol0, float* out,
                                                 int ld, const ig::Img& img, const uint8_t* smask, int g0,
                                                 float drop_scale, float* sums, int lane) {
-    const int c = (lane & 15) << 1, par = lane >> 4;
-    const bool active = c < dk;
-    const int col = gcol0 + c, g = col >> 3, gu = g & 7;
+    const int c = (lane & 7) << 2, rsub = lane >> 3;
+    const bool act0 = c < dk, act1 = c + 2 < dk;
     const bool has_img = img.hi != nullptr;
-    const long long choff = has_img ? (long long)(g >> 3) * img.chunk_stride + (col & 7) * 2 : 0;
+    const int col0 = gcol0 + c, col1 = col0 + 2;
+    const int ga = col0 >> 3, gb = col1 >> 3;
+    const long long ch0 = has_img ? (long long)(ga >> 3) * img.chunk_stride + (col0 & 7) * 2 : 0;
+    const long long ch1 = has_img ? (long long)(gb >> 3) * img.chunk_stride + (col1 & 7) * 2 : 0;
 #pragma unroll 1
-    for (int l = par; l < L; l += 2) {
-        if (!active) continue;
-        float2 v = *reinterpret_cast<const float2*>(slot + l * RS + c);
+    for (int l = rsub; l < L; l += 4) {
+        if (!act0) continue;
+        float4 v = *reinterpret_cast<const float4*>(slot + l * RS + c);
         if (smask) {
-            const uint32_t keep = (uint32_t)smask[l * 8 + g - g0] >> (col & 7);
-            v.x = (keep & 1u) ? v.x * drop_scale : 0.f;
-            v.y = (keep & 2u) ? v.y * drop_scale : 0.f;
+            const uint32_t k0 = (uint32_t)smask[l * 8 + ga - g0] >> (col0 & 7);
+            const uint32_t k1 = (uint32_t)smask[l * 8 + gb - g0] >> (col1 & 7);
+            v.x = (k0 & 1u) ? v.x * drop_scale : 0.f;
+            v.y = (k0 & 2u) ? v.y * drop_scale : 0.f;
+            v.z = (k1 & 1u) ? v.z * drop_scale : 0.f;
+            v.w = (k1 & 2u) ? v.w * drop_scale : 0.f;
         }
         const long long r = row0 + l;
-        if (out) *reinterpret_cast<float2*>(out + r * ld + col) = v;
+        if (out) {
+            *reinterpret_cast<float2*>(out + r * ld + col0) = make_float2(v.x, v.y);
+            if (act1) *reinterpret_cast<float2*>(out + r * ld + col1) = make_float2(v.z, v.w);
+        }
         if (has_img) {
-            __nv_bfloat16 h0b, l0b, h1b, l1b;
-            tc::split_bf16(v.x, h0b, l0b);
-            tc::split_bf16(v.y, h1b, l1b);
             const int r7 = (int)(r & 7);
-            const long long off = choff + (r >> 3) * 1024 + r7 * 128 + ((gu ^ r7) << 4);
-            *reinterpret_cast<uint32_t*>(img.hi + off) =
-                (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-            *reinterpret_cast<uint32_t*>(img.lo + off) =
-                (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+            const long long rbase = (r >> 3) * 1024 + r7 * 128;
+            uint32_t hi, lo;
+            split_pair(v.x, v.y, hi, lo);
+            long long off = ch0 + rbase + (((ga & 7) ^ r7) << 4);
+            *reinterpret_cast<uint32_t*>(img.hi + off) = hi;
+            *reinterpret_cast<uint32_t*>(img.lo + off) = lo;
+            if (act1) {
+                split_pair(v.z, v.w, hi, lo);
+                off = ch1 + rbase + (((gb & 7) ^ r7) << 4);
+                *reinterpret_cast<uint32_t*>(img.hi + off) = hi;
+                *reinterpret_cast<uint32_t*>(img.lo + off) = lo;
+            }
         }
     }
     if (SUMS && sums != nullptr && lane < dk) {
@@ -132,21 +151,16 @@ __device__ __forceinline__ float quad_sum(float v) {
 
 constexpr int kMS = 36;                 // slot row stride (floats): 3 CTAs of 4 warps fit an SM in the backward
 constexpr int kMSlot = kTile * kMS;     // floats per slot
-constexpr int kMmaWarps = 4;
+constexpr int kMmaWarps = 4;            // backward: 4 slots per warp, 3 CTAs per SM
+constexpr int kMmaWarpsFwd = 4;         // forward (5 warps/CTA measured slower: less L1 left beside the slots)
 
 __host__ __device__ inline size_t attn_mma_fwd_smem_bytes() {
-    return (size_t)kMmaWarps * (3 * kMSlot * sizeof(float) + kTile * 8);
+    return (size_t)kMmaWarpsFwd * (3 * kMSlot * sizeof(float) + kTile * 8);
 }
 __host__ __device__ inline size_t attn_mma_bwd_smem_bytes() {
     return (size_t)kMmaWarps * 4 * kMSlot * sizeof(float);
 }
 
-// (x, y) -> packed bf16 pairs: hi = {bf16(x) low, bf16(y) high}, lo = the same of the residuals
-__device__ __forceinline__ void split_pair(float x, float y, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
-    const float hx = __uint_as_float(hi << 16), hy = __uint_as_float(hi & 0xffff0000u);
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(y - hy), "f"(x - hx));
-}
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -289,10 +303,10 @@ __device__ __forceinline__ void store_frag_t(float* slot, const float (&c)[2][4]
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int TERMS>
-__global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const AttnArgs a, long long n_items) {
+__global__ void __launch_bounds__(kMmaWarpsFwd * 32) attn_mma_fwd_kernel(const AttnArgs a, long long n_items) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * kMmaWarps + warp;
+    const long long item = (long long)blockIdx.x * kMmaWarpsFwd + warp;
     if (item >= n_items) return;
     const int L = a.L, D = a.D, dk = a.dk;
     const long long seq = item / a.n_heads;
@@ -300,7 +314,7 @@ __global__ void __launch_bounds__(kMmaWarps * 32) attn_mma_fwd_kernel(const Attn
     float* Qh = smem + (size_t)warp * 3 * kMSlot;
     float* Kh = Qh + kMSlot;       // K, later the output staging
     float* Vh = Kh + kMSlot;
-    uint8_t* smask = reinterpret_cast<uint8_t*>(smem + (size_t)kMmaWarps * 3 * kMSlot) + warp * kTile * 8;
+    uint8_t* smask = reinterpret_cast<uint8_t*>(smem + (size_t)kMmaWarpsFwd * 3 * kMSlot) + warp * kTile * 8;
     const long long row0 = seq * L;
     const int ld = 3 * D, col = h * dk;
     const int g = lane >> 2, t = lane & 3;

@@ -3,7 +3,7 @@
 launch list of `scripts/prof_step.py` (one train step captured) into profiles/ncu_traffic.json:
 DRAM bytes and serialized device time per step for each library kernel label bench.py reports.
 
-    python scripts/ncu_traffic.py gpurun_out/step_metrics.csv profiles/ncu_traffic.json
+    python scripts/ncu_traffic.py gpurun_out/step_metrics.csv profiles/ncu_traffic.json [steps_in_capture]
 """
 import csv
 import json
@@ -26,7 +26,7 @@ def label(name):
     return None
 
 
-def main(src, dst):
+def main(src, dst, steps=1):
     rows = [r for r in csv.reader(open(src)) if r]
     hdr_i = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[hdr_i]
@@ -48,11 +48,15 @@ def main(src, dst):
             scale = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3}.get(unit, 1.0)
             rec["device_us_per_step"] += val * scale
             rec["launches_per_step"] += 1
-    json.dump({"source": src, "note": "one fused train step (cfg2), ncu per-launch metrics, cold-cache and serialised",
+    for rec in out.values():
+        rec["dram_bytes_per_step"] /= steps
+        rec["device_us_per_step"] /= steps
+        rec["launches_per_step"] /= steps
+    json.dump({"source": src, "steps_in_capture": steps, "note": "one fused train step (cfg2), ncu per-launch metrics, cold-cache and serialised",
                "kernels": out}, open(dst, "w"), indent=1, sort_keys=True)
     for k, v in sorted(out.items(), key=lambda kv: -kv[1]["device_us_per_step"]):
         print(f"{k:22s} {v['device_us_per_step']:9.1f} us  {v['dram_bytes_per_step'] / 1e6:9.1f} MB  x{v['launches_per_step']}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 1)
