@@ -152,10 +152,10 @@ __device__ __forceinline__ float quad_sum(float v) {
 constexpr int kMS = 36;                 // slot row stride (floats): 3 CTAs of 4 warps fit an SM in the backward
 constexpr int kMSlot = kTile * kMS;     // floats per slot
 constexpr int kMmaWarps = 4;            // backward: 4 slots per warp, 3 CTAs per SM
-constexpr int kMmaWarpsFwd = 4;         // forward (5 warps/CTA measured slower: less L1 left beside the slots)
+constexpr int kMmaWarpsFwd = 6;         // forward: 2 slots per warp (Q goes global -> registers), 3 CTAs per SM
 
 __host__ __device__ inline size_t attn_mma_fwd_smem_bytes() {
-    return (size_t)kMmaWarpsFwd * (3 * kMSlot * sizeof(float) + kTile * 8);
+    return (size_t)kMmaWarpsFwd * (2 * kMSlot * sizeof(float) + kTile * 8);
 }
 __host__ __device__ inline size_t attn_mma_bwd_smem_bytes() {
     return (size_t)kMmaWarps * 4 * kMSlot * sizeof(float);
@@ -216,6 +216,27 @@ __device__ __forceinline__ void mma_abt(float (&c)[2][4][4], const float* A, con
         uint32_t ahi[2][4], alo[2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) load_a_frag(ahi[mt], alo[mt], A, mt, ks, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            uint32_t bhi[2], blo[2];
+            load_b_frag_nk(bhi, blo, B, nt, ks, g, t);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma3<TERMS>(c[mt][nt], ahi[mt], alo[mt], bhi, blo);
+        }
+    }
+}
+// c[mt][nt] += A * B^T with A's fragments already in registers as raw fp32 pairs
+// (qa[ks][mt][0..3] = rows g / g+8, k 2t.. / 2t+8.. of the 16x16 block) and B a [n][k] slot:
+// S = Q K^T with Q read straight from global memory (no shared-memory slot for Q)
+template <int TERMS>
+__device__ __forceinline__ void mma_rawA_bt(float (&c)[2][4][4], const float2 (&qa)[2][2][4], const float* B, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_pair(qa[ks][mt][i].x, qa[ks][mt][i].y, ahi[mt][i], alo[mt][i]);
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             uint32_t bhi[2], blo[2];
@@ -311,17 +332,28 @@ __global__ void __launch_bounds__(kMmaWarpsFwd * 32) attn_mma_fwd_kernel(const A
     const int L = a.L, D = a.D, dk = a.dk;
     const long long seq = item / a.n_heads;
     const int h = (int)(item - seq * a.n_heads);
-    float* Qh = smem + (size_t)warp * 3 * kMSlot;
-    float* Kh = Qh + kMSlot;       // K, later the output staging
+    float* Kh = smem + (size_t)warp * 2 * kMSlot;   // K, later the output staging
     float* Vh = Kh + kMSlot;
-    uint8_t* smask = reinterpret_cast<uint8_t*>(smem + (size_t)kMmaWarpsFwd * 3 * kMSlot) + warp * kTile * 8;
+    uint8_t* smask = reinterpret_cast<uint8_t*>(smem + (size_t)kMmaWarpsFwd * 2 * kMSlot) + warp * kTile * 8;
     const long long row0 = seq * L;
     const int ld = 3 * D, col = h * dk;
     const int g = lane >> 2, t = lane & 3;
 
-    load_slot_async<kMS>(Qh, a.qkv, row0, ld, col, L, dk, lane);
     load_slot_async<kMS>(Kh, a.qkv, row0, ld, D + col, L, dk, lane);
     load_slot_async<kMS>(Vh, a.qkv, row0, ld, 2 * D + col, L, dk, lane);
+    // Q is only ever an A operand: its fragments come straight from global memory into registers
+    // (8 rows x 32 contiguous bytes per load instruction), one shared-memory slot less per warp
+    float2 qa[2][2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 16 * mt + 8 * (i & 1) + g, d = 16 * ks + 8 * (i >> 1) + 2 * t;
+                qa[ks][mt][i] = (r < L && d < dk) ? __ldg(reinterpret_cast<const float2*>(a.qkv + (row0 + r) * ld + col + d))
+                                                  : make_float2(0.f, 0.f);
+            }
     const int g0 = col >> 3;
     const bool drop = a.drop.enabled();
     if (drop) {
@@ -340,7 +372,7 @@ __global__ void __launch_bounds__(kMmaWarpsFwd * 32) attn_mma_fwd_kernel(const A
 
     float s[2][4][4];
     zero_frag(s);
-    mma_abt<TERMS>(s, Qh, Kh, g, t);
+    mma_rawA_bt<TERMS>(s, qa, Kh, g, t);
     // softmax over the keys: a row lives in the 4 lanes of a quad
     float inv[2][2];
 #pragma unroll
