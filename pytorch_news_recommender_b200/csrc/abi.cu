@@ -3,12 +3,15 @@
 // call only enqueues kernels on the caller's stream.
 #include "../../include/nrms_b200.h"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "attention.cuh"
 #include "attention_mma.cuh"
+#include "attention_hp.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gather.cuh"
@@ -92,8 +95,17 @@ constexpr int kWqkvRows = 1024, kWaRows = 256;
 
 inline int mask_bytes_for(int D) { return (int)align_up(ceil_div(D, 8), 4); }
 
+// Head-padded Q|K|V ("HP", gemm_img.cuh: hp_unpad; attention_hp.cuh): tensor-core GEMM modes,
+// sequences of at most 32 tokens, even head dim <= 32, 3*32*h <= 960 projection columns.
+inline bool use_hp(const nrms_encoder_dims& d) {
+    const int dk = d.d_model / d.n_heads;
+    return d.gemm_mode >= 1 && d.seq_len <= kTile && dk % 2 == 0 && dk <= 32 && 96 * d.n_heads <= 960 &&
+           getenv("NRMS_NO_HP") == nullptr;
+}
+inline int hp_cols(const nrms_encoder_dims& d) { return 96 * d.n_heads; }
+
 struct Saved {
-    float* qkv;      // [M, 3D]
+    float* qkv;      // [M, 3D] fp32; HP: bf16 planes hi [M, NP] then lo [M, NP]
     float* lse;      // [M, h]
     float* ctx;      // [M, D]   (post-dropout)
     float* t;        // [M, Q]
@@ -117,7 +129,7 @@ Saved saved_layout(void* blob, const nrms_encoder_dims& d) {
     };
     auto take = [&](int64_t nfloat) { return reinterpret_cast<float*>(take_bytes(nfloat * 4)); };
     Saved s{};
-    s.qkv = take(M * 3 * D);
+    s.qkv = use_hp(d) ? take((int64_t)d.n_seq * 32 * hp_cols(d)) : take(M * 3 * D);   // HP: 32-row blocks
     s.lse = take(M * d.n_heads);
     s.ctx = take(M * D);
     s.t = take(M * Q);
@@ -186,7 +198,8 @@ Scratch scratch_layout(void* blob, const nrms_encoder_dims& d) {
         s.d_pre_img = ig::img_view(take_bytes(ig::img_bytes(M, kPreChunks)), M, kPreChunks);
         s.d_qkv_img = ig::img_view(take_bytes(ig::img_bytes(M, kQkvChunks)), M, kQkvChunks);
         const int kch = ig::img_rows_pad(M) / 64;
-        const int64_t a = (int64_t)wgrad_splits_tc(ceil_div((int)(3 * D), 128), kch) * 3 * D * (D + 4);
+        const int64_t nq = use_hp(d) ? hp_cols(d) : 3 * D;   // output rows of dW_qkv (HP: padded order)
+        const int64_t a = (int64_t)wgrad_splits_tc(ceil_div((int)nq, 128), kch) * nq * (D + 4);
         const int64_t b = (int64_t)wgrad_splits_tc(ceil_div((int)Q, 128), kch) * Q * (D + 4);
         wpart = a > b ? a : b;
     } else {
@@ -314,6 +327,8 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     const int D = d.d_model, Q = d.d_query, L = d.seq_len, h = d.n_heads, dk = D / h;
     const int M = d.n_seq * L;
     const bool tcm = d.gemm_mode >= 1;
+    const bool hp = use_hp(d);
+    const int NP = hp_cols(d);
     const int terms = d.gemm_mode == 2 ? 1 : 3;   // mode 2: plain bf16 tensor-core products
     const ParamView pv = param_view<ParamView>(params, D, Q);
     const Dropout drop = make_dropout(d.dropout_p, d.seed);
@@ -336,7 +351,20 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         x_f32 = sv.x_f32;
     }
     // 2. Q|K|V projections (nrms_v0.py:53-58)
-    if (tcm) {
+    if (tcm && hp) {
+        // head-padded projection: weight image rows in padded order, output = split-bf16 planes
+        NRMS_CHECK_CUDA(ig::img_pack(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, s, D, dk));
+        NRMS_CHECK_CUDA(ig::img_pack(pv.Wa, Q, D, D, sv.wa_img, s));
+        ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, nullptr, NP, M, NP);
+        g.Chi = reinterpret_cast<uint16_t*>(sv.qkv);
+        g.Clo = g.Chi + (long long)d.n_seq * 32 * NP;
+        g.hp_D = D; g.hp_dk = dk; g.seq_len = L;
+        g.terms = terms;
+        g.bias = pv.bqkv;
+        g.m_tiles = sv.x_img.rows_pad / 128; g.n_tiles = ceil_div(NP, 256);
+        g.k_steps = ceil_div(D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+        NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT>(g, s, "gemm_fwd_qkv")));
+    } else if (tcm) {
         NRMS_CHECK_CUDA(ig::img_pack(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, s));
         NRMS_CHECK_CUDA(ig::img_pack(pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, sv.qkv, 3 * D, M, 3 * D);
@@ -359,7 +387,23 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
         a.scale = 1.f / sqrtf((float)dk);
         a.drop = news ? drop : make_dropout(0.f, 0);
-        if (L <= kTile && dk % 2 == 0) {
+        if (hp) {
+            // one independent warp per (sequence, head) over the head-padded planes (attention_hp.cuh)
+            a.qkv = nullptr;
+            a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
+            a.qkv_lo = a.qkv_hi + (long long)d.n_seq * 32 * NP;
+            a.np = NP;
+            const long long items = (long long)d.n_seq * h;
+            const size_t smem = attn_hp_fwd_smem_bytes();
+            const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpFwdWarps), getenv("NRMS_HP_FWD_GRID") ? atoi(getenv("NRMS_HP_FWD_GRID")) : 2 * kNumSMs);   // persistent warps
+            if (terms == 3) {
+                if ((rc = set_smem(attn_hp_fwd_kernel<3>, smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_hp_fwd_kernel<3><<<grid, kHpFwdWarps * 32, smem, s>>>(a, items)));
+            } else {
+                if ((rc = set_smem(attn_hp_fwd_kernel<1>, smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_hp_fwd_kernel<1><<<grid, kHpFwdWarps * 32, smem, s>>>(a, items)));
+            }
+        } else if (L <= kTile && dk % 2 == 0) {
             // one independent warp per (sequence, head), products on mma.sync (attention_mma.cuh)
             const long long items = (long long)d.n_seq * h;
             const size_t smem = attn_mma_fwd_smem_bytes();
@@ -439,6 +483,9 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     const int D = d.d_model, Q = d.d_query, L = d.seq_len, h = d.n_heads, dk = D / h;
     const int M = d.n_seq * L;
     const bool tcm = d.gemm_mode >= 1;
+    const bool hp = use_hp(d);
+    const int NP = hp_cols(d);
+    const int nq = hp ? NP : 3 * D;               // columns of the d_qkv image / rows of dW_qkv's partials
     const int terms = d.gemm_mode == 2 ? 1 : 3;
     const ParamView pv = param_view<ParamView>(params, D, Q);
     const GradView gv = param_view<GradView>(d_params, D, Q);
@@ -488,7 +535,22 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             a.M = M; a.L = L; a.D = D; a.n_heads = h; a.dk = dk;
             a.scale = 1.f / sqrtf((float)dk);
             a.drop = drop;
-            if (L <= kTile && dk % 2 == 0) {
+            if (hp) {
+                a.qkv = nullptr;
+                a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
+                a.qkv_lo = a.qkv_hi + (long long)d.n_seq * 32 * NP;
+                a.np = NP;
+                const long long items = (long long)d.n_seq * h;
+                const size_t smem = attn_hp_bwd_smem_bytes();
+                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpBwdWarps), getenv("NRMS_HP_BWD_GRID") ? atoi(getenv("NRMS_HP_BWD_GRID")) : 2 * kNumSMs);   // persistent warps
+                if (terms == 3) {
+                    if ((rc = set_smem(attn_hp_bwd_kernel<3>, smem))) return rc;
+                    NRMS_LAUNCH("attn_bwd", s, (attn_hp_bwd_kernel<3><<<grid, kHpBwdWarps * 32, smem, s>>>(a, items)));
+                } else {
+                    if ((rc = set_smem(attn_hp_bwd_kernel<1>, smem))) return rc;
+                    NRMS_LAUNCH("attn_bwd", s, (attn_hp_bwd_kernel<1><<<grid, kHpBwdWarps * 32, smem, s>>>(a, items)));
+                }
+            } else if (L <= kTile && dk % 2 == 0) {
                 const long long items = (long long)d.n_seq * h;
                 const size_t smem = attn_mma_bwd_smem_bytes();
                 const unsigned grid = (unsigned)ceil_div64(items, kMmaWarps);
@@ -519,7 +581,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 ig::IgArgs g = ig_args(sc.d_qkv_img, sv.wqkv_img, d_x, D, M, D);
                 g.terms = terms;
                 g.m_tiles = tok_tiles; g.n_tiles = 1;
-                g.k_steps = ceil_div(3 * D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+                g.k_steps = ceil_div(nq, 16); g.k_chunks = ceil_div(g.k_steps, 4);
                 if (drop.enabled()) {
                     g.mask_bits = reinterpret_cast<const uint32_t*>(sv.xmask);
                     g.mask_words = mb / 4;
@@ -560,7 +622,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             w.c_split_stride = (long long)Q * (D + 4);
             NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_additive")));
             NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)Q * (D + 1), 256), 256, 0, s>>>(
-                sc.wpart, w.splits, Q, D + 4, D, gv.Wa, gv.ba));
+                sc.wpart, w.splits, Q, D + 4, D, gv.Wa, gv.ba, 0, 0));
             NRMS_CHECK_CUDA(cudaGetLastError());
         } else {
             const int splits = wgrad_splits_simt(Q, D, M);
@@ -581,15 +643,16 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         // 5. dW_qkv = d_qkv^T x
         if (tcm) {
             // columns [0,D) = dW_qkv, column D = d_b_qkv (ones column of the input image)
-            ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D + 4, 3 * D, D + 4);
+            // (HP: partial rows in head-padded order, mapped back by the reduction)
+            ig::IgArgs w = ig_args(sc.d_qkv_img, sv.x_img, sc.wpart, D + 4, nq, D + 4);
             w.terms = terms;
-            w.m_tiles = ceil_div(3 * D, 128); w.n_tiles = 1;
+            w.m_tiles = ceil_div(nq, 128); w.n_tiles = 1;
             w.k_chunks = tok_tiles * 2; w.k_steps = 4 * w.k_chunks;
             w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
-            w.c_split_stride = 3ll * D * (D + 4);
+            w.c_split_stride = (long long)nq * (D + 4);
             NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_qkv")));
-            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for(3ll * D * (D + 1), 256), 256, 0, s>>>(
-                sc.wpart, w.splits, 3 * D, D + 4, D, gv.Wqkv, gv.bqkv));
+            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)nq * (D + 1), 256), 256, 0, s>>>(
+                sc.wpart, w.splits, nq, D + 4, D, gv.Wqkv, gv.bqkv, hp ? D : 0, hp ? dk : 0));
             NRMS_CHECK_CUDA(cudaGetLastError());
         } else {
             const int splits = wgrad_splits_simt(3 * D, D, M);

@@ -98,32 +98,50 @@ __device__ __forceinline__ void img_store8_zero(const Img& im, long long r, int 
     *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(0u, 0u, 0u, 0u);
 }
 
+// ---- head-padded ("HP") row order of the Q|K|V projection ---------------------------------------
+// The short-sequence attention kernels (attention_hp.cuh) want every head's d_k columns to start
+// on a 64-byte boundary of a bf16 row, so the projection is computed with every head padded to 32
+// output columns: padded row/column rp = which*32h + head*32 + d  (which = Q/K/V, d < d_k real,
+// d in [d_k,32) zero weight rows and zero bias).  hp_unpad maps rp back to the row of the
+// reference's [3D, D] weight block (nrms_v0.py:36-38), or -1 for a padding row.
+__host__ __device__ __forceinline__ int hp_unpad(int rp, int D, int dk) {
+    const int DP = (D / dk) * 32;
+    const int which = rp / DP, rem = rp - which * DP;
+    const int head = rem >> 5, d = rem & 31;
+    if (which >= 3 || d >= dk) return -1;
+    return which * D + head * dk + d;
+}
+
 // ---- fp32 row-major matrix -> image (weights; zero padded) -------------------------------------
-__global__ void img_pack_kernel(const float* __restrict__ src, int R, int C, int ld, Img im) {
+// hp_dk > 0: image row r holds source row hp_unpad(r, hp_D, hp_dk) (zeros for padding rows)
+__global__ void img_pack_kernel(const float* __restrict__ src, int R, int C, int ld, Img im, int hp_D, int hp_dk) {
     const int groups = im.chunks * 8;
     const long long total = (long long)im.rows_pad * groups;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int g = (int)(i % groups);
         const long long r = i / groups;
+        const long long sr = hp_dk > 0 ? hp_unpad((int)r, hp_D, hp_dk) : (r < R ? r : -1);
         float x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = g * 8 + j;
-            x[j] = (r < R && c < C) ? __ldg(src + r * ld + c) : 0.f;
+            x[j] = (sr >= 0 && c < C) ? __ldg(src + sr * ld + c) : 0.f;
         }
         img_store8(im, r, g, x);
     }
 }
-inline cudaError_t img_pack(const float* src, int R, int C, int ld, const Img& im, cudaStream_t s) {
+inline cudaError_t img_pack(const float* src, int R, int C, int ld, const Img& im, cudaStream_t s, int hp_D = 0,
+                            int hp_dk = 0) {
     const long long total = (long long)im.rows_pad * im.chunks * 8;
     NRMS_LAUNCH("img_pack", s,
-                img_pack_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(src, R, C, ld, im));
+                img_pack_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(src, R, C, ld, im, hp_D, hp_dk));
     return cudaGetLastError();
 }
 
 // ---- the GEMM ----------------------------------------------------------------------------------
-enum Epi { EPI_BIAS = 0, EPI_TANH_DOT = 1, EPI_ACCUM = 2, EPI_MASK = 3, EPI_PARTIAL = 4, EPI_POOLADD = 5 };
+enum Epi { EPI_BIAS = 0, EPI_TANH_DOT = 1, EPI_ACCUM = 2, EPI_MASK = 3, EPI_PARTIAL = 4, EPI_POOLADD = 5,
+           EPI_BIAS_SPLIT = 6 };   // bias (head-padded order) + split-bf16 row-major planes out
 
 struct IgArgs {
     Img A, B;
@@ -139,6 +157,10 @@ struct IgArgs {
     const float* row_w;         // EPI_POOLADD: [M] pooling weight of each token row
     const float* seq_vec;       // EPI_POOLADD: [M / seq_len, N] upstream gradient of each sequence
     int seq_len;                // EPI_POOLADD: C[m,n] = acc + row_w[m] * seq_vec[m / seq_len, n]
+    uint16_t* Chi;              // EPI_BIAS_SPLIT: head-blocked bf16 planes (hi = bf16(x), lo = bf16(x - hi)),
+                                //   [M / seq_len][3][heads] blocks of 32 rows x 32 columns (attention_hp.cuh)
+    uint16_t* Clo;
+    int hp_D, hp_dk;            // EPI_BIAS_SPLIT: bias index of output column n = hp_unpad(n, hp_D, hp_dk)
     int M, N;                   // valid output rows / columns
     int m_tiles, n_tiles;       // work grid (tiles of 128 rows x N_T columns)
     int k_chunks;               // 64-deep k chunks in total
@@ -328,7 +350,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
         // =============================== epilogue (warps 2..5) =================================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int et = (warp - 2) * 32 + lane;        // 0..127 within the epilogue group
-        static_assert(!(EPI == EPI_BIAS || EPI == EPI_TANH_DOT) || N_T <= 256, "epilogue staging holds 256 columns");
+        static_assert(!(EPI == EPI_BIAS || EPI == EPI_TANH_DOT || EPI == EPI_BIAS_SPLIT) || N_T <= 256,
+                      "epilogue staging holds 256 columns");
         float* s_bias = s_epi;                        // [256]
         float* s_qv = s_epi + 256;                    // [256] (EPI_TANH_DOT)
         uint32_t tile_it = 0;
@@ -338,10 +361,15 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
             const int n0 = n_tile * N_T;
             const int buf = DOUBLE_ACC ? (int)(tile_it & 1u) : 0;
             const uint32_t use = DOUBLE_ACC ? (tile_it >> 1) : tile_it;
-            if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT) {
+            if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT || EPI == EPI_BIAS_SPLIT) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
                 for (int i = et; i < N_T; i += 128) {
                     const int n = n0 + i;
+                    if (EPI == EPI_BIAS_SPLIT) {
+                        const int ns = n < a.N ? hp_unpad(n, a.hp_D, a.hp_dk) : -1;
+                        s_bias[i] = ns >= 0 ? __ldg(a.bias + ns) : 0.f;
+                        continue;
+                    }
                     s_bias[i] = n < a.N ? __ldg(a.bias + n) : 0.f;
                     if (EPI == EPI_TANH_DOT) s_qv[i] = n < a.N ? __ldg(a.qv + n) : 0.f;
                 }
@@ -373,6 +401,33 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
             for (int cb = 0; cb < N_T; cb += 32) {
                 float v[32];
                 tc::tmem_ld32(t_row + (uint32_t)cb, v);
+                if (EPI == EPI_BIAS_SPLIT) {
+                    // TMEM gives a lane one output row; 32 columns = one head of the head-padded order, i.e.
+                    // one contiguous 64-byte row of a head block per plane: the warp writes 32 consecutive
+                    // rows = 2 KB contiguous per plane, straight from registers
+                    const int jb = (n0 + cb) >> 5, nh = a.hp_D / a.hp_dk;
+                    if (n0 + cb < a.N && row_ok) {
+                        const int which = jb / nh, head = jb - which * nh;
+                        const long long sq = m / a.seq_len;
+                        const int l = m - (int)sq * a.seq_len;
+                        const long long off = (((sq * 3 + which) * nh + head) * 32 + l) * 32;
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            tc::split_bf16(v[2 * j] + s_bias[cb + 2 * j], h0, l0);
+                            tc::split_bf16(v[2 * j + 1] + s_bias[cb + 2 * j + 1], h1, l1);
+                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            *reinterpret_cast<uint4*>(a.Chi + off + 8 * j) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            *reinterpret_cast<uint4*>(a.Clo + off + 8 * j) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        }
+                    }
+                    continue;
+                }
                 float4 old[8];
                 if (EPI == EPI_ACCUM || EPI == EPI_POOLADD) {
                     // batched, independent loads (issued together, consumed below)

@@ -197,12 +197,15 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
 // Sum of split-K weight-gradient partials whose column `cols` carries the bias gradient (the
 // activation image has a ones column, gather.cuh): part [splits][rows][ldp] ->
 // dW[r, c] (c < cols, contiguous [rows, cols]) and db[r].  Fixed summation order over the splits.
+// hp_dk > 0: partial row r is row ig::hp_unpad(r, hp_D, hp_dk) of dW / db (padding rows skipped).
 __global__ void reduce_wgrad_kernel(const float* __restrict__ part, int splits, int rows, int ldp, int cols,
-                                    float* __restrict__ dW, float* __restrict__ db) {
+                                    float* __restrict__ dW, float* __restrict__ db, int hp_D, int hp_dk) {
     const long long per = (long long)rows * ldp;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * (cols + 1);
          i += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(i / (cols + 1)), c = (int)(i - (long long)r * (cols + 1));
+        const int ro = hp_dk > 0 ? ig::hp_unpad(r, hp_D, hp_dk) : r;
+        if (ro < 0) continue;
         const float* p = part + (long long)r * ldp + c;
         float s0 = 0.f, s1 = 0.f;
         int s = 0;
@@ -212,8 +215,8 @@ __global__ void reduce_wgrad_kernel(const float* __restrict__ part, int splits, 
         }
         if (s < splits) s0 += p[s * per];
         const float v = s0 + s1;
-        if (c < cols) dW[(long long)r * cols + c] = v;
-        else db[r] = v;
+        if (c < cols) dW[(long long)ro * cols + c] = v;
+        else db[ro] = v;
     }
 }
 
