@@ -273,13 +273,14 @@ struct AttnCfg {
     int hpb, threads, unit;
     size_t smem;
 };
-AttnCfg attn_fwd_cfg(int L, int n_heads) {
+AttnCfg attn_fwd_cfg(int L, int n_heads, int n_seq) {
     AttnCfg c;
     c.unit = L <= 32 ? 16 : 32;                       // lanes per (head, row-block) task; 2 rows per lane
     const int rb = ceil_div(L, 2 * c.unit);
     const size_t budget = 110 * 1024;                 // 2 CTAs per SM (registers allow no more)
     int hpb = n_heads;
     while (hpb > 1 && (attn_fwd_smem_bytes(L, hpb) > budget || hpb * rb * c.unit > 256)) --hpb;
+    (void)n_seq;   // (splitting the head groups further for few sequences measured slower)
     hpb = ceil_div(n_heads, ceil_div(n_heads, hpb));  // balance the head groups
     c.hpb = hpb;
     int threads = hpb * rb * c.unit;
@@ -288,13 +289,14 @@ AttnCfg attn_fwd_cfg(int L, int n_heads) {
     c.smem = attn_fwd_smem_bytes(L, hpb);
     return c;
 }
-AttnCfg attn_bwd_cfg(int L, int n_heads) {
+AttnCfg attn_bwd_cfg(int L, int n_heads, int n_seq) {
     AttnCfg c;
     c.unit = 32;
     const int rc = ceil_div(L, 32);
     const size_t budget = 110 * 1024;                 // 2 CTAs per SM
     int hpb = n_heads;
     while (hpb > 1 && (hpb * rc > 8 || attn_bwd_smem_bytes(L, hpb) > budget)) --hpb;
+    (void)n_seq;
     hpb = ceil_div(n_heads, ceil_div(n_heads, hpb));  // balance the head groups
     c.hpb = hpb;
     c.threads = hpb * rc * 32;
@@ -416,7 +418,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 NRMS_LAUNCH("attn_fwd", s, (attn_mma_fwd_kernel<1><<<grid, kMmaWarpsFwd * 32, smem, s>>>(a, items)));
             }
         } else {
-            const AttnCfg c = attn_fwd_cfg(L, h);
+            const AttnCfg c = attn_fwd_cfg(L, h, d.n_seq);
             a.hpb = c.hpb;
             const bool vec2 = (dk % 2 == 0);
             const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
@@ -517,6 +519,11 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             g.m_tiles = tok_tiles; g.n_tiles = 1;
             g.k_steps = ceil_div(Q, 16); g.k_chunks = ceil_div(g.k_steps, 4);
             g.row_w = sv.w; g.seq_vec = d_out; g.seq_len = L;
+            if (tok_tiles * 2 <= kNumSMs) {
+                // few token tiles (the user encoder): 64-column tiles so that the grid fills the SMs
+                g.n_tiles = ceil_div(D, 64);
+                NRMS_CHECK_CUDA((ig::ig_launch<false, true, 64, ig::EPI_POOLADD>(g, s, "gemm_dgrad_additive")));
+            } else
             NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_POOLADD>(g, s, "gemm_dgrad_additive")));
         } else {
             GemmArgs g{};
@@ -562,7 +569,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     NRMS_LAUNCH("attn_bwd", s, (attn_mma_bwd_kernel<1><<<grid, kMmaWarps * 32, smem, s>>>(a, items)));
                 }
             } else {
-                const AttnCfg c = attn_bwd_cfg(L, h);
+                const AttnCfg c = attn_bwd_cfg(L, h, d.n_seq);
                 a.hpb = c.hpb;
                 const dim3 grid(d.n_seq, ceil_div(h, c.hpb));
                 if (dk % 2 == 0) {
@@ -587,6 +594,10 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     g.mask_words = mb / 4;
                     g.mask_scale = drop.scale;
                 }
+                if (tok_tiles * 2 <= kNumSMs) {
+                    g.n_tiles = ceil_div(D, 64);
+                    NRMS_CHECK_CUDA((ig::ig_launch<false, true, 64, ig::EPI_MASK>(g, s, "gemm_dgrad_qkv")));
+                } else
                 NRMS_CHECK_CUDA((ig::ig_launch<false, true, 320, ig::EPI_MASK>(g, s, "gemm_dgrad_qkv")));
             }
         } else {

@@ -121,6 +121,23 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
     // d_pre = da_l * q_j * (1 - t^2), coalesced 2-column units (fp32 and/or image)
     const bool img = p.d_pre_img.hi != nullptr;
     {
+        if (img && !p.d_pre && Q % 8 == 0) {
+            // image only (the tcgen05 path): a thread owns one 16-byte unit (8 columns) of a row
+            const int q8 = Q >> 3;
+            for (int i = threadIdx.x; i < L * q8; i += blockDim.x) {
+                const int l = i / q8, u = i - l * q8, j = u << 3;
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.t + (row0 + l) * Q + j));
+                const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.t + (row0 + l) * Q + j + 4));
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.q + j));
+                const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.q + j + 4));
+                const float da = sda[l];
+                const float x[8] = {da * q0.x * (1.f - t0.x * t0.x), da * q0.y * (1.f - t0.y * t0.y),
+                                    da * q0.z * (1.f - t0.z * t0.z), da * q0.w * (1.f - t0.w * t0.w),
+                                    da * q1.x * (1.f - t1.x * t1.x), da * q1.y * (1.f - t1.y * t1.y),
+                                    da * q1.z * (1.f - t1.z * t1.z), da * q1.w * (1.f - t1.w * t1.w)};
+                ig::img_store8(p.d_pre_img, row0 + l, u, x);
+            }
+        } else {
         const int q2 = Q >> 1;
         for (int i = threadIdx.x; i < L * q2; i += blockDim.x) {
             const int l = i / q2, j = (i - l * q2) << 1;
@@ -139,6 +156,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
                 *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) =
                     (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
             }
+        }
         }
         if (img) {
             // zero padding: columns [Q, 16*ceil(Q/16)) feed the data-gradient GEMM's last k-step,
