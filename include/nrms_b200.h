@@ -172,6 +172,14 @@ int nrms_rank_metrics_padded(const float* scores, int64_t row_stride, const uint
                              const int64_t* offsets, int64_t n_impr, int32_t max_len,
                              double* out, nrms_stream_t stream);
 
+/* Rank lists of the submission writer (train_eval.py:279-285 `_cal_test`, written to
+ * sumbit_*.txt by train_eval.py:335-339): ranks[i, j] = 1 + position of candidate j in
+ * argsort(-scores[i, :lens[i]]) for j < lens[i] (ties: lower index first), 0 for j >= lens[i].
+ * scores / ranks are padded rows of row_stride elements; lens int64 [n_impr], clipped to
+ * [0, row_stride]. */
+int nrms_rank_positions(const float* scores, int64_t row_stride, const int64_t* lens,
+                        int64_t n_impr, int32_t* ranks, nrms_stream_t stream);
+
 /* Gather rows: out[i,:] = src[idx[i]-base,:] (idx < base -> zeros).  Used to build
  * [B,H,D]/[B,C,D] from the cached news-vector table keyed by browsed_ids/candidate_ids
  * (news row + 1, 0 = pad: data_handler.py:88,100) and, with int64 title tables, for the

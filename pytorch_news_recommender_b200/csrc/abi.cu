@@ -926,6 +926,22 @@ int nrms_rank_metrics_padded(const float* scores, int64_t row_stride, const uint
                         (cudaStream_t)stream);
 }
 
+int nrms_rank_positions(const float* scores, int64_t row_stride, const int64_t* lens,
+                        int64_t n_impr, int32_t* ranks, nrms_stream_t stream) {
+    if (n_impr < 1 || row_stride < 1 || row_stride > 4096)
+        return fail(NRMS_ERR_BAD_SHAPE, "n_impr=%lld row_stride=%lld", (long long)n_impr, (long long)row_stride);
+    NRMS_REQUIRE_PTR(scores); NRMS_REQUIRE_PTR(lens); NRMS_REQUIRE_PTR(ranks);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)kMetricWarps * row_stride * sizeof(float);
+    int rc = set_smem(rank_positions_kernel, smem);
+    if (rc) return rc;
+    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(n_impr, kMetricWarps), 8ll * kNumSMs);
+    NRMS_LAUNCH("rank_positions", s, rank_positions_kernel<<<grid, kMetricWarps * 32, smem, s>>>(
+        scores, row_stride, lens, n_impr, (int)row_stride, ranks));
+    NRMS_CHECK_CUDA(cudaGetLastError());
+    return NRMS_OK;
+}
+
 int nrms_gather_rows_f32(const float* src, int64_t n_src, int32_t D, const int64_t* idx,
                          int64_t n_idx, int64_t base, float* out, nrms_stream_t stream) {
     if (n_src < 1 || D < 1 || n_idx < 1) return fail(NRMS_ERR_BAD_SHAPE, "bad gather shape");

@@ -85,4 +85,39 @@ __global__ void __launch_bounds__(kMetricWarps * 32) rank_metrics_kernel(
     }
 }
 
+// Rank list of the submission writer (train_eval.py:279-285, `_cal_test`): for impression i with
+// n = lens[i] real candidates, ranks[i, j] = 1 + position of candidate j in argsort(-score[:n]).
+// Ties keep the lower index first (a stable sort; numpy's default sort leaves tie order
+// unspecified).  Slots j >= n get rank 0.  One warp per impression, O(n^2) compares.
+__global__ void __launch_bounds__(kMetricWarps * 32) rank_positions_kernel(
+    const float* __restrict__ scores, long long row_stride, const int64_t* __restrict__ lens,
+    long long n_impr, int max_n, int32_t* __restrict__ ranks) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* s = reinterpret_cast<float*>(smraw) + (size_t)warp * max_n;
+    for (long long imp = (long long)blockIdx.x * kMetricWarps + warp; imp < n_impr;
+         imp += (long long)gridDim.x * kMetricWarps) {
+        long long n64 = lens[imp];
+        const int n = (int)(n64 < 0 ? 0 : (n64 > max_n ? max_n : n64));
+        const float* row = scores + imp * row_stride;
+        int32_t* out = ranks + imp * row_stride;
+        for (int j = lane; j < n; j += 32) s[j] = row[j];
+        __syncwarp();
+        for (int j = lane; j < (int)row_stride; j += 32) {
+            int r = 0;
+            if (j < n) {
+                const float sj = s[j];
+                int before = 0;
+                for (int k = 0; k < n; ++k) {
+                    const float sk = s[k];
+                    before += (sk > sj) || (sk == sj && k < j);
+                }
+                r = before + 1;
+            }
+            out[j] = r;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace nrms

@@ -214,6 +214,18 @@ def rank_metrics(scores, labels, offsets, max_len: int, row_stride: Optional[int
     return out
 
 
+def rank_positions(scores, lens):
+    """Padded scores float32 [N, S], lens int64 [N] -> int32 [N, S]: 1-based rank of every real
+    candidate inside its impression (train_eval.py:279-285), 0 in the padded slots."""
+    _require_cuda(scores, lens)
+    scores = _cf32(scores)
+    n, S = scores.shape
+    out = torch.empty((n, S), dtype=torch.int32, device=scores.device)
+    check(_lib.load().nrms_rank_positions(ptr(scores), S, ptr(lens.contiguous()), n, ptr(out), _stream()),
+          "nrms_rank_positions")
+    return out
+
+
 def gather_rows(src, idx, base: int = 0):
     """out[i] = src[idx[i] - base] (zeros when idx[i] < base).  src float32 or int64 [n, D]."""
     _require_cuda(src, idx)

@@ -118,3 +118,66 @@ def make_eval_impressions(pool: NewsPool, n_impr: int, history_len: int,
         "n_candidates": torch.from_numpy(n_c),
         "y_true": y_true,
     }
+
+
+def make_sample_lists(pool: NewsPool, n_samples: int, history_len: int, n_candidates_lo: int,
+                      n_candidates_hi: int, seed: int = 0, min_hist: int = 5, n_categ: int = 18,
+                      n_subcateg: int = 270) -> List[list]:
+    """Sample lists in the `idx_*.pkl` layout (data_handler.py:100-103):
+    [history_idx, categ_idx, subcateg_idx, imp_idx, imp_categ_idx, imp_subcateg_idx], news ids =
+    table row + 1.  Candidate counts are uniform in [n_candidates_lo, n_candidates_hi]."""
+    rng = np.random.default_rng(seed + 4)
+    out = []
+    for _ in range(n_samples):
+        x = int(rng.integers(min(min_hist, history_len), history_len + 1))
+        y = int(rng.integers(n_candidates_lo, n_candidates_hi + 1))
+        hist = rng.integers(1, pool.n_news + 1, size=x).tolist()
+        imp = rng.integers(1, pool.n_news + 1, size=y).tolist()
+        out.append([hist, rng.integers(1, n_categ, size=x).tolist(), rng.integers(1, n_subcateg, size=x).tolist(),
+                    imp, rng.integers(1, n_categ, size=y).tolist(), rng.integers(1, n_subcateg, size=y).tolist()])
+    return out
+
+
+def write_demo_files(path: str, config, n_news: int = 500, vocab: int = 2000, n_train: int = 256,
+                     n_dev: int = 64, seed: int = 0, n_words_abst: Optional[int] = None) -> Dict[str, object]:
+    """Writes every file `run_demo.py` resolves under `path` (run_demo.py:30-45,
+    train_eval.py:157-159), with the literal names the reference uses:
+    demo_word_embedding.npz, demo_news_title.pkl, demo_news_abst.pkl, idx_small_train.pkl,
+    idx_small_dev.pkl, small_dev_behaviors.csv.  Returns the in-memory objects."""
+    import os
+    import pickle
+
+    os.makedirs(path, exist_ok=True)
+    rng = np.random.default_rng(seed + 5)
+    table = make_embedding_table(vocab, config.word_embed_size, seed=seed)
+    save_embedding_npz(os.path.join(path, 'demo_word_embedding.npz'), table)
+    pool = make_news_pool(n_news, config.n_words_title, vocab, seed=seed)
+    A = n_words_abst if n_words_abst is not None else getattr(config, 'n_words_abst', 40)
+    absts = make_news_pool(n_news, A, vocab, seed=seed + 100).titles
+    title_dict = {i: pool.titles[i].tolist() for i in range(n_news)}
+    abst_dict = {i: absts[i].tolist() for i in range(n_news)}
+    with open(os.path.join(path, 'demo_news_title.pkl'), 'wb') as f:
+        pickle.dump(title_dict, f)
+    with open(os.path.join(path, 'demo_news_abst.pkl'), 'wb') as f:
+        pickle.dump(abst_dict, f)
+    S = config.sample_size + 1
+    train = make_sample_lists(pool, n_train, config.history_len, max(1, S - 2), S, seed=seed)   # <= S: see pack_samples
+    dev = make_sample_lists(pool, n_dev, config.history_len, 2, min(40, config.max_candidate_size), seed=seed + 1,
+                            min_hist=1)
+    with open(os.path.join(path, 'idx_small_train.pkl'), 'wb') as f:
+        pickle.dump(train, f)
+    with open(os.path.join(path, 'idx_small_dev.pkl'), 'wb') as f:
+        pickle.dump(dev, f)
+    y_true = []
+    for d in dev:
+        n = len(d[3])
+        lab = (rng.random(n) < 0.2).astype(np.int64)
+        lab[int(rng.integers(0, n))] = 1
+        lab[(int(np.argmax(lab)) + 1) % n] = 0
+        y_true.append(lab.tolist())
+    with open(os.path.join(path, 'small_dev_behaviors.csv'), 'w') as f:
+        f.write('impression_id,y_true\n')
+        for i, lab in enumerate(y_true):
+            f.write('%d,%s\n' % (i, ' '.join(str(v) for v in lab)))
+    return {'table': table, 'pool': pool, 'title_dict': title_dict, 'abst_dict': abst_dict,
+            'train': train, 'dev': dev, 'y_true': y_true}

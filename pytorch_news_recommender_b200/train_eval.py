@@ -105,3 +105,74 @@ def evaluate(config, model, data_iter, AUC_best, y_true: Optional[Sequence[Seque
                         n_impressions=int(m.shape[0]))
     log('AUC:', AUC)
     return AUC
+
+
+# ---- checkpoints and the test-set ranking writer (train_eval.py:139-142, 279-341) -------------
+def checkpoint_name(config, total_batch, auc) -> str:
+    """The reference's checkpoint file name (train_eval.py:142)."""
+    return 'T{}_{}_epoch{}_iter_{}_auc_{:.3f}.ckpt'.format(time.strftime('%m-%d_%H.%M'), config.model_name,
+                                                           config.num_epochs, total_batch, auc)
+
+
+def save_checkpoint(config, model, total_batch, auc) -> str:
+    """`torch.save(model.state_dict(), config.save_path + name)`: the state_dict keys and shapes are
+    the reference's, so either implementation loads the other's files."""
+    import os
+    os.makedirs(config.save_path, exist_ok=True)
+    path = config.save_path + checkpoint_name(config, total_batch, auc)
+    torch.save(model.state_dict(), path)
+    return path
+
+
+def best_checkpoint(config) -> Optional[str]:
+    """train_eval.py:296-303: the checkpoint of `config.model_name` with the highest AUC in its
+    file name (only files above 0.5 qualify, as there)."""
+    import os
+    auc_best, ckpt_file = 0.5, None
+    for ckpt in sorted(os.listdir(config.save_path)):
+        if config.model_name in ckpt and ckpt.endswith('.ckpt'):
+            try:
+                tmp_auc = float(ckpt[:-len('.ckpt')].split('_')[-1])
+            except ValueError:
+                continue
+            if tmp_auc > auc_best:
+                auc_best, ckpt_file = tmp_auc, ckpt
+    return ckpt_file
+
+
+def test(config, model, data_iter, ckpt_file=None, test_list_nums: Optional[Sequence[int]] = None,
+         out_dir: str = '.', log=print) -> str:
+    """train_eval.py:294-341: load a checkpoint, score the test impressions, write
+    `sumbit_<model>_<time>.txt` with one line per impression: `<1-based index> [r1,r2,...]` where
+    r_j is the rank of candidate j among the impression's `test_list_nums[i]` real candidates.
+    The rank lists are computed on the GPU (`nrms_rank_positions`); only they cross to the host."""
+    import os
+    from . import ops
+    if ckpt_file is None:
+        ckpt_file = best_checkpoint(config)
+    if ckpt_file is not None:
+        path = ckpt_file if os.path.isabs(ckpt_file) or os.path.exists(ckpt_file) else config.save_path + ckpt_file
+        model.load_state_dict(torch.load(path, map_location='cpu'))
+        log('load the ckpt_file:{}'.format(ckpt_file))
+    if test_list_nums is None:
+        import pickle
+        with open(config.data_path + 'test_imps_list.pkl', 'rb') as f:
+            test_list_nums = pickle.load(f)
+    model.eval()
+    scores = []
+    with torch.no_grad():
+        for datas in data_iter:
+            scores.append(model(datas))
+    rank_score = torch.cat(scores, 0)
+    lens = torch.as_tensor(list(test_list_nums), dtype=torch.int64, device=rank_score.device)
+    if lens.numel() != rank_score.shape[0]:
+        raise ValueError(f"{lens.numel()} impression lengths for {rank_score.shape[0]} score rows")
+    ranks = ops.rank_positions(rank_score, lens).cpu().numpy()
+    file_name = os.path.join(out_dir, 'sumbit_{}_{}.txt'.format(config.model_name,
+                                                                time.strftime('%m-%d_%H.%M', time.localtime())))
+    with open(file_name, 'w') as f:
+        for i, n in enumerate(test_list_nums):
+            f.write(str(i + 1) + ' ')
+            f.write(str(ranks[i, :n].tolist()).replace(' ', '') + '\n')
+    log('saved to {}'.format(file_name))
+    return file_name
