@@ -172,6 +172,21 @@ int nrms_rank_metrics_padded(const float* scores, int64_t row_stride, const uint
                              const int64_t* offsets, int64_t n_impr, int32_t max_len,
                              double* out, nrms_stream_t stream);
 
+/* Batch assembly on the device: MyDataset.__getitem__ + default_collate of data_handler.py:185-250
+ * for the keys the NRMS path reads, in ONE launch.  Inputs are the sample matrices packed once on
+ * the host (front-aligned, zero padded: browsed_ids [N,H], candidate_ids [N,S], their lengths) and
+ * the title table [n_news, T] (news id = row + 1; id 0 -> all-zero title), all int64 in HBM;
+ * index [B] picks the samples.  Outputs: browsed_ids [B,H], browsed_lens [B], browsed_titles
+ * [B,H,T], browsed_mask [B,H] u8, candidate_ids [B,S], candidate_titles [B,S,T], candidate_mask
+ * [B,S] u8. */
+int nrms_assemble_batch(const int64_t* index, int32_t B, const int64_t* browsed_ids,
+                        const int64_t* browsed_lens, const int64_t* candidate_ids,
+                        const int64_t* candidate_lens, const int64_t* titles, int64_t n_news,
+                        int32_t H, int32_t S, int32_t T, int64_t* o_browsed_ids,
+                        int64_t* o_browsed_lens, int64_t* o_browsed_titles, uint8_t* o_browsed_mask,
+                        int64_t* o_candidate_ids, int64_t* o_candidate_titles,
+                        uint8_t* o_candidate_mask, nrms_stream_t stream);
+
 /* Rank lists of the submission writer (train_eval.py:279-285 `_cal_test`, written to
  * sumbit_*.txt by train_eval.py:335-339): ranks[i, j] = 1 + position of candidate j in
  * argsort(-scores[i, :lens[i]]) for j < lens[i] (ties: lower index first), 0 for j >= lens[i].

@@ -65,6 +65,7 @@ SIGNATURES = {
     "nrms_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _F, _P]),
     "nrms_rank_metrics": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     "nrms_rank_metrics_padded": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _P, _P]),
+    "nrms_assemble_batch": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nrms_rank_positions": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     "nrms_gather_rows_f32": (C.c_int, [_P, _I64, _I32, _P, _I64, _I64, _P, _P]),
     "nrms_gather_rows_i64": (C.c_int, [_P, _I64, _I32, _P, _I64, _I64, _P, _P]),

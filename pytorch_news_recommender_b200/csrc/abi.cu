@@ -926,6 +926,29 @@ int nrms_rank_metrics_padded(const float* scores, int64_t row_stride, const uint
                         (cudaStream_t)stream);
 }
 
+int nrms_assemble_batch(const int64_t* index, int32_t B, const int64_t* browsed_ids,
+                        const int64_t* browsed_lens, const int64_t* candidate_ids,
+                        const int64_t* candidate_lens, const int64_t* titles, int64_t n_news,
+                        int32_t H, int32_t S, int32_t T, int64_t* o_browsed_ids,
+                        int64_t* o_browsed_lens, int64_t* o_browsed_titles, uint8_t* o_browsed_mask,
+                        int64_t* o_candidate_ids, int64_t* o_candidate_titles,
+                        uint8_t* o_candidate_mask, nrms_stream_t stream) {
+    if (B < 1 || H < 1 || S < 1 || T < 1 || n_news < 1)
+        return fail(NRMS_ERR_BAD_SHAPE, "B=%d H=%d S=%d T=%d n_news=%lld", B, H, S, T, (long long)n_news);
+    // 8-byte elements, scalar accesses: no 16-byte alignment requirement (index is usually a slice)
+    if (!index || !browsed_ids || !browsed_lens || !candidate_ids || !candidate_lens || !titles || !o_browsed_ids ||
+        !o_browsed_lens || !o_browsed_titles || !o_browsed_mask || !o_candidate_ids || !o_candidate_titles ||
+        !o_candidate_mask)
+        return fail(NRMS_ERR_NULL, "NULL argument");
+    AssembleArgs a{index, browsed_ids, browsed_lens, candidate_ids, candidate_lens, titles, n_news, B, H, S, T,
+                   o_browsed_ids, o_browsed_lens, o_browsed_titles, o_browsed_mask, o_candidate_ids,
+                   o_candidate_titles, o_candidate_mask};
+    cudaStream_t s = (cudaStream_t)stream;
+    NRMS_LAUNCH("assemble_batch", s, assemble_batch_kernel<<<grid_for((long long)B * (H + S) * 32, 256, 16), 256, 0, s>>>(a));
+    NRMS_CHECK_CUDA(cudaGetLastError());
+    return NRMS_OK;
+}
+
 int nrms_rank_positions(const float* scores, int64_t row_stride, const int64_t* lens,
                         int64_t n_impr, int32_t* ranks, nrms_stream_t stream) {
     if (n_impr < 1 || row_stride < 1 || row_stride > 4096)

@@ -394,4 +394,49 @@ __global__ void validate_ids_kernel(const int64_t* ids, long long n, long long v
         if (ids[i] < 0 || ids[i] >= vocab) atomicOr(flag, 1);
 }
 
+// ---- batch assembly (MyDataset.__getitem__ + default_collate, data_handler.py:185-250) ----------
+// One launch builds a whole batch from device-resident sample matrices: a warp owns one
+// (sample, slot) of the H history + S candidate slots, copies the news id, the mask byte and the
+// title row of that news (id = title row + 1; id 0 or out of range -> the all-zero title).
+struct AssembleArgs {
+    const int64_t* index;            // [B] sample numbers
+    const int64_t* browsed_ids;      // [N, H]
+    const int64_t* browsed_lens;     // [N]
+    const int64_t* candidate_ids;    // [N, S]
+    const int64_t* candidate_lens;   // [N]
+    const int64_t* titles;           // [n_news, T]
+    long long n_news;
+    int B, H, S, T;
+    int64_t* o_browsed_ids;          // [B, H]
+    int64_t* o_browsed_lens;         // [B]
+    int64_t* o_browsed_titles;       // [B, H, T]
+    uint8_t* o_browsed_mask;         // [B, H]
+    int64_t* o_candidate_ids;        // [B, S]
+    int64_t* o_candidate_titles;     // [B, S, T]
+    uint8_t* o_candidate_mask;       // [B, S]
+};
+__global__ void __launch_bounds__(256) assemble_batch_kernel(const AssembleArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int N = a.H + a.S;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < (long long)a.B * N; w += warps) {
+        const int b = (int)(w / N), slot = (int)(w - (long long)b * N);
+        const long long src = a.index[b];
+        const bool hist = slot < a.H;
+        const int j = hist ? slot : slot - a.H;
+        const long long id = hist ? a.browsed_ids[src * a.H + j] : a.candidate_ids[src * a.S + j];
+        const long long len = hist ? a.browsed_lens[src] : a.candidate_lens[src];
+        const long long o = hist ? (long long)b * a.H + j : (long long)b * a.S + j;
+        if (lane == 0) {
+            (hist ? a.o_browsed_ids : a.o_candidate_ids)[o] = id;
+            (hist ? a.o_browsed_mask : a.o_candidate_mask)[o] = (uint8_t)(j < len);
+            if (slot == 0) a.o_browsed_lens[b] = len;
+        }
+        int64_t* dst = (hist ? a.o_browsed_titles : a.o_candidate_titles) + o * a.T;
+        const bool real = id >= 1 && id <= a.n_news;
+        const int64_t* row = a.titles + (real ? id - 1 : 0) * a.T;
+        for (int t = lane; t < a.T; t += 32) dst[t] = real ? __ldg(row + t) : 0;
+    }
+}
+
 }  // namespace nrms

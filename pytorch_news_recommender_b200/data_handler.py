@@ -17,8 +17,8 @@ host-side mirror that `torch.utils.data.DataLoader` can drive exactly like the r
 
 `DeviceBatcher` replaces DataLoader + MyDataset for the hot path: the ragged sample lists are packed
 ONCE into padded id matrices, the title dict becomes a resident `[n_news, T]` int64 table in HBM,
-and a batch is three row gathers by our `nrms_gather_rows_i64` kernel (sample rows of the two id
-matrices, then title rows by news id with id 0 -> the all-zero title).  The ~110 Python dict
+and a batch is ONE launch of our `nrms_assemble_batch` kernel (a warp per sample slot copies the
+news id, the mask byte and the title row of that news, id 0 -> the all-zero title).  The ~110 Python dict
 look-ups per sample of the reference loader disappear and the batch never touches the host.
 The tensors it yields are bit-identical to `default_collate` over `MyDataset` (tests/test_gpu_data.py).
 """
@@ -230,30 +230,14 @@ class DeviceBatcher:
         self.candidate_lens = torch.from_numpy(cl).to(dev)
         self._gen = torch.Generator()
         self._gen.manual_seed(seed)
-        self._ar_h = torch.arange(config.history_len, device=dev)
-        self._ar_s = torch.arange(self.sample_size, device=dev)
 
     def __len__(self):
         return self.n // self.batch_size if self.drop_last else (self.n + self.batch_size - 1) // self.batch_size
 
     def batch(self, index: torch.Tensor) -> Dict[str, torch.Tensor]:
         """The batch of the samples `index` (int64, CUDA)."""
-        H, S, T = self.config.history_len, self.sample_size, self.config.n_words_title
-        B = index.numel()
-        b_ids = ops.gather_rows(self.browsed_ids, index, base=0)            # [B, H]
-        c_ids = ops.gather_rows(self.candidate_ids, index, base=0)          # [B, S]
-        b_len = self.browsed_lens[index]
-        c_len = self.candidate_lens[index]
-        # news id = title row + 1; id 0 (padding) -> the all-zero title
-        b_t = ops.gather_rows(self.titles, b_ids.view(-1), base=1).view(B, H, T)
-        c_t = ops.gather_rows(self.titles, c_ids.view(-1), base=1).view(B, S, T)
-        return {'browsed_lens': b_len,
-                'browsed_ids': b_ids,
-                'browsed_titles': b_t,
-                'browsed_mask': (self._ar_h[None, :] < b_len[:, None]).to(torch.uint8),
-                'candidate_ids': c_ids,
-                'candidate_titles': c_t,
-                'candidate_mask': (self._ar_s[None, :] < c_len[:, None]).to(torch.uint8)}
+        return ops.assemble_batch(index, self.browsed_ids, self.browsed_lens, self.candidate_ids,
+                                  self.candidate_lens, self.titles)
 
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         order = torch.randperm(self.n, generator=self._gen) if self.shuffle else torch.arange(self.n)

@@ -214,6 +214,28 @@ def rank_metrics(scores, labels, offsets, max_len: int, row_stride: Optional[int
     return out
 
 
+def assemble_batch(index, browsed_ids, browsed_lens, candidate_ids, candidate_lens, titles):
+    """One-launch batch assembly (include/nrms_b200.h: nrms_assemble_batch).  All inputs int64 CUDA
+    tensors; returns the dict of batch tensors `MyDataset` + default_collate would produce for the
+    keys the NRMS path reads."""
+    _require_cuda(index, browsed_ids, browsed_lens, candidate_ids, candidate_lens, titles)
+    B, H, S, T = index.numel(), browsed_ids.shape[1], candidate_ids.shape[1], titles.shape[1]
+    dev = index.device
+    out = {'browsed_lens': torch.empty(B, dtype=torch.int64, device=dev),
+           'browsed_ids': torch.empty((B, H), dtype=torch.int64, device=dev),
+           'browsed_titles': torch.empty((B, H, T), dtype=torch.int64, device=dev),
+           'browsed_mask': torch.empty((B, H), dtype=torch.uint8, device=dev),
+           'candidate_ids': torch.empty((B, S), dtype=torch.int64, device=dev),
+           'candidate_titles': torch.empty((B, S, T), dtype=torch.int64, device=dev),
+           'candidate_mask': torch.empty((B, S), dtype=torch.uint8, device=dev)}
+    check(_lib.load().nrms_assemble_batch(
+        ptr(index), B, ptr(browsed_ids), ptr(browsed_lens), ptr(candidate_ids), ptr(candidate_lens), ptr(titles),
+        titles.shape[0], H, S, T, ptr(out['browsed_ids']), ptr(out['browsed_lens']), ptr(out['browsed_titles']),
+        ptr(out['browsed_mask']), ptr(out['candidate_ids']), ptr(out['candidate_titles']),
+        ptr(out['candidate_mask']), _stream()), "nrms_assemble_batch")
+    return out
+
+
 def rank_positions(scores, lens):
     """Padded scores float32 [N, S], lens int64 [N] -> int32 [N, S]: 1-based rank of every real
     candidate inside its impression (train_eval.py:279-285), 0 in the padded slots."""
