@@ -519,6 +519,13 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             g.m_tiles = tok_tiles; g.n_tiles = 1;
             g.k_steps = ceil_div(Q, 16); g.k_chunks = ceil_div(g.k_steps, 4);
             g.row_w = sv.w; g.seq_vec = d_out; g.seq_len = L;
+            if (hp && drop.enabled()) {
+                // the head-padded attention backward takes dO = d_ctx * keep/(1-p) ready-made: the context
+                // dropout mask (nrms_v0.py:171-173) is applied here, where every row is already in registers
+                g.mask_bits = reinterpret_cast<const uint32_t*>(sv.cmask);
+                g.mask_words = mb / 4;
+                g.mask_scale = drop.scale;
+            }
             if (tok_tiles * 2 <= kNumSMs) {
                 // few token tiles (the user encoder): 64-column tiles so that the grid fills the SMs
                 g.n_tiles = ceil_div(D, 64);
@@ -547,6 +554,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
                 a.qkv_lo = a.qkv_hi + (long long)d.n_seq * 32 * NP;
                 a.np = NP;
+                a.cmask = nullptr;   // d_ctx arrives with the context-dropout mask applied (dgrad GEMM epilogue)
                 const long long items = (long long)d.n_seq * h;
                 const size_t smem = attn_hp_bwd_smem_bytes();
                 const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpBwdWarps), getenv("NRMS_HP_BWD_GRID") ? atoi(getenv("NRMS_HP_BWD_GRID")) : 2 * kNumSMs);   // persistent warps

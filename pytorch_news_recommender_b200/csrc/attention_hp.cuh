@@ -144,34 +144,26 @@ __device__ __forceinline__ void hp_store_a(uint32_t pair, const uint32_t (&ah)[2
 template <int TERMS, bool BT>
 __device__ __forceinline__ void hp_mma(float (&c)[2][4][4], const uint32_t (&ah)[2][2][4], const uint32_t (&al)[2][2][4],
                                        uint32_t pair, int lane) {
-    // all B fragments first (one ldmatrix.x4 per 8-wide n block = the (k 0-7, k 8-15) halves of both
-    // k-steps), then the MMAs ordered so that eight independent accumulators sit between two
-    // updates of the same one: the tensor pipe never waits on its own result
-    uint32_t bh[4][4], bl[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
+        // one ldmatrix.x4 = the (k 0-7, k 8-15) halves of both k-steps for this 8-wide n block
         const uint32_t addr = BT ? pair + lane * kHpRowB + nt * 16 : pair + (8 * nt + (lane & 7)) * kHpRowB + (lane >> 3) * 16;
-        if (BT) ldsm_x4_t(bh[nt], addr); else ldsm_x4(bh[nt], addr);
+        uint32_t bh[4], bl[4];
+        if (BT) ldsm_x4_t(bh, addr); else ldsm_x4(bh, addr);
         if (TERMS == 3) {
-            if (BT) ldsm_x4_t(bl[nt], addr + kHpPlaneB); else ldsm_x4(bl[nt], addr + kHpPlaneB);
-        }
-    }
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-        if (TERMS == 3) {
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) mma_bf16(c[mt][nt], al[ks][mt], bh[nt][2 * ks], bh[nt][2 * ks + 1]);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) mma_bf16(c[mt][nt], ah[ks][mt], bl[nt][2 * ks], bl[nt][2 * ks + 1]);
+            if (BT) ldsm_x4_t(bl, addr + kHpPlaneB); else ldsm_x4(bl, addr + kHpPlaneB);
         }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int ks = 0; ks < 2; ++ks) {
+            if (TERMS == 3) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) mma_bf16(c[mt][nt], ah[ks][mt], bh[nt][2 * ks], bh[nt][2 * ks + 1]);
+                for (int mt = 0; mt < 2; ++mt) mma_bf16(c[mt][nt], al[ks][mt], bh[2 * ks], bh[2 * ks + 1]);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) mma_bf16(c[mt][nt], ah[ks][mt], bl[2 * ks], bl[2 * ks + 1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) mma_bf16(c[mt][nt], ah[ks][mt], bh[2 * ks], bh[2 * ks + 1]);
+        }
     }
 }
 // accumulator layout -> fp32 staging tile (row stride kHpStage), rows scaled by mul[mt][half]
@@ -250,14 +242,13 @@ __global__ void __launch_bounds__(kHpFwdWarps * 32, 2) attn_hp_fwd_kernel(const 
     const int g0 = col >> 3;
     const bool drop = a.drop.enabled();
     if (drop) {
+        // only the ng (<= 5) eight-column groups this head touches: L*ng Philox calls over the warp
         const int ng = ((col + dk + 7) >> 3) - g0;
-        for (int it = lane; it < L * 8; it += 32) {
-            const int l = it >> 3, gi = it & 7;
-            if (gi < ng) {
-                const uint32_t keep = a.drop.keep8(kDropContext, (uint64_t)(row0 + l), (uint32_t)(g0 + gi));
-                smask[l * 8 + gi] = (uint8_t)keep;
-                if (a.cmask && g0 + gi < a.mask_bytes) a.cmask[(row0 + l) * a.mask_bytes + g0 + gi] = (uint8_t)keep;
-            }
+        for (int it = lane; it < L * ng; it += 32) {
+            const int l = it / ng, gi = it - l * ng;
+            const uint32_t keep = a.drop.keep8(kDropContext, (uint64_t)(row0 + l), (uint32_t)(g0 + gi));
+            smask[l * 8 + gi] = (uint8_t)keep;
+            if (a.cmask && g0 + gi < a.mask_bytes) a.cmask[(row0 + l) * a.mask_bytes + g0 + gi] = (uint8_t)keep;
         }
     }
     cp_async_wait_all();
@@ -317,6 +308,34 @@ __global__ void __launch_bounds__(kHpFwdWarps * 32, 2) attn_hp_fwd_kernel(const 
     }
 }
 
+// dO of one (sequence, head): fp32 rows [row0, row0+L) x columns [col, col+dk) of d_ctx land in a
+// 32 x kHpStage fp32 tile by 8-byte cp.async (16 lanes walk the even rows, 16 the odd rows)
+__device__ __forceinline__ void hp_request_do(uint32_t tile, const float* d_ctx, long long row0, int D, int col, int L,
+                                              int dk, int lane) {
+    const int pp = lane & 15, par = lane >> 4;
+    if (2 * pp < dk) {
+        const float* gp = d_ctx + (row0 + par) * D + col + 2 * pp;
+        uint32_t dst = tile + (par * kHpStage + 2 * pp) * 4;
+        for (int l = par; l < L; l += 2) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gp) : "memory");
+            dst += 2 * kHpStage * 4;
+            gp += 2 * D;
+        }
+    }
+}
+// the tile -> A fragments (raw fp32 pairs; zero outside [L) x [dk): those cells were never written)
+__device__ __forceinline__ void hp_read_do(float2 (&v)[2][2][4], const float* tile, int L, int dk, int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = 16 * mt + 8 * (i & 1) + g, d = 16 * ks + 8 * (i >> 1) + 2 * t;
+                v[ks][mt][i] = (r < L && d < dk) ? *reinterpret_cast<const float2*>(tile + r * kHpStage + d) : make_float2(0.f, 0.f);
+            }
+}
+
 // ------------------------------------------------------------------------------------------------
 // backward
 //   P = exp(scale*Q K^T - lse) ; dP = dO V^T ; dS = scale * P o (dP - delta) ; delta = rowsum(P o dP)
@@ -328,6 +347,17 @@ __global__ void __launch_bounds__(kHpBwdWarps * 32, 2) attn_hp_bwd_kernel(const 
     uint8_t* sm = reinterpret_cast<uint8_t*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * kHpBwdWarps;
+    // dO of the NEXT item is requested (cp.async into the dO/dS pair, dead after the dK product) while
+    // the current item still has its dQ product and two write-outs to do, and is consumed at the top
+    // of the next iteration: its DRAM latency never stalls the warp
+    {
+        const long long item0 = (long long)blockIdx.x * kHpBwdWarps + warp;
+        if (item0 < n_items) {
+            const long long seq0 = item0 / a.n_heads;
+            const uint32_t G0 = (uint32_t)__cvta_generic_to_shared(sm + (size_t)warp * 4 * kHpPairB) + 3 * kHpPairB;
+            hp_request_do(G0, a.d_ctx, seq0 * a.L, a.D, (int)(item0 - seq0 * a.n_heads) * a.dk, a.L, a.dk, lane);
+        }
+    }
     for (long long item = (long long)blockIdx.x * kHpBwdWarps + warp; item < n_items; item += stride) {
     const int L = a.L, D = a.D, dk = a.dk, DP = 32 * a.n_heads;
     const long long seq = item / a.n_heads;
@@ -345,30 +375,6 @@ __global__ void __launch_bounds__(kHpBwdWarps * 32, 2) attn_hp_bwd_kernel(const 
     hp_load_pair<TERMS == 3>(Qs, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 0, h, a.n_heads), L, lane);
     hp_load_pair<TERMS == 3>(Ks, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads), L, lane);
     hp_load_pair<TERMS == 3>(Vs, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads), L, lane);
-    // dO = d_ctx * keep/(1-p): fp32 rows straight from global memory in the A-fragment layout
-    // (8 rows x 32 contiguous bytes per load), split once, kept as the A operand of dP and stored
-    // as a [row][d] pair for dV's B operand
-    uint32_t gh[2][2][4], gl[2][2][4];
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = 16 * mt + 8 * (i & 1) + g, d = 16 * ks + 8 * (i >> 1) + 2 * t;
-                float2 v = make_float2(0.f, 0.f);
-                if (r < L && d < dk) {
-                    v = __ldg(reinterpret_cast<const float2*>(a.d_ctx + (row0 + r) * D + col + d));
-                    if (drop) {
-                        const int c = col + d;
-                        const uint32_t keep = (uint32_t)__ldg(a.cmask + (row0 + r) * a.mask_bytes + (c >> 3)) >> (c & 7);
-                        v.x = (keep & 1u) ? v.x * a.drop.scale : 0.f;
-                        v.y = (keep & 2u) ? v.y * a.drop.scale : 0.f;
-                    }
-                }
-                split_pair(v.x, v.y, gh[ks][mt][i], gl[ks][mt][i]);
-            }
-    hp_store_a<TERMS>(Gs, gh, gl, g, t);
     // rows of this lane in the accumulator layout: r(mt,hf) = 16mt + 8hf + g
     float lse[2][2];
 #pragma unroll
@@ -380,14 +386,42 @@ __global__ void __launch_bounds__(kHpBwdWarps * 32, 2) attn_hp_bwd_kernel(const 
         }
     cp_async_wait_all();
     __syncwarp();
+    // dO (requested during the previous item; d_ctx carries the context-dropout mask already when the
+    // tensor-core data-gradient GEMM produced it): fp32 tile -> fragments, split once, kept as the A
+    // operand of dP and stored over the tile as a [row][d] pair for dV's B operand
+    uint32_t gh[2][2][4], gl[2][2][4];
+    {
+        float2 v[2][2][4];
+        hp_read_do(v, reinterpret_cast<const float*>(Qb + 3 * kHpPairB), L, dk, g, t);
+        __syncwarp();                                   // every lane has its fp32 values before the planes overwrite them
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 x = v[ks][mt][i];
+                    if (drop) {
+                        const int r = 16 * mt + 8 * (i & 1) + g, c = col + 16 * ks + 8 * (i >> 1) + 2 * t;
+                        if (r < L && c < col + dk) {
+                            const uint32_t keep = (uint32_t)__ldg(a.cmask + (row0 + r) * a.mask_bytes + (c >> 3)) >> (c & 7);
+                            x.x = (keep & 1u) ? x.x * a.drop.scale : 0.f;
+                            x.y = (keep & 2u) ? x.y * a.drop.scale : 0.f;
+                        }
+                    }
+                    split_pair(x.x, x.y, gh[ks][mt][i], gl[ks][mt][i]);
+                }
+    }
+    hp_store_a<TERMS>(Gs, gh, gl, g, t);
+    __syncwarp();
     if (item + stride < n_items) {
         const long long nseq = (item + stride) / a.n_heads;
         const int nh = (int)(item + stride - nseq * a.n_heads);
         hp_prefetch_blocks<TERMS == 3>(a, nseq, nh, 0, lane);
+        // the next item's keep bits and log-sum-exps are small, latency-exposed loads: pull them into L2
         if (lane < L) {
-            const float* q = a.d_ctx + (nseq * L + lane) * D + nh * dk;
-            prefetch_l2(q);
-            prefetch_l2(q + dk - 1);
+            if (drop) prefetch_l2(a.cmask + (nseq * L + lane) * a.mask_bytes + ((nh * dk) >> 3));
+            prefetch_l2(a.lse + (nseq * L + lane) * a.n_heads + nh);
         }
     }
 
@@ -448,7 +482,11 @@ __global__ void __launch_bounds__(kHpBwdWarps * 32, 2) attn_hp_bwd_kernel(const 
     zero_frag(acc);
     hp_load_a<TERMS, true>(ah, al, Gs, lane);           // dS^T
     hp_mma<TERMS, true>(acc, ah, al, Qs, lane);         // dK[key][d] = sum_row dS[row][key] Q[row][d]
-    __syncwarp();                                       // all reads of Q are done
+    __syncwarp();                                       // all reads of Q and of dS^T are done
+    if (item + stride < n_items) {                      // the dO/dS pair is dead: the next item's dO lands there
+        const long long nseq = (item + stride) / a.n_heads;
+        hp_request_do(Gs, a.d_ctx, nseq * L, D, (int)(item + stride - nseq * a.n_heads) * dk, L, dk, lane);
+    }
     hp_stage(reinterpret_cast<float*>(Qb), acc, one, g, t);                  // dK over Q
     __syncwarp();
     hp_write_img(reinterpret_cast<const float*>(Qb), L, row0, DP + colp, im, lane);

@@ -151,7 +151,7 @@ struct IgArgs {
     const float* bias;          // EPI_BIAS / EPI_TANH_DOT: [N]
     const float* qv;            // EPI_TANH_DOT: [N]
     float* dot_out;             // EPI_TANH_DOT: [M]  sum_n tanh(.)*qv[n]
-    const uint32_t* mask_bits;  // EPI_MASK: [M, mask_words] keep bits (bit n%32 of word n/32), or NULL
+    const uint32_t* mask_bits;  // EPI_MASK / EPI_POOLADD: [M, mask_words] keep bits (bit n%32 of word n/32), or NULL
     int mask_words;
     float mask_scale;           // 1/(1-p)
     const float* row_w;         // EPI_POOLADD: [M] pooling weight of each token row
@@ -377,13 +377,6 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
             }
             const int m = m_tile * 128 + q * 32 + lane;
             const bool row_ok = m < a.M;
-            uint32_t mw[10];
-            if (EPI == EPI_MASK) {
-#pragma unroll
-                for (int i = 0; i < 10; ++i)
-                    mw[i] = (a.mask_bits && row_ok && i < a.mask_words) ? __ldg(a.mask_bits + (long long)m * a.mask_words + i)
-                                                                       : 0xffffffffu;
-            }
             float rw = 0.f;
             const float* svec = nullptr;
             if (EPI == EPI_POOLADD && row_ok) {
@@ -399,6 +392,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
             float dot = 0.f;
 #pragma unroll 1
             for (int cb = 0; cb < N_T; cb += 32) {
+                // keep bits of this row's 32 columns [n0 + cb, +32): one word (n0 and cb are multiples of 32),
+                // requested before the TMEM read so that its latency hides behind it
+                uint32_t mword = 0xffffffffu;
+                if ((EPI == EPI_MASK || EPI == EPI_POOLADD) && a.mask_bits && row_ok && ((n0 + cb) >> 5) < a.mask_words)
+                    mword = __ldg(a.mask_bits + (long long)m * a.mask_words + ((n0 + cb) >> 5));
                 float v[32];
                 tc::tmem_ld32(t_row + (uint32_t)cb, v);
                 if (EPI == EPI_BIAS_SPLIT) {
@@ -461,8 +459,8 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                         o.x = fmaf(rw, old[g].x, o.x); o.y = fmaf(rw, old[g].y, o.y);
                         o.z = fmaf(rw, old[g].z, o.z); o.w = fmaf(rw, old[g].w, o.w);
                     }
-                    if (EPI == EPI_MASK) {
-                        const uint32_t bits = mw[(n0 + n) >> 5] >> ((n0 + n) & 31);
+                    if (EPI == EPI_MASK || EPI == EPI_POOLADD) {   // POOLADD: the context-dropout mask of the consumer
+                        const uint32_t bits = mword >> (4 * g);
                         o.x = (bits & 1u) ? o.x * a.mask_scale : 0.f;
                         o.y = (bits & 2u) ? o.y * a.mask_scale : 0.f;
                         o.z = (bits & 4u) ? o.z * a.mask_scale : 0.f;
