@@ -556,6 +556,18 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 a.np = NP;
                 a.cmask = nullptr;   // d_ctx arrives with the context-dropout mask applied (dgrad GEMM epilogue)
                 const long long items = (long long)d.n_seq * h;
+                if (getenv("NRMS_HP_BWD1") == nullptr) {
+                    // two warps per (sequence, head): twice the warps for the same shared memory
+                    const size_t smem2 = (size_t)kHp2Pairs * 4 * kHpPairB;
+                    const unsigned grid2 = (unsigned)std::min<long long>(ceil_div64(items, kHp2Pairs), 2 * kNumSMs);
+                    if (terms == 3) {
+                        if ((rc = set_smem(attn_hp2_bwd_kernel<3>, smem2))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hp2_bwd_kernel<3><<<grid2, kHp2Pairs * 64, smem2, s>>>(a, items)));
+                    } else {
+                        if ((rc = set_smem(attn_hp2_bwd_kernel<1>, smem2))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hp2_bwd_kernel<1><<<grid2, kHp2Pairs * 64, smem2, s>>>(a, items)));
+                    }
+                } else {
                 const size_t smem = attn_hp_bwd_smem_bytes();
                 const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpBwdWarps), getenv("NRMS_HP_BWD_GRID") ? atoi(getenv("NRMS_HP_BWD_GRID")) : 2 * kNumSMs);   // persistent warps
                 if (terms == 3) {
@@ -564,6 +576,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 } else {
                     if ((rc = set_smem(attn_hp_bwd_kernel<1>, smem))) return rc;
                     NRMS_LAUNCH("attn_bwd", s, (attn_hp_bwd_kernel<1><<<grid, kHpBwdWarps * 32, smem, s>>>(a, items)));
+                }
                 }
             } else if (L <= kTile && dk % 2 == 0) {
                 const long long items = (long long)d.n_seq * h;

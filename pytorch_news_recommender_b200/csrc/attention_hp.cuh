@@ -502,4 +502,255 @@ __global__ void __launch_bounds__(kHpBwdWarps * 32, 2) attn_hp_bwd_kernel(const 
     }
 }
 
+// ================================================================================================
+// Two warps per (sequence, head)  ("hp2")
+// ================================================================================================
+// Shared memory holds ten items per SM whatever the kernel does (four pairs = 20 KB each), so with one
+// warp per item an SM runs ten warps and the kernel is bound by the latency of each warp's serial
+// instruction stream.  Here a PAIR of warps owns an item: warp `mh` owns query rows [16mh, 16mh+16)
+// for S, dP, P, dS and dQ, and key rows [16mh, 16mh+16) for dV and dK (A = P^T / dS^T over ALL query
+// rows, read from the shared P / dS planes), so no product needs a cross-warp reduction.  Twenty
+// warps per SM, half the registers per thread, the item's critical path roughly halved.  The two
+// warps meet at a 64-thread named barrier wherever one reads what the other wrote.
+constexpr int kHp2Pairs = 5;                   // warp pairs (items in flight) per CTA, 2 CTAs / SM
+
+__device__ __forceinline__ void pair_bar(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+template <int TERMS, bool AT>
+__device__ __forceinline__ void hp2_load_a(uint32_t (&ah)[2][4], uint32_t (&al)[2][4], uint32_t pair, int mh, int lane) {
+    const int r7 = lane & 7, j0 = (lane >> 3) & 1, j1 = lane >> 4;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const uint32_t addr = AT ? pair + (16 * ks + r7 + 8 * j1) * kHpRowB + (16 * mh + 8 * j0) * 2
+                                 : pair + (16 * mh + r7 + 8 * j0) * kHpRowB + (16 * ks + 8 * j1) * 2;
+        if (AT) ldsm_x4_t(ah[ks], addr); else ldsm_x4(ah[ks], addr);
+        if (TERMS == 3) {
+            if (AT) ldsm_x4_t(al[ks], addr + kHpPlaneB); else ldsm_x4(al[ks], addr + kHpPlaneB);
+        }
+    }
+}
+template <int TERMS>
+__device__ __forceinline__ void hp2_split_acc(uint32_t (&ah)[2][4], uint32_t (&al)[2][4], const float (&p)[4][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        split_pair(p[2 * ks][0], p[2 * ks][1], ah[ks][0], al[ks][0]);
+        split_pair(p[2 * ks][2], p[2 * ks][3], ah[ks][1], al[ks][1]);
+        split_pair(p[2 * ks + 1][0], p[2 * ks + 1][1], ah[ks][2], al[ks][2]);
+        split_pair(p[2 * ks + 1][2], p[2 * ks + 1][3], ah[ks][3], al[ks][3]);
+    }
+}
+template <int TERMS>
+__device__ __forceinline__ void hp2_store_a(uint32_t pair, const uint32_t (&ah)[2][4], const uint32_t (&al)[2][4], int mh,
+                                            int g, int t) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t addr = pair + (16 * mh + g + 8 * (i & 1)) * kHpRowB + (16 * ks + 8 * (i >> 1) + 2 * t) * 2;
+            sts32(addr, ah[ks][i]);
+            if (TERMS == 3) sts32(addr + kHpPlaneB, al[ks][i]);
+        }
+}
+// c[nt] += A[16 x 32] * B[32 x 32]: A fragments in registers, B in a pair ([n][k] or, BT, [k][n])
+template <int TERMS, bool BT>
+__device__ __forceinline__ void hp2_mma(float (&c)[4][4], const uint32_t (&ah)[2][4], const uint32_t (&al)[2][4], uint32_t pair,
+                                        int lane) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const uint32_t addr = BT ? pair + lane * kHpRowB + nt * 16 : pair + (8 * nt + (lane & 7)) * kHpRowB + (lane >> 3) * 16;
+        uint32_t bh[4], bl[4];
+        if (BT) ldsm_x4_t(bh, addr); else ldsm_x4(bh, addr);
+        if (TERMS == 3) {
+            if (BT) ldsm_x4_t(bl, addr + kHpPlaneB); else ldsm_x4(bl, addr + kHpPlaneB);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            if (TERMS == 3) {
+                mma_bf16(c[nt], al[ks], bh[2 * ks], bh[2 * ks + 1]);
+                mma_bf16(c[nt], ah[ks], bl[2 * ks], bl[2 * ks + 1]);
+            }
+            mma_bf16(c[nt], ah[ks], bh[2 * ks], bh[2 * ks + 1]);
+        }
+    }
+}
+__device__ __forceinline__ void hp2_zero(float (&c)[4][4]) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[nt][i] = 0.f;
+}
+__device__ __forceinline__ void hp2_stage(float* tile, const float (&c)[4][4], int mh, int g, int t) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        float* p = tile + (16 * mh + g) * kHpStage + 8 * nt + 2 * t;
+        *reinterpret_cast<float2*>(p) = make_float2(c[nt][0], c[nt][1]);
+        *reinterpret_cast<float2*>(p + 8 * kHpStage) = make_float2(c[nt][2], c[nt][3]);
+    }
+}
+// rows [16mh, 16mh+16) of the staging tile -> image columns [gcol0, gcol0 + 32)
+__device__ __forceinline__ void hp2_write_img(const float* tile, int mh, int L, long long row0, int gcol0, const ig::Img& img,
+                                              int lane) {
+    const int r8 = lane >> 2, u = lane & 3;
+    const int gg = (gcol0 >> 3) + u;
+    const long long cbase = (long long)(gg >> 3) * img.chunk_stride;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int l = 16 * mh + r8 + 8 * i;
+        if (l < L) {
+            const float4 v0 = *reinterpret_cast<const float4*>(tile + l * kHpStage + 8 * u);
+            const float4 v1 = *reinterpret_cast<const float4*>(tile + l * kHpStage + 8 * u + 4);
+            uint32_t hi[4], lo[4];
+            split_pair(v0.x, v0.y, hi[0], lo[0]);
+            split_pair(v0.z, v0.w, hi[1], lo[1]);
+            split_pair(v1.x, v1.y, hi[2], lo[2]);
+            split_pair(v1.z, v1.w, hi[3], lo[3]);
+            const long long r = row0 + l;
+            const int r7 = (int)(r & 7);
+            const long long off = cbase + (r >> 3) * 1024 + r7 * 128 + (((gg & 7) ^ r7) << 4);
+            *reinterpret_cast<uint4*>(img.hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(img.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
+template <int TERMS>
+__global__ void __launch_bounds__(kHp2Pairs * 64, 2) attn_hp2_bwd_kernel(const AttnArgs a, long long n_items) {
+    extern __shared__ __align__(16) float smem[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pr = warp >> 1, mh = warp & 1, bar = 1 + pr;
+    const int g = lane >> 2, t = lane & 3;
+    const int L = a.L, D = a.D, dk = a.dk, DP = 32 * a.n_heads;
+    const long long stride = (long long)gridDim.x * kHp2Pairs;
+    uint8_t* Qb = sm + (size_t)pr * 4 * kHpPairB;
+    const uint32_t Qs = (uint32_t)__cvta_generic_to_shared(Qb);   // Q  -> dK staging
+    const uint32_t Ks = Qs + kHpPairB;                            // K  -> dQ staging
+    const uint32_t Vs = Ks + kHpPairB;                            // V  -> P -> dV staging
+    const uint32_t Gs = Vs + kHpPairB;                            // dO (fp32 tile, then planes) -> dS
+    float* const stageQ = reinterpret_cast<float*>(Qb);
+    float* const stageK = reinterpret_cast<float*>(Qb + kHpPairB);
+    float* const stageV = reinterpret_cast<float*>(Qb + 2 * kHpPairB);
+    const float* const tileG = reinterpret_cast<const float*>(Qb + 3 * kHpPairB);
+    const bool drop = a.drop.enabled() && a.cmask != nullptr;
+    const ig::Img& im = a.d_qkv_img;
+    {
+        const long long item0 = (long long)blockIdx.x * kHp2Pairs + pr;
+        if (item0 < n_items && mh == 1) {
+            const long long seq0 = item0 / a.n_heads;
+            hp_request_do(Gs, a.d_ctx, seq0 * L, D, (int)(item0 - seq0 * a.n_heads) * dk, L, dk, lane);
+        }
+    }
+    for (long long item = (long long)blockIdx.x * kHp2Pairs + pr; item < n_items; item += stride) {
+        const long long seq = item / a.n_heads;
+        const int h = (int)(item - seq * a.n_heads);
+        const long long row0 = seq * L;
+        const int col = h * dk, colp = h * 32;
+        const bool has_next = item + stride < n_items;
+        const long long nseq = (item + stride) / a.n_heads;
+        const int nh = (int)(item + stride - nseq * a.n_heads);
+        if (mh == 0) {
+            hp_load_pair<TERMS == 3>(Qs, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 0, h, a.n_heads), L, lane);
+            hp_load_pair<TERMS == 3>(Ks, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads), L, lane);
+        } else {
+            hp_load_pair<TERMS == 3>(Vs, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads), L, lane);
+        }
+        float lse[2];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int r = 16 * mh + 8 * hf + g;
+            lse[hf] = r < L ? a.lse[(row0 + r) * a.n_heads + h] : 0.f;
+        }
+        cp_async_wait_all();
+        pair_bar(bar);                                      // Q K V and the dO tile are visible to both warps
+        uint32_t gh[2][4], gl[2][4];
+        {
+            float2 v[2][4];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = 16 * mh + 8 * (i & 1) + g, d = 16 * ks + 8 * (i >> 1) + 2 * t;
+                    v[ks][i] = (r < L && d < dk) ? *reinterpret_cast<const float2*>(tileG + r * kHpStage + d) : make_float2(0.f, 0.f);
+                    if (drop && r < L && d < dk) {
+                        const int c = col + d;
+                        const uint32_t keep = (uint32_t)__ldg(a.cmask + (row0 + r) * a.mask_bytes + (c >> 3)) >> (c & 7);
+                        v[ks][i].x = (keep & 1u) ? v[ks][i].x * a.drop.scale : 0.f;
+                        v[ks][i].y = (keep & 2u) ? v[ks][i].y * a.drop.scale : 0.f;
+                    }
+                }
+            pair_bar(bar);                                  // both warps hold their fp32 dO before the planes overwrite the tile
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split_pair(v[ks][i].x, v[ks][i].y, gh[ks][i], gl[ks][i]);
+        }
+        hp2_store_a<TERMS>(Gs, gh, gl, mh, g, t);           // own rows of the dO planes (dV's B operand)
+        if (has_next && mh == 0) {
+            hp_prefetch_blocks<TERMS == 3>(a, nseq, nh, 0, lane);
+            if (lane < L) prefetch_l2(a.lse + (nseq * L + lane) * a.n_heads + nh);
+        }
+        float p[4][4], ds[4][4];
+        hp2_zero(p);
+        hp2_zero(ds);
+        {
+            uint32_t qh[2][4], ql[2][4];
+            hp2_load_a<TERMS, false>(qh, ql, Qs, mh, lane);
+            hp2_mma<TERMS, false>(p, qh, ql, Ks, lane);     // S  (own query rows x all keys)
+        }
+        hp2_mma<TERMS, false>(ds, gh, gl, Vs, lane);        // dP
+        float delta[2] = {0.f, 0.f};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int hf = i >> 1;
+                const bool ok = (16 * mh + 8 * hf + g < L) && (8 * nt + 2 * t + (i & 1) < L);
+                const float pv = ok ? __expf(p[nt][i] * a.scale - lse[hf]) : 0.f;
+                p[nt][i] = pv;
+                delta[hf] = fmaf(pv, ds[nt][i], delta[hf]);
+            }
+        delta[0] = quad_sum(delta[0]);
+        delta[1] = quad_sum(delta[1]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ds[nt][i] = p[nt][i] * (ds[nt][i] - delta[i >> 1]) * a.scale;
+        uint32_t sh[2][4], sl[2][4];                        // dS fragments: A operand of dQ, stored for dK
+        hp2_split_acc<TERMS>(sh, sl, ds);
+        {
+            uint32_t ph[2][4], pl[2][4];
+            hp2_split_acc<TERMS>(ph, pl, p);
+            pair_bar(bar);                                  // both warps are done reading V (dP); dO planes complete
+            hp2_store_a<TERMS>(Vs, ph, pl, mh, g, t);       // own rows of P[row][key] over V
+        }
+        pair_bar(bar);                                      // P complete
+        float acc[4][4];
+        uint32_t ah[2][4], al[2][4];
+        hp2_zero(acc);
+        hp2_load_a<TERMS, true>(ah, al, Vs, mh, lane);      // P^T, own keys x all query rows
+        hp2_mma<TERMS, true>(acc, ah, al, Gs, lane);        // dV[own keys][d]
+        pair_bar(bar);                                      // both warps are done reading P and dO
+        hp2_stage(stageV, acc, mh, g, t);                   // own rows of dV over P
+        hp2_store_a<TERMS>(Gs, sh, sl, mh, g, t);           // own rows of dS[row][key] over dO
+        pair_bar(bar);                                      // dS complete (and the own staging rows are visible)
+        hp2_write_img(stageV, mh, L, row0, 2 * DP + colp, im, lane);
+        hp2_zero(acc);
+        hp2_load_a<TERMS, true>(ah, al, Gs, mh, lane);      // dS^T, own keys x all query rows
+        hp2_mma<TERMS, true>(acc, ah, al, Qs, lane);        // dK[own keys][d]
+        pair_bar(bar);                                      // both warps are done reading Q and dS
+        if (has_next && mh == 1) hp_request_do(Gs, a.d_ctx, nseq * L, D, nh * dk, L, dk, lane);   // next item's dO
+        hp2_stage(stageQ, acc, mh, g, t);                   // own rows of dK over Q
+        __syncwarp();
+        hp2_write_img(stageQ, mh, L, row0, DP + colp, im, lane);
+        hp2_zero(acc);
+        hp2_mma<TERMS, true>(acc, sh, sl, Ks, lane);        // dQ[own rows][d]
+        pair_bar(bar);                                      // both warps are done reading K
+        hp2_stage(stageK, acc, mh, g, t);                   // own rows of dQ over K
+        __syncwarp();
+        hp2_write_img(stageK, mh, L, row0, colp, im, lane);
+        if (mh == 0) pad_image(im, row0, L, 0, 0, false, item == n_items - 1, a.M, lane);
+        pair_bar(bar);                                      // all staging reads are done before the next item's copies land
+    }
+}
+
 }  // namespace nrms
