@@ -12,6 +12,7 @@
 #include "attention.cuh"
 #include "attention_mma.cuh"
 #include "attention_hp.cuh"
+#include "attention_hpn.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gather.cuh"
@@ -95,14 +96,15 @@ constexpr int kWqkvRows = 1024, kWaRows = 256;
 
 inline int mask_bytes_for(int D) { return (int)align_up(ceil_div(D, 8), 4); }
 
-// Head-padded Q|K|V ("HP", gemm_img.cuh: hp_unpad; attention_hp.cuh): tensor-core GEMM modes,
-// sequences of at most 32 tokens, even head dim <= 32, 3*32*h <= 960 projection columns.
+// Head-padded Q|K|V ("HP", gemm_img.cuh: hp_unpad; attention_hp.cuh, attention_hpn.cuh): tensor-core
+// GEMM modes, sequences of at most 64 tokens, even head dim <= 32, 3*32*h <= 960 projection columns.
 inline bool use_hp(const nrms_encoder_dims& d) {
     const int dk = d.d_model / d.n_heads;
-    return d.gemm_mode >= 1 && d.seq_len <= kTile && dk % 2 == 0 && dk <= 32 && 96 * d.n_heads <= 960 &&
+    return d.gemm_mode >= 1 && d.seq_len <= 64 && dk % 2 == 0 && dk <= 32 && 96 * d.n_heads <= 960 &&
            getenv("NRMS_NO_HP") == nullptr;
 }
 inline int hp_cols(const nrms_encoder_dims& d) { return 96 * d.n_heads; }
+inline int hp_rows(const nrms_encoder_dims& d) { return d.seq_len <= 32 ? 32 : 64; }   // rows per head block
 
 struct Saved {
     float* qkv;      // [M, 3D] fp32; HP: bf16 planes hi [M, NP] then lo [M, NP]
@@ -129,7 +131,7 @@ Saved saved_layout(void* blob, const nrms_encoder_dims& d) {
     };
     auto take = [&](int64_t nfloat) { return reinterpret_cast<float*>(take_bytes(nfloat * 4)); };
     Saved s{};
-    s.qkv = use_hp(d) ? take((int64_t)d.n_seq * 32 * hp_cols(d)) : take(M * 3 * D);   // HP: 32-row blocks
+    s.qkv = use_hp(d) ? take((int64_t)d.n_seq * hp_rows(d) * hp_cols(d)) : take(M * 3 * D);   // HP: 32/64-row blocks
     s.lse = take(M * d.n_heads);
     s.ctx = take(M * D);
     s.t = take(M * Q);
@@ -359,8 +361,8 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         NRMS_CHECK_CUDA(ig::img_pack(pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, nullptr, NP, M, NP);
         g.Chi = reinterpret_cast<uint16_t*>(sv.qkv);
-        g.Clo = g.Chi + (long long)d.n_seq * 32 * NP;
-        g.hp_D = D; g.hp_dk = dk; g.seq_len = L;
+        g.Clo = g.Chi + (long long)d.n_seq * hp_rows(d) * NP;
+        g.hp_D = D; g.hp_dk = dk; g.seq_len = L; g.hp_rows = hp_rows(d);
         g.terms = terms;
         g.bias = pv.bqkv;
         g.m_tiles = sv.x_img.rows_pad / 128; g.n_tiles = ceil_div(NP, 256);
@@ -393,17 +395,32 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             // one independent warp per (sequence, head) over the head-padded planes (attention_hp.cuh)
             a.qkv = nullptr;
             a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
-            a.qkv_lo = a.qkv_hi + (long long)d.n_seq * 32 * NP;
+            a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
             a.np = NP;
             const long long items = (long long)d.n_seq * h;
+            if (L > 32) {
+                // four warps per (sequence, head) over 64-row blocks (attention_hpn.cuh)
+                using C = HpN<64>;
+                const size_t smem = (size_t)C::ITEMS_FWD * C::ITEM_FWD;
+                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_FWD), 4 * kNumSMs);
+                const int threads = C::ITEMS_FWD * C::NW * 32;
+                if (terms == 3) {
+                    if ((rc = set_smem(attn_hpn_fwd_kernel<3, 64>, smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<3, 64><<<grid, threads, smem, s>>>(a, items)));
+                } else {
+                    if ((rc = set_smem(attn_hpn_fwd_kernel<1, 64>, smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<1, 64><<<grid, threads, smem, s>>>(a, items)));
+                }
+            } else {
             const size_t smem = attn_hp_fwd_smem_bytes();
-            const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpFwdWarps), getenv("NRMS_HP_FWD_GRID") ? atoi(getenv("NRMS_HP_FWD_GRID")) : 2 * kNumSMs);   // persistent warps
+            const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpFwdWarps), 2 * kNumSMs);   // persistent warps
             if (terms == 3) {
                 if ((rc = set_smem(attn_hp_fwd_kernel<3>, smem))) return rc;
                 NRMS_LAUNCH("attn_fwd", s, (attn_hp_fwd_kernel<3><<<grid, kHpFwdWarps * 32, smem, s>>>(a, items)));
             } else {
                 if ((rc = set_smem(attn_hp_fwd_kernel<1>, smem))) return rc;
                 NRMS_LAUNCH("attn_fwd", s, (attn_hp_fwd_kernel<1><<<grid, kHpFwdWarps * 32, smem, s>>>(a, items)));
+            }
             }
         } else if (L <= kTile && dk % 2 == 0) {
             // one independent warp per (sequence, head), products on mma.sync (attention_mma.cuh)
@@ -552,31 +569,35 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             if (hp) {
                 a.qkv = nullptr;
                 a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
-                a.qkv_lo = a.qkv_hi + (long long)d.n_seq * 32 * NP;
+                a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
                 a.np = NP;
                 a.cmask = nullptr;   // d_ctx arrives with the context-dropout mask applied (dgrad GEMM epilogue)
                 const long long items = (long long)d.n_seq * h;
-                if (getenv("NRMS_HP_BWD1") == nullptr) {
-                    // two warps per (sequence, head): twice the warps for the same shared memory
-                    const size_t smem2 = (size_t)kHp2Pairs * 4 * kHpPairB;
-                    const unsigned grid2 = (unsigned)std::min<long long>(ceil_div64(items, kHp2Pairs), 2 * kNumSMs);
+                // two (sequences of <= 32 tokens) or four warps per (sequence, head): attention_hpn.cuh
+                if (L > 32) {
+                    using C = HpN<64>;
+                    const size_t smem = (size_t)C::ITEMS_BWD * C::ITEM_BWD;
+                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), 2 * kNumSMs);
+                    const int threads = C::ITEMS_BWD * C::NW * 32;
                     if (terms == 3) {
-                        if ((rc = set_smem(attn_hp2_bwd_kernel<3>, smem2))) return rc;
-                        NRMS_LAUNCH("attn_bwd", s, (attn_hp2_bwd_kernel<3><<<grid2, kHp2Pairs * 64, smem2, s>>>(a, items)));
+                        if ((rc = set_smem(attn_hpn_bwd_kernel<3, 64>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<3, 64><<<grid, threads, smem, s>>>(a, items)));
                     } else {
-                        if ((rc = set_smem(attn_hp2_bwd_kernel<1>, smem2))) return rc;
-                        NRMS_LAUNCH("attn_bwd", s, (attn_hp2_bwd_kernel<1><<<grid2, kHp2Pairs * 64, smem2, s>>>(a, items)));
+                        if ((rc = set_smem(attn_hpn_bwd_kernel<1, 64>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<1, 64><<<grid, threads, smem, s>>>(a, items)));
                     }
                 } else {
-                const size_t smem = attn_hp_bwd_smem_bytes();
-                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpBwdWarps), getenv("NRMS_HP_BWD_GRID") ? atoi(getenv("NRMS_HP_BWD_GRID")) : 2 * kNumSMs);   // persistent warps
-                if (terms == 3) {
-                    if ((rc = set_smem(attn_hp_bwd_kernel<3>, smem))) return rc;
-                    NRMS_LAUNCH("attn_bwd", s, (attn_hp_bwd_kernel<3><<<grid, kHpBwdWarps * 32, smem, s>>>(a, items)));
-                } else {
-                    if ((rc = set_smem(attn_hp_bwd_kernel<1>, smem))) return rc;
-                    NRMS_LAUNCH("attn_bwd", s, (attn_hp_bwd_kernel<1><<<grid, kHpBwdWarps * 32, smem, s>>>(a, items)));
-                }
+                    using C = HpN<32>;
+                    const size_t smem = (size_t)C::ITEMS_BWD * C::ITEM_BWD;
+                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), 2 * kNumSMs);
+                    const int threads = C::ITEMS_BWD * C::NW * 32;
+                    if (terms == 3) {
+                        if ((rc = set_smem(attn_hpn_bwd_kernel<3, 32>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<3, 32><<<grid, threads, smem, s>>>(a, items)));
+                    } else {
+                        if ((rc = set_smem(attn_hpn_bwd_kernel<1, 32>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<1, 32><<<grid, threads, smem, s>>>(a, items)));
+                    }
                 }
             } else if (L <= kTile && dk % 2 == 0) {
                 const long long items = (long long)d.n_seq * h;

@@ -67,7 +67,7 @@ __device__ __forceinline__ void load_slot_async(float* slot, const float* src, l
 template <bool SUMS, int RS = kRowStride>
 __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk, long long row0, int gcol0, float* out,
                                                 int ld, const ig::Img& img, const uint8_t* smask, int g0,
-                                                float drop_scale, float* sums, int lane) {
+                                                float drop_scale, float* sums, int lane, int l0 = 0) {
     const int c = (lane & 7) << 2, rsub = lane >> 3;
     const bool act0 = c < dk, act1 = c + 2 < dk;
     const bool has_img = img.hi != nullptr;
@@ -76,7 +76,7 @@ __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk
     const long long ch0 = has_img ? (long long)(ga >> 3) * img.chunk_stride + (col0 & 7) * 2 : 0;
     const long long ch1 = has_img ? (long long)(gb >> 3) * img.chunk_stride + (col1 & 7) * 2 : 0;
 #pragma unroll 1
-    for (int l = rsub; l < L; l += 4) {
+    for (int l = l0 + rsub; l < L; l += 4) {   // rows [l0, L)
         if (!act0) continue;
         float4 v = *reinterpret_cast<const float4*>(slot + l * RS + c);
         if (smask) {

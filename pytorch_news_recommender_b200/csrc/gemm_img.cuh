@@ -158,9 +158,10 @@ struct IgArgs {
     const float* seq_vec;       // EPI_POOLADD: [M / seq_len, N] upstream gradient of each sequence
     int seq_len;                // EPI_POOLADD: C[m,n] = acc + row_w[m] * seq_vec[m / seq_len, n]
     uint16_t* Chi;              // EPI_BIAS_SPLIT: head-blocked bf16 planes (hi = bf16(x), lo = bf16(x - hi)),
-                                //   [M / seq_len][3][heads] blocks of 32 rows x 32 columns (attention_hp.cuh)
+                                //   [M / seq_len][3][heads] blocks of hp_rows rows x 32 columns (attention_hp.cuh)
     uint16_t* Clo;
     int hp_D, hp_dk;            // EPI_BIAS_SPLIT: bias index of output column n = hp_unpad(n, hp_D, hp_dk)
+    int hp_rows;                // EPI_BIAS_SPLIT: rows per head block (32, or 64 for sequences of 33..64 tokens)
     int M, N;                   // valid output rows / columns
     int m_tiles, n_tiles;       // work grid (tiles of 128 rows x N_T columns)
     int k_chunks;               // 64-deep k chunks in total
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                         const int which = jb / nh, head = jb - which * nh;
                         const long long sq = m / a.seq_len;
                         const int l = m - (int)sq * a.seq_len;
-                        const long long off = (((sq * 3 + which) * nh + head) * 32 + l) * 32;
+                        const long long off = (((sq * 3 + which) * nh + head) * a.hp_rows + l) * 32;
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
