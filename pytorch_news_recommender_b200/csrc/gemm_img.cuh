@@ -77,17 +77,18 @@ __host__ __device__ __forceinline__ long long img_unit_off(long long chunk_strid
     const int chunk = g >> 3, u = g & 7, r7 = (int)(r & 7);
     return (long long)chunk * chunk_stride + (r >> 3) * 1024 + r7 * 128 + ((u ^ r7) << 4);
 }
+// (x, y) -> packed bf16 pairs: hi = {bf16(x) low half, bf16(y) high half}, lo = the same of the
+// residuals x - hi, y - hi (round to nearest even both times): 6 instructions per pair
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(y), "f"(x));
+    const float hx = __uint_as_float(hi << 16), hy = __uint_as_float(hi & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(y - hy), "f"(x - hx));
+}
 // split 8 floats and store them as one 16-byte unit into both planes
 __device__ __forceinline__ void img_store8(const Img& im, long long r, int g, const float* x) {
     uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        tc::split_bf16(x[2 * j], h0, l0);
-        tc::split_bf16(x[2 * j + 1], h1, l1);
-        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
+    for (int j = 0; j < 4; ++j) split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
     const long long off = img_unit_off(im.chunk_stride, r, g);
     *reinterpret_cast<uint4*>(im.hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -387,6 +388,20 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
             float* cbase = a.C + (EPI == EPI_PARTIAL ? (long long)split * a.c_split_stride : 0ll);
             float* crow = cbase + (long long)m * a.ldc + n0;
             float* s_x = s_epi + 2 * 256 + (warp - 2) * (IG_XPOSE_BYTES / 4);
+            // EPI_BIAS_SPLIT: element offset of the four block rows this lane stores (row 8i + lane/4 of the
+            // warp's 32), without the head part: ((seq * 3 * heads) * rows_per_block + l) * 32; -1 past M
+            long long split_row_off[4] = {-1, -1, -1, -1};
+            if (EPI == EPI_BIAS_SPLIT) {
+                const int nh = a.hp_D / a.hp_dk;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int mm = m_tile * 128 + q * 32 + 8 * i + (lane >> 2);
+                    if (mm < a.M) {
+                        const int sq = mm / a.seq_len, l = mm - sq * a.seq_len;
+                        split_row_off[i] = ((long long)sq * 3 * nh * a.hp_rows + l) * 32;
+                    }
+                }
+            }
             tc::mbar_wait(accf_bar(buf), use & 1u);
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(buf * ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
@@ -402,28 +417,39 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
                 tc::tmem_ld32(t_row + (uint32_t)cb, v);
                 if (EPI == EPI_BIAS_SPLIT) {
                     // TMEM gives a lane one output row; 32 columns = one head of the head-padded order, i.e.
-                    // one contiguous 64-byte row of a head block per plane: the warp writes 32 consecutive
-                    // rows = 2 KB contiguous per plane, straight from registers
-                    const int jb = (n0 + cb) >> 5, nh = a.hp_D / a.hp_dk;
-                    if (n0 + cb < a.N && row_ok) {
-                        const int which = jb / nh, head = jb - which * nh;
-                        const long long sq = m / a.seq_len;
-                        const int l = m - (int)sq * a.seq_len;
-                        const long long off = (((sq * 3 + which) * nh + head) * a.hp_rows + l) * 32;
+                    // one 64-byte row of a head block per plane.  The rows go through the warp's staging
+                    // buffer so that a store instruction writes 8 consecutive block rows = 512 contiguous
+                    // bytes (a direct store would touch 32 rows x 16 bytes: measured, the epilogue then
+                    // costs more than the main loop)
+                    if (n0 + cb < a.N) {
+                        uint8_t* sb = reinterpret_cast<uint8_t*>(s_x);
                         uint32_t hi[16], lo[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            tc::split_bf16(v[2 * j] + s_bias[cb + 2 * j], h0, l0);
-                            tc::split_bf16(v[2 * j + 1] + s_bias[cb + 2 * j + 1], h1, l1);
-                            hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                            lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + 4 * j);
+                            split2(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, hi[2 * j], lo[2 * j]);
+                            split2(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w, hi[2 * j + 1], lo[2 * j + 1]);
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            *reinterpret_cast<uint4*>(a.Chi + off + 8 * j) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            *reinterpret_cast<uint4*>(a.Clo + off + 8 * j) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            *reinterpret_cast<uint4*>(sb + lane * (IG_XPOSE_STRIDE * 4) + 16 * j) =
+                                make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            *reinterpret_cast<uint4*>(sb + lane * (IG_XPOSE_STRIDE * 4) + 64 + 16 * j) =
+                                make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                         }
+                        __syncwarp();
+                        const long long jpart = (long long)((n0 + cb) >> 5) * a.hp_rows * 32 + (lane & 3) * 8;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            if (split_row_off[i] >= 0) {
+                                const int rr = 8 * i + (lane >> 2);
+                                const uint4 h4 = *reinterpret_cast<const uint4*>(sb + rr * (IG_XPOSE_STRIDE * 4) + 16 * (lane & 3));
+                                const uint4 l4 = *reinterpret_cast<const uint4*>(sb + rr * (IG_XPOSE_STRIDE * 4) + 64 + 16 * (lane & 3));
+                                *reinterpret_cast<uint4*>(a.Chi + split_row_off[i] + jpart) = h4;
+                                *reinterpret_cast<uint4*>(a.Clo + split_row_off[i] + jpart) = l4;
+                            }
+                        }
+                        __syncwarp();
                     }
                     continue;
                 }

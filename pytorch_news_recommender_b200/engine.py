@@ -273,8 +273,14 @@ class FusedTrainer:
                                                      ops.scratch_bytes(user_shape, gm)), dev)
         table = self.table.data
         # counting sort of the step's token ids (only needs the ids: off the backward's critical path)
+        # (five small latency-bound launches: they run on a side stream underneath the forward)
         plan = self.blobs.get("plan", ops.embedding_plan_bytes(n_titles * T, V), dev)
-        ops.embedding_plan(b["ids"], V, plan)
+        main = torch.cuda.current_stream(dev)
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=dev)
+        self._side.wait_stream(main)          # the ids are on the device; last step's use of the plan is over
+        with torch.cuda.stream(self._side):
+            ops.embedding_plan(b["ids"], V, plan)
         # ---- forward ----------------------------------------------------------------------
         ops.news_encoder_fwd(news_shape, b["ids"], table, news_flat, news_saved, p, seed, gm,
                              out=b["news_vec"])
@@ -295,6 +301,7 @@ class FusedTrainer:
         nb = (news_shape, b["ids"], table, news_flat, b["d_news_vec"], news_saved, news_scratch,
               self.flat_grad[:self.n_enc], b["d_rows"], p, seed, gm)
         ops.news_encoder_bwd(*nb, phase=ops.BWD_DATA)
+        main.wait_stream(self._side)
         ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
         # ---- gradient exchange (data parallel): SUM-allreduce, gradients already carry 1/B_global
         pending = self.exchange.allreduce([self.table_grad], async_op=True)
