@@ -674,7 +674,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
             w.c_split_stride = (long long)Q * (D + 4);
             NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_additive")));
-            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)Q * (D + 1), 256), 256, 0, s>>>(
+            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)Q * (D / 4 + 1), 128), 128, 0, s>>>(
                 sc.wpart, w.splits, Q, D + 4, D, gv.Wa, gv.ba, 0, 0));
             NRMS_CHECK_CUDA(cudaGetLastError());
         } else {
@@ -704,7 +704,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             w.splits = wgrad_splits_tc(w.m_tiles, w.k_chunks);
             w.c_split_stride = (long long)nq * (D + 4);
             NRMS_CHECK_CUDA((ig::ig_launch<true, true, 320, ig::EPI_PARTIAL>(w, s, "gemm_wgrad_qkv")));
-            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)nq * (D + 1), 256), 256, 0, s>>>(
+            NRMS_LAUNCH("reduce_wgrad", s, reduce_wgrad_kernel<<<grid_for((long long)nq * (D / 4 + 1), 128), 128, 0, s>>>(
                 sc.wpart, w.splits, nq, D + 4, D, gv.Wqkv, gv.bqkv, hp ? D : 0, hp ? dk : 0));
             NRMS_CHECK_CUDA(cudaGetLastError());
         } else {

@@ -259,7 +259,9 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
             uint32_t it = 0;
             for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
                 const int tile = w % (a.m_tiles * a.n_tiles), split = w / (a.m_tiles * a.n_tiles);
-                const int m_tile = tile / a.n_tiles, n_tile = tile % a.n_tiles;
+                // K-major-A GEMMs walk the token tiles from the LAST one down: the producer kernel wrote the
+                // activation image in increasing row order, so its tail is what is still in the 126 MB L2
+                const int m_tile = A_MN ? tile / a.n_tiles : a.m_tiles - 1 - tile / a.n_tiles, n_tile = tile % a.n_tiles;
                 const int c0 = split * cps, c1 = min(a.k_chunks, c0 + cps);
                 for (int kc = c0; kc < c1; ++kc, ++it) {
                     const int s = it % STAGES;
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
         uint32_t tile_it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
             const int tile = w % (a.m_tiles * a.n_tiles), split = w / (a.m_tiles * a.n_tiles);
-            const int m_tile = tile / a.n_tiles, n_tile = tile % a.n_tiles;
+            const int m_tile = A_MN ? tile / a.n_tiles : a.m_tiles - 1 - tile / a.n_tiles, n_tile = tile % a.n_tiles;
             const int n0 = n_tile * N_T;
             const int buf = DOUBLE_ACC ? (int)(tile_it & 1u) : 0;
             const uint32_t use = DOUBLE_ACC ? (tile_it >> 1) : tile_it;

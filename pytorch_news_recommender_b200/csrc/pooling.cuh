@@ -218,23 +218,31 @@ __global__ void reduce_rows_kernel(const float* __restrict__ in, float* __restri
 // hp_dk > 0: partial row r is row ig::hp_unpad(r, hp_D, hp_dk) of dW / db (padding rows skipped).
 __global__ void reduce_wgrad_kernel(const float* __restrict__ part, int splits, int rows, int ldp, int cols,
                                     float* __restrict__ dW, float* __restrict__ db, int hp_D, int hp_dk) {
-    const long long per = (long long)rows * ldp;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * (cols + 1);
+    // a thread owns 4 consecutive columns of a row (ldp and cols are multiples of 4: 16-byte loads,
+    // four independent sums, two splits in flight) — the walk over the splits is latency-bound
+    const long long per4 = (long long)rows * ldp / 4;
+    const int q4 = cols / 4 + 1;                        // float4 units per row: cols/4 of dW, then {db, pad}
+    const float4* part4 = reinterpret_cast<const float4*>(part);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)rows * q4;
          i += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(i / (cols + 1)), c = (int)(i - (long long)r * (cols + 1));
+        const int r = (int)(i / q4), c4 = (int)(i - (long long)r * q4);
         const int ro = hp_dk > 0 ? ig::hp_unpad(r, hp_D, hp_dk) : r;
         if (ro < 0) continue;
-        const float* p = part + (long long)r * ldp + c;
-        float s0 = 0.f, s1 = 0.f;
+        const float4* p = part4 + ((long long)r * ldp) / 4 + c4;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
         int s = 0;
         for (; s + 1 < splits; s += 2) {
-            s0 += p[s * per];
-            s1 += p[(s + 1) * per];
+            const float4 x = __ldg(p + s * per4), y = __ldg(p + (s + 1) * per4);
+            s0.x += x.x; s0.y += x.y; s0.z += x.z; s0.w += x.w;
+            s1.x += y.x; s1.y += y.y; s1.z += y.z; s1.w += y.w;
         }
-        if (s < splits) s0 += p[s * per];
-        const float v = s0 + s1;
-        if (c < cols) dW[(long long)ro * cols + c] = v;
-        else db[ro] = v;
+        if (s < splits) {
+            const float4 x = __ldg(p + s * per4);
+            s0.x += x.x; s0.y += x.y; s0.z += x.z; s0.w += x.w;
+        }
+        const float4 v = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+        if (4 * c4 < cols) *reinterpret_cast<float4*>(dW + (long long)ro * cols + 4 * c4) = v;
+        else db[ro] = v.x;
     }
 }
 
