@@ -349,8 +349,8 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         if (tcm) g.x_img = sv.x_img;
         g.mask = sv.xmask; g.mask_bytes = mb;
         g.drop = news ? drop : make_dropout(0.f, 0);
-        const long long rows = tcm ? sv.x_img.rows_pad : M;
-        NRMS_LAUNCH("gather", s, gather_rows_img_kernel<<<grid_for(rows * 32, 256, 16), 256, 0, s>>>(g));
+        const long long items = tcm ? (long long)sv.x_img.rows_pad * sv.x_img.chunks * 8 : (long long)M * ceil_div(D, 8);
+        NRMS_LAUNCH("gather", s, gather_rows_img_kernel<<<grid_for(items, 256, 16), 256, 0, s>>>(g));
         NRMS_CHECK_CUDA(cudaGetLastError());
         x_f32 = sv.x_f32;
     }

@@ -1,8 +1,9 @@
 // gather.cuh — word-embedding gather + embedding dropout (NewsEncoder.forward nrms_v0.py:166:
 // `F.dropout(self.word_embedding(news))`), producing the operand formats of the projections.
 //
-// HBM-bound: one warp per token row; a lane owns 8 consecutive columns (two coalesced float4
-// reads of the table row, one Philox call for its 8 dropout decisions) and writes
+// HBM-bound: a thread owns 8 consecutive columns of a token row (two float4 reads of the table
+// row, one Philox call for its 8 dropout decisions; consecutive lanes take consecutive groups, so
+// reads and writes of a row are coalesced) and writes
 //   * the split-bf16 image unit (16 B to each plane; a row of a chunk is one 128-byte line),
 //   * optionally the fp32 row (exact-fp32 GEMM mode),
 //   * the 8 keep bits (1 byte) for the backward.
@@ -27,52 +28,53 @@ struct GatherArgs {
     Dropout drop;         // stream kDropEmbedding
 };
 
+// Work items are (row, 8-column group) pairs, flattened: with D = 300 a row has 40 groups (5 image
+// chunks), so a warp that walked one row at a time would run a second, quarter-full pass per row;
+// flattened, four rows are exactly five full passes.
 __global__ void __launch_bounds__(256) gather_rows_img_kernel(const GatherArgs a) {
-    const int lane = threadIdx.x & 31;
-    const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const bool img = a.x_img.hi != nullptr;
     const long long rows = img ? a.x_img.rows_pad : a.M;
     const int groups = img ? a.x_img.chunks * 8 : ceil_div(a.D, 8);
-    for (long long m = warp_g; m < rows; m += nwarps) {
+    const long long total = rows * groups;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+        const long long m = it / groups;
+        const int g = (int)(it - m * groups);
         if (m >= a.M) {   // image pad rows: zero (they enter the weight-gradient reduction)
-            for (int g = lane; g < groups; g += 32) ig::img_store8_zero(a.x_img, m, g);
+            ig::img_store8_zero(a.x_img, m, g);
             continue;
         }
         long long src = m;
         bool ok = true;
         if (a.ids) {
-            src = a.ids[m];
+            src = __ldg(a.ids + m);
             ok = src >= 0 && src < a.vocab;
         }
         const float* row = a.table + src * a.D;
-        for (int g = lane; g < groups; g += 32) {
-            const int c = g * 8;
-            float x[8];
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (ok && c < a.D) v0 = __ldg(reinterpret_cast<const float4*>(row + c));
-            if (ok && c + 4 < a.D) v1 = __ldg(reinterpret_cast<const float4*>(row + c + 4));
-            x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-            x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-            if (a.drop.enabled() && c < a.D) {
-                const uint32_t keep = a.drop.keep8(kDropEmbedding, (uint64_t)m, (uint32_t)g);
+        const int c = g * 8;
+        float x[8];
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (ok && c < a.D) v0 = __ldg(reinterpret_cast<const float4*>(row + c));
+        if (ok && c + 4 < a.D) v1 = __ldg(reinterpret_cast<const float4*>(row + c + 4));
+        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+        x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+        if (a.drop.enabled() && c < a.D) {
+            const uint32_t keep = a.drop.keep8(kDropEmbedding, (uint64_t)m, (uint32_t)g);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) x[j] = ((keep >> j) & 1u) ? x[j] * a.drop.scale : 0.f;
-                if (a.mask && g < a.mask_bytes) a.mask[m * a.mask_bytes + g] = (uint8_t)keep;
-            }
-            // image column D carries 1.0: the weight-gradient GEMM then yields the bias gradient as
-            // its column D (sum_t dY[t,j] * 1); the forward GEMM's weight image is zero there
-            if (img && c <= a.D && a.D < c + 8) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c + j == a.D) x[j] = 1.f;
-            }
-            if (a.x_f32) {
-                if (c < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c) = make_float4(x[0], x[1], x[2], x[3]);
-                if (c + 4 < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            }
-            if (img) ig::img_store8(a.x_img, m, g, x);
+            for (int j = 0; j < 8; ++j) x[j] = ((keep >> j) & 1u) ? x[j] * a.drop.scale : 0.f;
+            if (a.mask && g < a.mask_bytes) a.mask[m * a.mask_bytes + g] = (uint8_t)keep;
         }
+        // image column D carries 1.0: the weight-gradient GEMM then yields the bias gradient as
+        // its column D (sum_t dY[t,j] * 1); the forward GEMM's weight image is zero there
+        if (img && c <= a.D && a.D < c + 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (c + j == a.D) x[j] = 1.f;
+        }
+        if (a.x_f32) {
+            if (c < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c) = make_float4(x[0], x[1], x[2], x[3]);
+            if (c + 4 < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c + 4) = make_float4(x[4], x[5], x[6], x[7]);
+        }
+        if (img) ig::img_store8(a.x_img, m, g, x);
     }
 }
 
