@@ -171,7 +171,11 @@ struct IgArgs {
     int terms;                  // 3 = bf16x3 (fp32-grade), 1 = plain bf16 (hi planes only)
 };
 
-constexpr int IG_THREADS = 192;
+// loader warp + MMA warp + epilogue warps.  The 320-column variants have a single TMEM accumulator
+// (2 x 320 > 512 columns), so their epilogue is NOT hidden behind the next tile's main loop: they
+// run EIGHT epilogue warps, two per TMEM lane quadrant, each pair splitting the tile's columns.
+__host__ __device__ constexpr int ig_epi_warps(int n_t) { return n_t > 256 ? 8 : 4; }
+__host__ __device__ constexpr int ig_threads(int n_t) { return 64 + 32 * ig_epi_warps(n_t); }
 
 __host__ __device__ constexpr int ig_stage_bytes(int n_t) { return 2 * A_TILE_B + 2 * n_t * IMG_ROW_B; }
 __host__ __device__ constexpr int ig_stages(int n_t) {
@@ -204,7 +208,7 @@ __host__ __device__ constexpr uint32_t make_idesc2(int n, bool a_mn, bool b_mn) 
 }
 
 template <bool A_MN, bool B_MN, int N_T, int EPI>
-__global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) {
+__global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArgs a) {
     constexpr int STAGES = ig_stages(N_T);
     constexpr int STAGE_B = ig_stage_bytes(N_T);
     constexpr int B_PLANE_B = N_T * IMG_ROW_B;
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(accf_bar(b), 1);
-            tc::mbar_init(acce_bar(b), 4);
+            tc::mbar_init(acce_bar(b), ig_epi_warps(N_T));
         }
         tc::fence_barrier_init();
     }
@@ -409,7 +413,11 @@ __global__ void __launch_bounds__(IG_THREADS, 1) ig_gemm_kernel(const IgArgs a) 
             const uint32_t t_row = tmem_base + (uint32_t)(buf * ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
             float dot = 0.f;
 #pragma unroll 1
-            for (int cb = 0; cb < N_T; cb += 32) {
+            // (eight epilogue warps: warps 6..9 take the upper half of the columns)
+            constexpr int CB_SPAN = ig_epi_warps(N_T) == 8 ? N_T / 2 : N_T;
+            static_assert(ig_epi_warps(N_T) == 4 || CB_SPAN % 32 == 0, "column halves in 32-column blocks");
+            const int cb0 = ig_epi_warps(N_T) == 8 ? ((warp - 2) >> 2) * CB_SPAN : 0;
+            for (int cb = cb0; cb < cb0 + CB_SPAN; cb += 32) {
                 // keep bits of this row's 32 columns [n0 + cb, +32): one word (n0 and cb are multiples of 32),
                 // requested before the TMEM read so that its latency hides behind it
                 uint32_t mword = 0xffffffffu;
@@ -545,7 +553,7 @@ inline cudaError_t ig_launch(const IgArgs& a, cudaStream_t s, const char* name) 
     }
     const int total = a.m_tiles * a.n_tiles * a.splits;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    NRMS_LAUNCH(name, s, (ig_gemm_kernel<A_MN, B_MN, N_T, EPI><<<grid, IG_THREADS, smem, s>>>(a)));
+    NRMS_LAUNCH(name, s, (ig_gemm_kernel<A_MN, B_MN, N_T, EPI><<<grid, ig_threads(N_T), smem, s>>>(a)));
     return cudaGetLastError();
 }
 
