@@ -262,7 +262,11 @@ def main():
                     help="1 = tcgen05 split-bf16 GEMMs (default), 0 = exact-fp32 CUDA-core GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--zipf", action="store_true", help="Zipf(1.0) token distribution instead of uniform")
+    ap.add_argument("--batch-per-gpu", type=int, default=None,
+                    help="other BASELINE configs (not the default bench line): e.g. 512 with --gemm-mode 2 = cfg3's per-GPU shape")
     args = ap.parse_args()
+    if args.batch_per_gpu:
+        WORKLOAD["batch_per_gpu"] = args.batch_per_gpu
     if args.impl == "reference":
         run_reference(args)
         return
@@ -419,9 +423,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg2: NRMS train step (fwd + CE + bwd + dense Adam), fp32, batch 64 per GPU, "
-                                   "T=30 H=50 K=4 D=300 heads=10 Q=200 V=70k, dropout 0.2",
+            "dtype": "bf16" if args.gemm_mode == 2 else "f32", "data": "synthetic",
+            "config": {"workload": ("cfg2" if B == 64 and args.gemm_mode != 2 else "cfg3-shape" if B == 512 else "custom") +
+                                   ": NRMS train step (fwd + CE + bwd + dense Adam), " +
+                                   ("bf16 tensor-core products" if args.gemm_mode == 2 else "fp32") +
+                                   f", batch {B} per GPU, T=30 H=50 K=4 D=300 heads=10 Q=200 V=70k, dropout 0.2",
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "gemm_mode": args.gemm_mode, "tokens": "zipf" if args.zipf else "uniform",
                        "l2": "per-step working set (~1.5 GB activations + 607 MB Adam state) exceeds the 126 MB L2; "
