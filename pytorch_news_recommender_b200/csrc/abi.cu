@@ -393,6 +393,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         a.drop = news ? drop : make_dropout(0.f, 0);
         if (hp) {
             // one independent warp per (sequence, head) over the head-padded planes (attention_hp.cuh)
+            a.ctx = nullptr;    // the context lives in its image only: the pooling kernels read hi + lo
             a.qkv = nullptr;
             a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
             a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
@@ -477,10 +478,13 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     // 5. softmax over the sequence + weighted sum (nrms_v0.py:110-126)
     {
         PoolArgs p{};
-        p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.out = out;
+        p.ctx = hp ? nullptr : sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.out = out;
+        if (hp) p.ctx_img = sv.ctx_img;
         p.score = tcm ? sv.score : nullptr;
         p.M = M; p.L = L; p.D = D; p.Q = Q;
-        NRMS_LAUNCH("pool_fwd", s, pool_fwd_kernel<<<d.n_seq, 256, L * sizeof(float), s>>>(p));
+        const int pu = ceil_div(D, 8);
+        const size_t pool_smem = (L + (hp ? 8 * pu * (256 / pu) : 0)) * sizeof(float);
+        NRMS_LAUNCH("pool_fwd", s, pool_fwd_kernel<<<d.n_seq, 256, pool_smem, s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     return NRMS_OK;
@@ -521,7 +525,8 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         // 1. pooling backward: d_ctx (pool path), d_pre, partials of d_b_a and d_query
         {
             PoolArgs p{};
-            p.ctx = sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.d_out = d_out;
+            p.ctx = hp ? nullptr : sv.ctx; p.t = sv.t; p.q = pv.qv; p.w = sv.w; p.d_out = d_out;
+            if (hp) p.ctx_img = sv.ctx_img;
             p.d_part = sc.part_q;
             if (tcm) p.d_pre_img = sc.d_pre_img; else { p.d_pre = sc.d_pre; p.d_ctx = sc.d_ctx; }
             p.M = M; p.L = L; p.D = D; p.Q = Q;

@@ -10,7 +10,8 @@
 namespace nrms {
 
 struct PoolArgs {
-    const float* ctx;    // [M, D]
+    const float* ctx;    // [M, D], or nullptr: read the context from its split-bf16 image instead
+    ig::Img ctx_img;     //   (x = hi + lo, 2^-17 relative: the values the projection GEMM sees)
     const float* t;      // [M, Q]
     const float* q;      // [Q]
     const float* score;  // [M] a_l = t_l . q when the projection GEMM's epilogue already made it, else nullptr
@@ -26,7 +27,20 @@ struct PoolArgs {
     int L, D, Q;
 };
 
-// one CTA per sequence; dynamic smem: L floats
+// columns [8u, 8u+8) of row r of a split-bf16 image as fp32 (hi + lo)
+__device__ __forceinline__ void img_load8(const ig::Img& im, long long r, int u, float* x) {
+    const long long off = ig::img_unit_off(im.chunk_stride, r, u);
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(im.hi + off));
+    const uint4 l = __ldg(reinterpret_cast<const uint4*>(im.lo + off));
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        x[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+        x[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+    }
+}
+
+// one CTA per sequence; dynamic smem: L floats (+ 8 * ceil(D/8) * (256 / ceil(D/8)) with an image context)
 __global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolArgs p) {
     extern __shared__ float sw[];
     const int seq = blockIdx.x, L = p.L, D = p.D, Q = p.Q;
@@ -63,6 +77,31 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(const PoolArgs p) {
         }
     }
     __syncthreads();
+    if (p.ctx == nullptr) {
+        // image context: a thread owns one 8-column unit for every `slices`-th row, then the slices are summed
+        const int units = ceil_div(D, 8), slices = blockDim.x / units;
+        float* part = sw + L;                              // [slices][units * 8]
+        const int u = threadIdx.x % units, sl = threadIdx.x / units;
+        if (sl < slices) {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int l = sl; l < L; l += slices) {
+                float x[8];
+                img_load8(p.ctx_img, row0 + l, u, x);
+                const float wl = sw[l];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(wl, x[j], acc[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[(sl * units + u) * 8 + j] = acc[j];
+        }
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float acc = 0.f;
+            for (int s2 = 0; s2 < slices; ++s2) acc += part[s2 * units * 8 + d];
+            p.out[(long long)seq * D + d] = acc;
+        }
+        return;
+    }
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         float acc0 = 0.f, acc1 = 0.f;
         int l = 0;
@@ -87,9 +126,19 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
     const float* go = p.d_out + (long long)seq * D;
     // dw_l = d_out . ctx_l
     for (int l = warp; l < L; l += nw) {
-        const float* cr = p.ctx + (row0 + l) * D;
         float s = 0.f;
-        for (int d = lane; d < D; d += 32) s = fmaf(__ldg(go + d), __ldg(cr + d), s);
+        if (p.ctx == nullptr) {
+            for (int u = lane; 8 * u < D; u += 32) {       // image context: a lane owns 8-column units
+                float x[8];
+                img_load8(p.ctx_img, row0 + l, u, x);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (8 * u + j < D) s = fmaf(__ldg(go + 8 * u + j), x[j], s);
+            }
+        } else {
+            const float* cr = p.ctx + (row0 + l) * D;
+            for (int d = lane; d < D; d += 32) s = fmaf(__ldg(go + d), __ldg(cr + d), s);
+        }
         s = warp_sum(s);
         if (lane == 0) {
             sda[l] = s;
