@@ -240,9 +240,9 @@ def kernel_work(name, B):
         "gemm_dgrad_additive": ("tensor", 2.0 * M * Qd * D),
         "gemm_wgrad_qkv": ("tensor", 2.0 * M * 3 * D * D),
         "gemm_wgrad_additive": ("tensor", 2.0 * M * Qd * D),
-        # bytes per token row: fwd reads Q|K|V (3D fp32), writes the context as fp32 + split-bf16
-        # image (2D x 4 B); bwd reads Q|K|V + d_ctx (4D), writes the dQ|dK|dV image (3D x 4 B)
-        "attn_fwd": ("hbm", 4.0 * M * (3 * D + 2 * D)),
+        # bytes per token row (4 B per element: fp32, or a split-bf16 hi + lo pair): fwd reads Q|K|V
+        # (3D), writes the context image (D); bwd reads Q|K|V + d_ctx (4D), writes the dQ|dK|dV image (3D)
+        "attn_fwd": ("hbm", 4.0 * M * (3 * D + D)),
         "attn_bwd": ("hbm", 4.0 * M * (4 * D + 3 * D)),
         "adam": ("hbm", 7.0 * 4 * (V * D + 662600)),
         "pool_fwd": ("hbm", 4.0 * M * (D + Qd)),
