@@ -12,7 +12,7 @@ python scripts/prof_step.py > gpurun_out/plain_step.log 2>&1 || { tail -5 gpurun
 # all three steps of prof_step.py (scripts/ncu_traffic.py divides by 3)
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     -c 600 --csv --log-file gpurun_out/step_metrics.csv python scripts/prof_step.py > gpurun_out/ncu_step.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip 2 --launch-count 1 -o gpurun_out/prof_top -f \
+ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip 3 --launch-count 1 -o gpurun_out/prof_top -f \
     python scripts/prof_step.py > gpurun_out/ncu_top.log 2>&1
 ncu -i gpurun_out/prof_top.ncu-rep --page raw --csv > gpurun_out/prof_top_raw.csv
 ncu -i gpurun_out/prof_top.ncu-rep --page source --csv > gpurun_out/prof_top_src.csv
