@@ -264,9 +264,15 @@ def main():
     ap.add_argument("--zipf", action="store_true", help="Zipf(1.0) token distribution instead of uniform")
     ap.add_argument("--batch-per-gpu", type=int, default=None,
                     help="other BASELINE configs (not the default bench line): e.g. 512 with --gemm-mode 2 = cfg3's per-GPU shape")
+    ap.add_argument("--title-len", type=int, default=None, help="with --history-len / --negatives: cfg5 is 48 / 200 / 8")
+    ap.add_argument("--history-len", type=int, default=None)
+    ap.add_argument("--negatives", type=int, default=None)
     args = ap.parse_args()
     if args.batch_per_gpu:
         WORKLOAD["batch_per_gpu"] = args.batch_per_gpu
+    for key, val in (("n_words_title", args.title_len), ("history_len", args.history_len), ("n_neg", args.negatives)):
+        if val:
+            WORKLOAD[key] = val
     if args.impl == "reference":
         run_reference(args)
         return
@@ -424,10 +430,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.gemm_mode == 2 else "f32", "data": "synthetic",
-            "config": {"workload": ("cfg2" if B == 64 and args.gemm_mode != 2 else "cfg3-shape" if B == 512 else "custom") +
+            "config": {"workload": ("cfg2" if (B, WORKLOAD["n_words_title"], WORKLOAD["history_len"], WORKLOAD["n_neg"], args.gemm_mode != 2)
+                                    == (64, 30, 50, 4, True) else "cfg3-shape" if B == 512 else "custom") +
                                    ": NRMS train step (fwd + CE + bwd + dense Adam), " +
                                    ("bf16 tensor-core products" if args.gemm_mode == 2 else "fp32") +
-                                   f", batch {B} per GPU, T=30 H=50 K=4 D=300 heads=10 Q=200 V=70k, dropout 0.2",
+                                   f", batch {B} per GPU, T={WORKLOAD['n_words_title']} H={WORKLOAD['history_len']} "
+                                   f"K={WORKLOAD['n_neg']} D=300 heads=10 Q=200 V=70k, dropout 0.2",
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "gemm_mode": args.gemm_mode, "tokens": "zipf" if args.zipf else "uniform",
                        "l2": "per-step working set (~1.5 GB activations + 607 MB Adam state) exceeds the 126 MB L2; "
