@@ -214,6 +214,53 @@ def test_train_step_is_bitwise_repeatable(name, gemm_mode, built_lib):
             assert torch.equal(v, ref[1][k]), f"run {rep}: {k} differs by {(v - ref[1][k]).abs().max().item()}"
 
 
+# (T, H, K, D, heads, Q, B): edge shapes of the head-padded attention path — full 32- and 64-row
+# tiles, lengths that straddle the 16-row ownership of a warp, head dim 32 (no padding columns) and
+# 16, batch sizes that leave the last CTA's item slots partly empty, and 12 heads (3*32*12 > 960
+# projection columns: the path must step aside for the fp32-qkv kernels)
+HP_SHAPES = [(32, 64, 2, 64, 2, 12, 3), (17, 33, 1, 120, 4, 8, 5), (31, 47, 3, 300, 10, 200, 2),
+             (5, 16, 1, 96, 6, 16, 7), (20, 50, 2, 288, 12, 40, 2)]
+
+
+@pytest.mark.parametrize("shape", HP_SHAPES)
+def test_hp_attention_edge_shapes_match_oracle(shape, built_lib):
+    """Forward logits, loss and every gradient of the drop-in autograd path against the oracle
+    (itself pinned to the reference) on shapes the golden cases do not cover."""
+    from pytorch_news_recommender_b200 import synthetic as S
+    from pytorch_news_recommender_b200.config import Config
+    from pytorch_news_recommender_b200.model import NRMS_V0
+    T, H, K, D, h, Q, B = shape
+    vocab, n_news = 300, 120
+    ocfg = O.OracleConfig(T, H, K, D, h, Q, 0.0, 1e-3)
+    table = S.make_embedding_table(vocab, D, seed=3)
+    pool = S.make_news_pool(n_news, T, vocab, seed=3, min_len=1)
+    batch = S.make_train_batch(pool, B, H, K, seed=3, short_tail=0.3, min_hist=1)
+    sd = O.init_state_dict(ocfg, table, seed=42)
+    cfg = Config("NRMS_V0_SHAPES").__nrms__()
+    cfg.n_words_title, cfg.history_len, cfg.sample_size, cfg.dropout = T, H, K, 0.0
+    cfg.word_embed_size, cfg.num_attention_heads, cfg.query_vector_dim, cfg.gemm_mode = D, h, Q, 1
+    tmp = tempfile.mkdtemp()
+    S.save_embedding_npz(os.path.join(tmp, "emb.npz"), table)
+    cfg.data_path, cfg.word_embedding_pretrained, cfg.device = tmp + "/", "emb.npz", torch.device("cuda:0")
+    torch.manual_seed(42)
+    model = NRMS_V0(cfg)
+    model.load_state_dict(sd)
+    model = model.to(cfg.device)
+    model.train()
+    out = model(batch)
+    loss = torch.nn.CrossEntropyLoss()(out, torch.zeros(len(out)).long().to(cfg.device))
+    model.zero_grad()
+    loss.backward()
+    ref_loss, ref_logits, ref_grads = O.loss_and_grads(sd, batch, ocfg, training=False, per_slot=False)
+    real = batch["candidate_mask"].bool()
+    assert _rel_err(out.detach().cpu()[real], ref_logits[real]) < 1e-3
+    assert abs(loss.item() - float(ref_loss)) < 2e-4 * max(1.0, abs(float(ref_loss)))
+    for k, p in model.named_parameters():
+        g = ref_grads[k]
+        dn, gn = float((p.grad.cpu() - g).norm()), float(g.norm())
+        assert dn <= 2e-3 * gn + 1e-6 * np.sqrt(g.numel()), f"{shape} grad {k}: |d|={dn} |g|={gn}"
+
+
 def test_golden_train_losses_with_reference_masks_unavailable_on_device():
     """The reference's dropout masks come from ATen's RNG stream and cannot be reproduced by
     the kernels' Philox counters (SURVEY §7 hard parts): train-mode parity is therefore pinned
