@@ -181,13 +181,13 @@ __host__ __device__ constexpr int ig_stage_bytes(int n_t) { return 2 * A_TILE_B 
 __host__ __device__ constexpr int ig_stages(int n_t) {
     return (227 * 1024 - 1280) / ig_stage_bytes(n_t) >= 4 ? 4 : (227 * 1024 - 1280) / ig_stage_bytes(n_t);
 }
-// tail after the ring: 128 B of mbarriers + TMEM slot, then 2*N_T floats of epilogue staging
+// tail after the ring: 256 B of mbarriers + TMEM slot, then 2*N_T floats of epilogue staging
 // (bias / query vector; only the N_T <= 256 variants stage anything)
 // + (N_T <= 256 only: the 320-column variants have no shared memory left) one 32x36-float
 // transposition buffer per epilogue warp for coalesced stores
 constexpr int IG_XPOSE_STRIDE = 36;
 constexpr int IG_XPOSE_BYTES = 32 * IG_XPOSE_STRIDE * 4;
-__host__ __device__ constexpr int ig_tail_bytes(int n_t) { return n_t <= 256 ? 128 + 2 * 256 * 4 + 4 * IG_XPOSE_BYTES : 256; }
+__host__ __device__ constexpr int ig_tail_bytes(int n_t) { return n_t <= 256 ? 256 + 2 * 256 * 4 + 4 * IG_XPOSE_BYTES : 384; }
 __host__ __device__ constexpr int ig_smem_bytes(int n_t) {
     return ig_stages(n_t) * ig_stage_bytes(n_t) + 1024 /*alignment slack*/ + ig_tail_bytes(n_t);
 }
@@ -224,9 +224,9 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_B);
-    // bars: [0,S) full | [S,2S) empty | [2S,2S+2) acc full | [2S+2,2S+4) acc empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-    float* s_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_B + 128);   // [2][256] floats (N_T <= 256 only)
+    // bars: [0,S) hi planes full | [S,2S) empty | [2S,2S+2) acc full | [2S+2,2S+4) acc empty | [2S+4,3S+4) lo planes full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    float* s_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_B + 256);   // [2][256] floats (N_T <= 256 only)
     constexpr bool XPOSE = N_T <= 256;   // stage the tile through shared memory for full-line stores
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -236,10 +236,12 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
     auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+    auto full_lo_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(full_bar(s), 1);
+            tc::mbar_init(full_lo_bar(s), 1);
             tc::mbar_init(empty_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
@@ -271,32 +273,38 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                     const int s = it % STAGES;
                     tc::mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
                     const uint32_t dst = smem_base + s * STAGE_B;
+                    // The hi planes of a stage signal their own barrier: the Ahi*Bhi products of a k-chunk
+                    // start when HALF of the stage has landed, while its lo planes are still in flight.
                     const bool lo = a.terms == 3;     // plain-bf16 mode streams the hi planes only
-                    tc::mbar_arrive_expect_tx(full_bar(s), lo ? STAGE_B : STAGE_B / 2);
-                    if (A_MN) {
-#pragma unroll
-                        for (int b = 0; b < 2; ++b) {
-                            const long long off = (long long)(m_tile * 2 + b) * a.A.chunk_stride + (long long)kc * IMG_BLOCK_B;
-                            tc::bulk_g2s(dst + b * IMG_BLOCK_B, a.A.hi + off, IMG_BLOCK_B, full_bar(s));
-                            if (lo) tc::bulk_g2s(dst + A_TILE_B + b * IMG_BLOCK_B, a.A.lo + off, IMG_BLOCK_B, full_bar(s));
-                        }
-                    } else {
-                        const long long off = (long long)kc * a.A.chunk_stride + (long long)m_tile * A_TILE_B;
-                        tc::bulk_g2s(dst, a.A.hi + off, A_TILE_B, full_bar(s));
-                        if (lo) tc::bulk_g2s(dst + A_TILE_B, a.A.lo + off, A_TILE_B, full_bar(s));
-                    }
+                    constexpr uint32_t HALF_B = A_TILE_B + B_PLANE_B;
                     const uint32_t dstb = dst + 2 * A_TILE_B;
-                    if (B_MN) {
 #pragma unroll
-                        for (int b = 0; b < N_T / 64; ++b) {
-                            const long long off = (long long)(n_tile * (N_T / 64) + b) * a.B.chunk_stride + (long long)kc * IMG_BLOCK_B;
-                            tc::bulk_g2s(dstb + b * IMG_BLOCK_B, a.B.hi + off, IMG_BLOCK_B, full_bar(s));
-                            if (lo) tc::bulk_g2s(dstb + B_PLANE_B + b * IMG_BLOCK_B, a.B.lo + off, IMG_BLOCK_B, full_bar(s));
+                    for (int pl = 0; pl < 2; ++pl) {
+                        if (pl == 1 && !lo) break;
+                        const uint32_t bar = pl == 0 ? full_bar(s) : full_lo_bar(s);
+                        const uint8_t* Ap = pl == 0 ? a.A.hi : a.A.lo;
+                        const uint8_t* Bp = pl == 0 ? a.B.hi : a.B.lo;
+                        tc::mbar_arrive_expect_tx(bar, HALF_B);
+                        if (A_MN) {
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) {
+                                const long long off = (long long)(m_tile * 2 + b) * a.A.chunk_stride + (long long)kc * IMG_BLOCK_B;
+                                tc::bulk_g2s(dst + pl * A_TILE_B + b * IMG_BLOCK_B, Ap + off, IMG_BLOCK_B, bar);
+                            }
+                        } else {
+                            const long long off = (long long)kc * a.A.chunk_stride + (long long)m_tile * A_TILE_B;
+                            tc::bulk_g2s(dst + pl * A_TILE_B, Ap + off, A_TILE_B, bar);
                         }
-                    } else {
-                        const long long off = (long long)kc * a.B.chunk_stride + (long long)n_tile * B_PLANE_B;
-                        tc::bulk_g2s(dstb, a.B.hi + off, B_PLANE_B, full_bar(s));
-                        if (lo) tc::bulk_g2s(dstb + B_PLANE_B, a.B.lo + off, B_PLANE_B, full_bar(s));
+                        if (B_MN) {
+#pragma unroll
+                            for (int b = 0; b < N_T / 64; ++b) {
+                                const long long off = (long long)(n_tile * (N_T / 64) + b) * a.B.chunk_stride + (long long)kc * IMG_BLOCK_B;
+                                tc::bulk_g2s(dstb + pl * B_PLANE_B + b * IMG_BLOCK_B, Bp + off, IMG_BLOCK_B, bar);
+                            }
+                        } else {
+                            const long long off = (long long)kc * a.B.chunk_stride + (long long)n_tile * B_PLANE_B;
+                            tc::bulk_g2s(dstb + pl * B_PLANE_B, Bp + off, B_PLANE_B, bar);
+                        }
                     }
                 }
             }
@@ -327,22 +335,31 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                     const uint32_t sa = smem_base + s * STAGE_B;
                     const uint32_t sb = sa + 2 * A_TILE_B;
                     const int steps = min(4, a.k_steps - 4 * kc);
+                    // hi x hi of every k-step first (needs the hi planes only) ...
                     for (int j = 0; j < steps; ++j) {
                         const uint64_t a_hi = make_sw128_desc(sa + j * A_ADV, A_LBO);
-                        const uint64_t a_lo = make_sw128_desc(sa + A_TILE_B + j * A_ADV, A_LBO);
                         const uint64_t b_hi = make_sw128_desc(sb + j * B_ADV, B_LBO);
-                        const uint64_t b_lo = make_sw128_desc(sb + B_PLANE_B + j * B_ADV, B_LBO);
                         const uint32_t acc = (kc > c0 || j > 0) ? 1u : 0u;
                         tc::umma_bf16(d_tmem, a_hi, b_hi, idesc1, acc);
-                        if (a.terms == 3) {
-                            tc::umma_bf16(d_tmem, a_lo, b_hi, idesc1, 1u);
-                            tc::umma_bf16(d_tmem, a_hi, b_lo, idesc1, 1u);
-                        }
                         if (N2 > 0) {
                             const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
-                            const uint64_t b2_lo = make_sw128_desc(sb + B_PLANE_B + B2_OFF + j * B_ADV, B_LBO);
                             tc::umma_bf16(d_tmem + N1, a_hi, b2_hi, idesc2, acc);
-                            if (a.terms == 3) {
+                        }
+                    }
+                    // ... then the two cross terms, once the lo planes have landed
+                    if (a.terms == 3) {
+                        tc::mbar_wait(full_lo_bar(s), (it / STAGES) & 1u);
+                        tc::tc_fence_after();
+                        for (int j = 0; j < steps; ++j) {
+                            const uint64_t a_hi = make_sw128_desc(sa + j * A_ADV, A_LBO);
+                            const uint64_t a_lo = make_sw128_desc(sa + A_TILE_B + j * A_ADV, A_LBO);
+                            const uint64_t b_hi = make_sw128_desc(sb + j * B_ADV, B_LBO);
+                            const uint64_t b_lo = make_sw128_desc(sb + B_PLANE_B + j * B_ADV, B_LBO);
+                            tc::umma_bf16(d_tmem, a_lo, b_hi, idesc1, 1u);
+                            tc::umma_bf16(d_tmem, a_hi, b_lo, idesc1, 1u);
+                            if (N2 > 0) {
+                                const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
+                                const uint64_t b2_lo = make_sw128_desc(sb + B_PLANE_B + B2_OFF + j * B_ADV, B_LBO);
                                 tc::umma_bf16(d_tmem + N1, a_lo, b2_hi, idesc2, 1u);
                                 tc::umma_bf16(d_tmem + N1, a_hi, b2_lo, idesc2, 1u);
                             }
@@ -412,11 +429,11 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
             tc::tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t)(buf * ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
             float dot = 0.f;
-#pragma unroll 1
             // (eight epilogue warps: warps 6..9 take the upper half of the columns)
             constexpr int CB_SPAN = ig_epi_warps(N_T) == 8 ? N_T / 2 : N_T;
             static_assert(ig_epi_warps(N_T) == 4 || CB_SPAN % 32 == 0, "column halves in 32-column blocks");
             const int cb0 = ig_epi_warps(N_T) == 8 ? ((warp - 2) >> 2) * CB_SPAN : 0;
+#pragma unroll 1
             for (int cb = cb0; cb < cb0 + CB_SPAN; cb += 32) {
                 // keep bits of this row's 32 columns [n0 + cb, +32): one word (n0 and cb are multiples of 32),
                 // requested before the TMEM read so that its latency hides behind it
