@@ -100,8 +100,7 @@ inline int mask_bytes_for(int D) { return (int)align_up(ceil_div(D, 8), 4); }
 // GEMM modes, sequences of at most 64 tokens, even head dim <= 32, 3*32*h <= 960 projection columns.
 inline bool use_hp(const nrms_encoder_dims& d) {
     const int dk = d.d_model / d.n_heads;
-    return d.gemm_mode >= 1 && d.seq_len <= 64 && dk % 2 == 0 && dk <= 32 && 96 * d.n_heads <= 960 &&
-           getenv("NRMS_NO_HP") == nullptr;
+    return d.gemm_mode >= 1 && d.seq_len <= 64 && dk % 2 == 0 && dk <= 32 && 96 * d.n_heads <= 960;
 }
 inline int hp_cols(const nrms_encoder_dims& d) { return 96 * d.n_heads; }
 inline int hp_rows(const nrms_encoder_dims& d) { return d.seq_len <= 32 ? 32 : 64; }   // rows per head block
@@ -397,7 +396,6 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             a.qkv = nullptr;
             a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
             a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
-            a.np = NP;
             const long long items = (long long)d.n_seq * h;
             if (L > 32) {
                 // four warps per (sequence, head) over 64-row blocks (attention_hpn.cuh)
@@ -575,8 +573,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 a.qkv = nullptr;
                 a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
                 a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
-                a.np = NP;
-                a.cmask = nullptr;   // d_ctx arrives with the context-dropout mask applied (dgrad GEMM epilogue)
+                    a.cmask = nullptr;   // d_ctx arrives with the context-dropout mask applied (dgrad GEMM epilogue)
                 const long long items = (long long)d.n_seq * h;
                 // two (sequences of <= 32 tokens) or four warps per (sequence, head): attention_hpn.cuh
                 if (L > 32) {

@@ -29,9 +29,8 @@ constexpr int kKeyGroup = 6;    // keys per softmax rescale in the forward
 
 struct AttnArgs {
     const float* qkv;    // [M, 3D]
-    const uint16_t* qkv_hi;   // head-padded split-bf16 planes [M, np] (attention_hp.cuh), instead of qkv
+    const uint16_t* qkv_hi;   // head-padded, head-blocked split-bf16 planes (attention_hp.cuh), instead of qkv
     const uint16_t* qkv_lo;
-    int np;              // row stride of the planes in elements: 3 * 32 * n_heads
     float* ctx;          // fwd out / bwd in: post-dropout context [M, D]
     ig::Img ctx_img;     // fwd out (optional): image of the post-dropout context
     uint8_t* cmask;      // fwd out / bwd in (optional): keep bits [M, mask_bytes] (dropout only)
