@@ -339,7 +339,8 @@ def main():
     resident = []
     for b in pinned:
         bufs = trainer.load_batch(b)
-        resident.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in bufs.items()})
+        resident.append({k: (v.clone() if torch.is_tensor(v) else v) for k, v in bufs.items()
+                         if k not in ("ids_slots", "mask_slots", "slot_free", "slot")})
     torch.cuda.synchronize()
 
     def step_resident(i):
@@ -363,6 +364,7 @@ def main():
 
     def step_e2e(i):
         loss = trainer.step(pinned[i % len(pinned)])
+        trainer.prefetch(pinned[(i + 1) % len(pinned)])   # next batch's H2D runs underneath this step
         losses.append(loss.item())          # D2H read of the step's result (train_eval.py:198)
 
     for i in range(3):

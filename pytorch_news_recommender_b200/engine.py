@@ -221,8 +221,11 @@ class FusedTrainer:
             dev, D = self.device, self.table.shape[1]
             n_titles = B * (C + H)
             b = {
-                "ids": torch.empty((n_titles, T), dtype=torch.int64, device=dev),
-                "mask": torch.empty((B, C), dtype=torch.uint8, device=dev),
+                # two input slots: the next batch's H2D copy (prefetch) lands in one while the step in
+                # flight reads the other; "ids" / "mask" name the slot of the current step
+                "ids_slots": [torch.empty((n_titles, T), dtype=torch.int64, device=dev) for _ in range(2)],
+                "mask_slots": [torch.empty((B, C), dtype=torch.uint8, device=dev) for _ in range(2)],
+                "slot_free": [None, None], "slot": 0,
                 "news_vec": torch.empty((n_titles, D), dtype=torch.float32, device=dev),
                 "d_news_vec": torch.empty((n_titles, D), dtype=torch.float32, device=dev),
                 "user_vec": torch.empty((B, D), dtype=torch.float32, device=dev),
@@ -231,21 +234,60 @@ class FusedTrainer:
                 "loss_rows": torch.empty((B,), dtype=torch.float32, device=dev),
                 "d_rows": torch.empty((n_titles * T, D), dtype=torch.float32, device=dev),
             }
+            b["ids"], b["mask"] = b["ids_slots"][0], b["mask_slots"][0]
             self._bufs[key] = b
         return b
 
+    @staticmethod
+    def _copy_in(b, slot, batch, B, C, H, T):
+        ids, mask = b["ids_slots"][slot], b["mask_slots"][slot]
+        ids[:B * C].view(B, C, T).copy_(batch["candidate_titles"], non_blocking=True)
+        ids[B * C:].view(B, H, T).copy_(batch["browsed_titles"], non_blocking=True)
+        mask.copy_(batch["candidate_mask"], non_blocking=True)
+
     def load_batch(self, batch) -> Dict[str, torch.Tensor]:
         """H2D copy of the three tensors the path reads (nrms_v0.py:248-250,272) into the
-        persistent device buffers; candidate titles first, then clicked titles."""
-        ct, bt, cm = batch["candidate_titles"], batch["browsed_titles"], batch["candidate_mask"]
+        persistent device buffers; candidate titles first, then clicked titles.  A batch announced
+        with `prefetch` is already on its way: the step only waits for that copy."""
+        ct, bt = batch["candidate_titles"], batch["browsed_titles"]
         B, C, T = ct.shape
         H = bt.shape[1]
         b = self._buffers(B, C, H, T)
-        b["ids"][:B * C].view(B, C, T).copy_(ct, non_blocking=True)
-        b["ids"][B * C:].view(B, H, T).copy_(bt, non_blocking=True)
-        b["mask"].copy_(cm, non_blocking=True)
+        pf = getattr(self, "_prefetched", None)
+        if pf is not None and pf[0] is ct and pf[1] is b:
+            slot, ready = pf[2], pf[3]
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            self._prefetched = None
+        else:
+            if pf is not None and pf[1] is b:     # an announced batch was dropped: let its copy finish first
+                torch.cuda.current_stream(self.device).wait_event(pf[3])
+                self._prefetched = None
+            slot = b["slot"] ^ 1
+            self._copy_in(b, slot, batch, B, C, H, T)
+        b["slot"] = slot
+        b["ids"], b["mask"] = b["ids_slots"][slot], b["mask_slots"][slot]
         b["dims"] = (B, C, H, T)
         return b
+
+    def prefetch(self, batch) -> None:
+        """Start the H2D copy of the NEXT step's host batch on a copy stream, underneath the step in
+        flight (call it right after `step`).  The batch must stay alive and unchanged (pinned memory
+        for a truly asynchronous copy) until the step that consumes it has been issued."""
+        ct, bt = batch["candidate_titles"], batch["browsed_titles"]
+        B, C, T = ct.shape
+        H = bt.shape[1]
+        b = self._buffers(B, C, H, T)
+        slot = b["slot"] ^ 1                      # the slot the step in flight does not read
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        if b["slot_free"][slot] is not None:
+            cs.wait_event(b["slot_free"][slot])   # its last reader (the step before the one in flight) is done
+        with torch.cuda.stream(cs):
+            self._copy_in(b, slot, batch, B, C, H, T)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        self._prefetched = (ct, b, slot, ready)
 
     def step(self, batch, b_global: Optional[int] = None) -> torch.Tensor:
         """One optimisation step on this rank's shard; returns the mean loss of the shard as
@@ -264,17 +306,24 @@ class FusedTrainer:
         if b_global is None:
             b_global = B * self.world
         n_titles = B * (C + H)
-        news_shape = EncoderShape(n_titles, T, D, h, Q, V)
-        user_shape = EncoderShape(B, H, D, h, Q, 0)
+        # shapes and blob sizes depend only on (batch shape, GEMM mode): looked up once, not per step
+        # (a step that follows a host read-back has this prologue on its critical path)
+        meta = b.get("meta")
+        if meta is None or meta[0] != (B, C, H, T, gm, V):
+            ns, us = EncoderShape(n_titles, T, D, h, Q, V), EncoderShape(B, H, D, h, Q, 0)
+            meta = ((B, C, H, T, gm, V), ns, us, ops.saved_bytes(ns, gm), ops.saved_bytes(us, gm),
+                    max(ops.scratch_bytes(ns, gm), ops.scratch_bytes(us, gm)),
+                    ops.embedding_plan_bytes(n_titles * T, V))
+            b["meta"] = meta
+        _, news_shape, user_shape, news_saved_b, user_saved_b, scratch_b, plan_b = meta
         news_flat, user_flat = self.flat[:self.n_enc], self.flat[self.n_enc:]
-        news_saved = self.blobs.get("news_saved", ops.saved_bytes(news_shape, gm), dev)
-        user_saved = self.blobs.get("user_saved", ops.saved_bytes(user_shape, gm), dev)
-        news_scratch = self.blobs.get("scratch", max(ops.scratch_bytes(news_shape, gm),
-                                                     ops.scratch_bytes(user_shape, gm)), dev)
+        news_saved = self.blobs.get("news_saved", news_saved_b, dev)
+        user_saved = self.blobs.get("user_saved", user_saved_b, dev)
+        news_scratch = self.blobs.get("scratch", scratch_b, dev)
         table = self.table.data
         # counting sort of the step's token ids (only needs the ids: off the backward's critical path)
         # (five small latency-bound launches: they run on a side stream underneath the forward)
-        plan = self.blobs.get("plan", ops.embedding_plan_bytes(n_titles * T, V), dev)
+        plan = self.blobs.get("plan", plan_b, dev)
         main = torch.cuda.current_stream(dev)
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=dev)
@@ -315,6 +364,10 @@ class FusedTrainer:
                       b1, b2, self.eps)
         ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
                       b1, b2, self.eps)
+        if "slot_free" in b:                      # this step's input slot may be overwritten from here on
+            ev = torch.cuda.Event()
+            ev.record(main)
+            b["slot_free"][b["slot"]] = ev
         return b["loss_rows"].mean()
 
     def grads_as_state_dict(self) -> Dict[str, torch.Tensor]:

@@ -261,6 +261,36 @@ def test_hp_attention_edge_shapes_match_oracle(shape, built_lib):
         assert dn <= 2e-3 * gn + 1e-6 * np.sqrt(g.numel()), f"{shape} grad {k}: |d|={dn} |g|={gn}"
 
 
+def test_prefetched_batches_give_identical_steps(built_lib):
+    """`FusedTrainer.prefetch` (next batch's H2D on a copy stream, double-buffered input slots)
+    changes when the copy happens, never what the step computes: bit-identical losses and weights,
+    also when an announced batch is dropped for another one."""
+    from pytorch_news_recommender_b200 import synthetic as S
+    from pytorch_news_recommender_b200.engine import FusedTrainer
+    c = Case("mind")
+    pool = S.make_news_pool(300, c.T, c.vocab, seed=5)
+    batches = [{k: v.pin_memory() for k, v in S.make_train_batch(pool, c.B, c.H, c.C - 1, seed=40 + i).items()}
+               for i in range(5)]
+    results = []
+    for mode in ("plain", "prefetch", "dropped"):
+        model, cfg, _ = _model_from_case(c, gemm_mode=1)
+        cfg.dropout_seed = 9
+        model.train()
+        tr = FusedTrainer(model)
+        losses = []
+        for i, b in enumerate(batches):
+            loss = tr.step(b)
+            if mode != "plain" and i + 1 < len(batches):
+                # "dropped": announce a batch that is then not the next one stepped
+                tr.prefetch(batches[i + 1] if mode == "prefetch" or i % 2 else batches[0])
+            losses.append(loss.item())
+        results.append((losses, {k: v.detach().clone() for k, v in model.state_dict().items()}))
+    for losses, sd in results[1:]:
+        assert losses == results[0][0]
+        for k, v in sd.items():
+            assert torch.equal(v, results[0][1][k]), k
+
+
 def test_golden_train_losses_with_reference_masks_unavailable_on_device():
     """The reference's dropout masks come from ATen's RNG stream and cannot be reproduced by
     the kernels' Philox counters (SURVEY §7 hard parts): train-mode parity is therefore pinned
