@@ -365,7 +365,7 @@ def main():
     def step_e2e(i):
         loss = trainer.step(pinned[i % len(pinned)])
         trainer.prefetch(pinned[(i + 1) % len(pinned)])   # next batch's H2D runs underneath this step
-        losses.append(loss.item())          # D2H read of the step's result (train_eval.py:198)
+        losses.append(trainer.last_loss())  # D2H read of the step's result (train_eval.py:198), every step
 
     for i in range(3):
         step_e2e(i)

@@ -341,6 +341,20 @@ class FusedTrainer:
         d_hist = b["d_news_vec"][B * C:].view(B, H, D)
         ops.score_ce_fwd_bwd(cand_vec, b["user_vec"], b["mask"], b_global, b["logits"],
                              b["loss_rows"], d_cand, b["d_user_vec"])
+        # The loss is final here, half a step before the optimizer is: it starts its way to the host
+        # now, so that `last_loss()` (the `loss.item()` of train_eval.py:198) does not wait for the
+        # backward and Adam — and the host can already enqueue the next step while they run.
+        loss = b["loss_rows"].mean()
+        if getattr(self, "_loss_host", None) is None:
+            self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+            self._loss_event, self._loss_ready = torch.cuda.Event(), torch.cuda.Event()
+            self._loss_stream = torch.cuda.Stream(device=dev)
+        # (on its own stream: a D2H copy in the compute stream would hold back the backward's first kernel)
+        self._loss_ready.record(torch.cuda.current_stream(dev))
+        self._loss_stream.wait_event(self._loss_ready)
+        with torch.cuda.stream(self._loss_stream):
+            self._loss_host.copy_(loss.reshape(1), non_blocking=True)
+            self._loss_event.record(self._loss_stream)
         # ---- backward -----------------------------------------------------------------------
         ops.user_encoder_bwd(user_shape, hist_vec, user_flat, b["d_user_vec"], user_saved,
                              news_scratch, self.flat_grad[self.n_enc:], d_hist, gm)
@@ -368,7 +382,13 @@ class FusedTrainer:
             ev = torch.cuda.Event()
             ev.record(main)
             b["slot_free"][b["slot"]] = ev
-        return b["loss_rows"].mean()
+        return loss
+
+    def last_loss(self) -> float:
+        """The mean loss of the last `step` as a Python float: waits only for the forward + loss of
+        that step (its 4-byte D2H copy), not for its backward and optimizer update."""
+        self._loss_event.synchronize()
+        return float(self._loss_host[0])
 
     def grads_as_state_dict(self) -> Dict[str, torch.Tensor]:
         """Last step's gradients keyed like model.state_dict() (for parity tests)."""

@@ -74,7 +74,7 @@ def train_demo(config, model, train_iter, dev_iter, y_true: Optional[Sequence[Se
                 loss = criterion(outputs, y)
                 loss.backward()
                 optimizer.step()
-            loss_list.append(loss.item())
+            loss_list.append(trainer.last_loss() if fused else loss.item())
             if total_batch % STEP_SIZE == 0:
                 msg = 'Iter: {0:>6},  Train Loss: {1:>5.6},  Time: {2} {3}'
                 log(msg.format(total_batch, np.mean(loss_list), get_time_dif(start_time), improve))
