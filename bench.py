@@ -15,8 +15,10 @@ and gradients are all-reduced over NCCL.
 
 `value`  : device-resident batches (4 distinct batches rotated), CUDA events around exactly K
            steps, barrier + synchronize on both sides, max over ranks.
-`e2e`    : the same step through `FusedTrainer.step(host_batch)`: pinned HOST batch -> H2D
-           inside the timed region, loss read back (D2H) every step.
+`e2e`    : the same step through the public training API with HOST batches: every step
+           `FusedTrainer.step(host_batch)` (pinned host -> device copy of that step's inputs inside
+           the timed region; the NEXT batch's copy is announced with `prefetch` and overlaps the
+           step), and the step's loss read back to the host (`last_loss()`: a 4-byte D2H copy).
 `roofline`: the dominant kernel of the step, timed live with CUDA events on its own stream
            by the library's opt-in profiler in a separate profiled pass of the same steps.
 `cpu_baseline`: the oracle port of the reference step (oracle/nrms_oracle.py, per-slot loops
