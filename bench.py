@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--zipf", action="store_true", help="Zipf(1.0) token distribution instead of uniform")
     ap.add_argument("--batch-per-gpu", type=int, default=None,
                     help="other BASELINE configs (not the default bench line): e.g. 512 with --gemm-mode 2 = cfg3's per-GPU shape")
+    ap.add_argument("--table-sync", default="dense", choices=["dense", "sparse"],
+                    help="exchange of the embedding-table gradient under data parallelism (engine.FusedTrainer)")
     ap.add_argument("--title-len", type=int, default=None, help="with --history-len / --negatives: cfg5 is 48 / 200 / 8")
     ap.add_argument("--history-len", type=int, default=None)
     ap.add_argument("--negatives", type=int, default=None)
@@ -312,7 +314,7 @@ def main():
     torch.manual_seed(42)
     model = NRMS_V0(cfg).to(device)
     model.train()
-    trainer = FusedTrainer(model)
+    trainer = FusedTrainer(model, table_sync=args.table_sync)
     host_batches = make_batches(4, rank, zipf=args.zipf)
     pinned = [{k: v.pin_memory() for k, v in b.items()} for b in host_batches]
     B = WORKLOAD["batch_per_gpu"]

@@ -179,6 +179,8 @@ class FusedTrainer:
         self.pg = process_group
         self.exchange = GradientExchange(process_group)
         self.world = self.exchange.world
+        if table_sync not in ("dense", "sparse"):
+            raise ValueError("table_sync must be 'dense' or 'sparse'")
         self.table_sync = table_sync
         self.step_count = 0
         self.table = model.news_encoder.word_embedding[0].weight
@@ -367,7 +369,11 @@ class FusedTrainer:
         main.wait_stream(self._side)
         ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
         # ---- gradient exchange (data parallel): SUM-allreduce, gradients already carry 1/B_global
-        pending = self.exchange.allreduce([self.table_grad], async_op=True)
+        if self.world > 1 and self.table_sync == "sparse":
+            self._exchange_table_sparse(V, D)
+            pending = []
+        else:
+            pending = self.exchange.allreduce([self.table_grad], async_op=True)
         ops.news_encoder_bwd(*nb, phase=ops.BWD_PARAMS)
         pending += self.exchange.allreduce([self.flat_grad], async_op=True)
         for h_ in pending:
@@ -383,6 +389,26 @@ class FusedTrainer:
             ev.record(main)
             b["slot_free"][b["slot"]] = ev
         return loss
+
+    def _exchange_table_sparse(self, V: int, D: int) -> None:
+        """table_sync="sparse" (SURVEY.md §8e): instead of all-reducing the dense 84 MB table gradient,
+        all-gather only the rows this step touched — (ids, rows) per rank — and rebuild the dense sum
+        locally with the same deduplicating kernels that built the local gradient (counting sort of the
+        gathered ids + segmented reduce, fixed order: identical bits on every rank).  Pays off when
+        the ranks together touch well under V rows (small batches, skewed tokens, many GPUs); with
+        uniform tokens at 64 impressions per GPU a rank already touches ~60 % of the rows and the dense
+        all-reduce moves less.  Reading the row counts synchronises the host once per step."""
+        tg = self.table_grad
+        ids = torch.nonzero(tg.abs().amax(dim=1) > 0).squeeze(1)          # touched rows with a non-zero gradient
+        rows = ops.gather_rows(tg, ids, base=0) if ids.numel() else tg[:0]
+        ids_all, rows_all = self.exchange.allgather_rows(ids, rows)
+        n = ids_all.numel()
+        if n == 0:
+            tg.zero_()
+            return
+        plan = self.blobs.get("plan_sparse", ops.embedding_plan_bytes(n, V), self.device)
+        ops.embedding_plan(ids_all, V, plan)
+        ops.embedding_grad_dense(plan, rows_all, n, V, D, tg)
 
     def last_loss(self) -> float:
         """The mean loss of the last `step` as a Python float: waits only for the forward + loss of

@@ -80,6 +80,28 @@ class GradientExchange:
                 handles.append(h)
         return handles
 
+    def allgather_rows(self, ids: torch.Tensor, rows: torch.Tensor):
+        """The sparse form of the table-gradient exchange: every rank contributes
+        its touched vocabulary rows `ids` [U_r] int64 and their gradient `rows` [U_r, D]; returns
+        (ids_all [G*U_max], rows_all [G*U_max, D]) in rank order, ranks with fewer rows padded
+        with id 0 / zero rows (id 0 is the padding row, whose gradient is dropped anyway).  The
+        row counts differ per rank, so one tiny all-gather of the counts comes first."""
+        if self.world == 1:
+            return ids, rows
+        n = torch.tensor([ids.numel()], dtype=torch.int64, device=ids.device)
+        counts = torch.empty(self.world, dtype=torch.int64, device=ids.device)
+        dist.all_gather_into_tensor(counts, n, group=self.group)
+        u_max = int(counts.max().item())
+        ids_pad = torch.zeros(u_max, dtype=torch.int64, device=ids.device)
+        rows_pad = torch.zeros((u_max, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        ids_pad[:ids.numel()] = ids
+        rows_pad[:rows.shape[0]] = rows
+        ids_all = torch.empty(self.world * u_max, dtype=torch.int64, device=ids.device)
+        rows_all = torch.empty((self.world * u_max, rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        dist.all_gather_into_tensor(ids_all, ids_pad, group=self.group)
+        dist.all_gather_into_tensor(rows_all, rows_pad, group=self.group)
+        return ids_all, rows_all
+
     def max_over_ranks(self, value: float, device) -> float:
         """Timing helper: the slowest rank defines the step time."""
         if self.world == 1:

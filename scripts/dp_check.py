@@ -43,7 +43,7 @@ def main():
     batches = [S.make_train_batch(pool, B, 50, 4, seed=10 + i) for i in range(steps)]
     cfg, model = build(dev, tmp, vocab)
     model.train()
-    tr = FusedTrainer(model)
+    tr = FusedTrainer(model, table_sync=os.environ.get("TABLE_SYNC", "dense"))
     # gradients of the FIRST step (before Adam's sign-like update amplifies rounding differences of
     # mathematically-zero gradients such as the W_K bias), then the remaining steps for the weights
     tr.step(parallel.shard_batch(batches[0], rank, world), b_global=B)
@@ -79,6 +79,7 @@ def main():
                 ok = False
                 print("PARAM MISMATCH", k, d, file=sys.stderr)
         print(json.dumps({"check": "data_parallel_equals_single_process", "world": world, "steps": steps,
+                          "table_sync": tr.table_sync,
                           "grad_err_over_tol_max": worst_g, "max_abs_param_diff": worst_p, "ok": ok}))
     if world > 1:
         dist.barrier()
