@@ -28,53 +28,72 @@ struct GatherArgs {
     Dropout drop;         // stream kDropEmbedding
 };
 
+__device__ __forceinline__ void gather_emit(const GatherArgs& a, bool img, long long m, int g, float4 v0, float4 v1) {
+    const int c = g * 8;
+    float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (a.drop.enabled() && c < a.D) {
+        const uint32_t keep = a.drop.keep8(kDropEmbedding, (uint64_t)m, (uint32_t)g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = ((keep >> j) & 1u) ? x[j] * a.drop.scale : 0.f;
+        if (a.mask && g < a.mask_bytes) a.mask[m * a.mask_bytes + g] = (uint8_t)keep;
+    }
+    // image column D carries 1.0: the weight-gradient GEMM then yields the bias gradient as
+    // its column D (sum_t dY[t,j] * 1); the forward GEMM's weight image is zero there
+    if (img && c <= a.D && a.D < c + 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (c + j == a.D) x[j] = 1.f;
+    }
+    if (a.x_f32) {
+        if (c < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c) = make_float4(x[0], x[1], x[2], x[3]);
+        if (c + 4 < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    }
+    if (img) ig::img_store8(a.x_img, m, g, x);
+}
+
 // Work items are (row, 8-column group) pairs, flattened: with D = 300 a row has 40 groups (5 image
 // chunks), so a warp that walked one row at a time would run a second, quarter-full pass per row;
-// flattened, four rows are exactly five full passes.
+// flattened, four rows are exactly five full passes.  A thread carries TWO items per pass so that
+// the dependent load chains (token id -> table row) of the two overlap.
 __global__ void __launch_bounds__(256) gather_rows_img_kernel(const GatherArgs a) {
     const bool img = a.x_img.hi != nullptr;
     const long long rows = img ? a.x_img.rows_pad : a.M;
     const int groups = img ? a.x_img.chunks * 8 : ceil_div(a.D, 8);
     const long long total = rows * groups;
-    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
-        const long long m = it / groups;
-        const int g = (int)(it - m * groups);
-        if (m >= a.M) {   // image pad rows: zero (they enter the weight-gradient reduction)
-            ig::img_store8_zero(a.x_img, m, g);
-            continue;
-        }
-        long long src = m;
-        bool ok = true;
-        if (a.ids) {
-            src = __ldg(a.ids + m);
-            ok = src >= 0 && src < a.vocab;
-        }
-        const float* row = a.table + src * a.D;
-        const int c = g * 8;
-        float x[8];
-        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-        if (ok && c < a.D) v0 = __ldg(reinterpret_cast<const float4*>(row + c));
-        if (ok && c + 4 < a.D) v1 = __ldg(reinterpret_cast<const float4*>(row + c + 4));
-        x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
-        x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-        if (a.drop.enabled() && c < a.D) {
-            const uint32_t keep = a.drop.keep8(kDropEmbedding, (uint64_t)m, (uint32_t)g);
+    const long long nthreads = (long long)gridDim.x * blockDim.x;
+    for (long long it0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; it0 < total; it0 += 2 * nthreads) {
+        long long m[2];
+        int g[2];
+        bool live[2], real[2];
+        float4 v0[2], v1[2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = ((keep >> j) & 1u) ? x[j] * a.drop.scale : 0.f;
-            if (a.mask && g < a.mask_bytes) a.mask[m * a.mask_bytes + g] = (uint8_t)keep;
+        for (int k = 0; k < 2; ++k) {
+            const long long it = it0 + k * nthreads;
+            live[k] = it < total;
+            m[k] = live[k] ? it / groups : 0;
+            g[k] = live[k] ? (int)(it - m[k] * groups) : 0;
+            real[k] = live[k] && m[k] < a.M;
         }
-        // image column D carries 1.0: the weight-gradient GEMM then yields the bias gradient as
-        // its column D (sum_t dY[t,j] * 1); the forward GEMM's weight image is zero there
-        if (img && c <= a.D && a.D < c + 8) {
+        long long src[2];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (c + j == a.D) x[j] = 1.f;
+        for (int k = 0; k < 2; ++k) src[k] = real[k] ? (a.ids ? __ldg(a.ids + m[k]) : m[k]) : -1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const bool ok = real[k] && src[k] >= 0 && src[k] < a.vocab;
+            const float* row = a.table + (ok ? src[k] : 0) * a.D;
+            const int c = g[k] * 8;
+            v0[k] = (ok && c < a.D) ? __ldg(reinterpret_cast<const float4*>(row + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            v1[k] = (ok && c + 4 < a.D) ? __ldg(reinterpret_cast<const float4*>(row + c + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (a.x_f32) {
-            if (c < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c) = make_float4(x[0], x[1], x[2], x[3]);
-            if (c + 4 < a.D) *reinterpret_cast<float4*>(a.x_f32 + m * a.D + c + 4) = make_float4(x[4], x[5], x[6], x[7]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!live[k]) continue;
+            if (!real[k]) {   // image pad rows: zero (they enter the weight-gradient reduction)
+                ig::img_store8_zero(a.x_img, m[k], g[k]);
+                continue;
+            }
+            gather_emit(a, img, m[k], g[k], v0[k], v1[k]);
         }
-        if (img) ig::img_store8(a.x_img, m, g, x);
     }
 }
 
