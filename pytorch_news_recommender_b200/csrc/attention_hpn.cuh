@@ -36,7 +36,7 @@ struct HpN {
     static constexpr bool SEP = LT > 32;               // P / dS in their own buffers
     static constexpr int ITEM_BWD = 4 * PAIR + (SEP ? 4 * PPLANE : 0);
     static constexpr int ITEM_FWD = 2 * PAIR + LT * 8;
-    static constexpr int ITEMS_BWD = LT == 32 ? 5 : 1; // items per CTA
+    static constexpr int ITEMS_BWD = LT == 32 ? 4 : 1; // items per CTA (4 x 2 warps = 256 threads: 128 registers each, no spills; 5 measured 7 % slower)
     static constexpr int ITEMS_FWD = LT == 32 ? 5 : 2;
 };
 
