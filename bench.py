@@ -135,9 +135,11 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # reference / CPU arm
 # ------------------------------------------------------------------------------------------
-def cpu_step_time(batch_size, steps, warmup, budget_s):
+def cpu_step_time(batch_size, steps, warmup, budget_s, device="cpu"):
     """Times the oracle port of the reference train step (per-slot encoder loops, dropout from
-    torch's RNG, autograd backward, Adam) on the host cores.  Returns (impressions/s, info)."""
+    torch's RNG, autograd backward, Adam) on the host cores.  Returns (impressions/s, info).
+    device="cuda:0" runs the same torch-eager port on the GPU instead — what the reference itself
+    does when it is given a CUDA device (`--eager-gpu-baseline`; SURVEY.md §8d "the real bar")."""
     from oracle import nrms_oracle as O
     from pytorch_news_recommender_b200 import synthetic as S
     w = WORKLOAD
@@ -147,13 +149,22 @@ def cpu_step_time(batch_size, steps, warmup, budget_s):
     ocfg = O.OracleConfig(w["n_words_title"], w["history_len"], w["n_neg"], w["d_model"], w["n_heads"],
                           w["d_query"], w["dropout"], 1e-3)
     sd = O.init_state_dict(ocfg, S.make_embedding_table(w["vocab"], w["d_model"], seed=0), seed=42)
+    on_gpu = str(device) != "cpu"
+    if on_gpu:
+        sd = {k: v.to(device) for k, v in sd.items()}
     st = O.adam_init(sd)
     pool = S.make_news_pool(w["n_news"], w["n_words_title"], w["vocab"], seed=0)
 
     def run(bs, i):
         batch = S.make_train_batch(pool, bs, w["history_len"], w["n_neg"], seed=i)
+        if on_gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        O.train_step(sd, st, batch, ocfg, training=True, per_slot=True)
+        if on_gpu:   # the model owns the H2D copy in the reference too (nrms_v0.py:248-250,272)
+            batch = {k: v.to(device) for k, v in batch.items()}
+        O.train_step(sd, st, batch, ocfg, training=True, per_slot=True)   # float(loss): D2H sync
+        if on_gpu:
+            torch.cuda.synchronize()
         return time.perf_counter() - t0
 
     bs = batch_size
@@ -169,7 +180,8 @@ def cpu_step_time(batch_size, steps, warmup, budget_s):
     t = float(np.mean(ts))
     info = {"cores": cores, "threads": torch.get_num_threads(), "kind": "port",
             "sample": f"{steps} timed train steps of {bs} impressions (per-slot oracle port of "
-                      f"train_eval.py:189-205, torch CPU fp32, dropout {w['dropout']}, dense Adam over V={w['vocab']})",
+                      f"train_eval.py:189-205, torch {'eager on ' + str(device) if on_gpu else 'CPU'} fp32, "
+                      f"dropout {w['dropout']}, dense Adam over V={w['vocab']})",
             "batch": bs, "s_per_step": t}
     return bs / t, info
 
@@ -263,6 +275,8 @@ def main():
     ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("NRMS_GEMM_MODE", "1")),
                     help="1 = tcgen05 split-bf16 GEMMs (default), 0 = exact-fp32 CUDA-core GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-gpu-baseline", action="store_true",
+                    help="also time the reference-style torch-eager step (oracle port, per-slot loops) on cuda:0")
     ap.add_argument("--zipf", action="store_true", help="Zipf(1.0) token distribution instead of uniform")
     ap.add_argument("--batch-per-gpu", type=int, default=None,
                     help="other BASELINE configs (not the default bench line): e.g. 512 with --gemm-mode 2 = cfg3's per-GPU shape")
@@ -427,6 +441,16 @@ def main():
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                             "sample": f"failed: {e!r}"}
 
+    # ---- optional: the reference-style torch-eager step on THIS GPU (oracle port, per-slot loops)
+    eager_gpu = None
+    if rank == 0 and world == 1 and args.eager_gpu_baseline:
+        try:
+            v, info = cpu_step_time(B, steps=5, warmup=2, budget_s=60.0, device=f"cuda:{local_rank}")
+            eager_gpu = {"value": v, "unit": UNIT, "kind": "port", "ms_per_step": info["s_per_step"] * 1e3,
+                         "sample": info["sample"]}
+        except Exception as e:
+            eager_gpu = {"value": None, "unit": UNIT, "kind": "port", "sample": f"failed: {e!r}"}
+
     if rank == 0:
         alg = algorithmic_counts()
         peaks = load_peaks()
@@ -455,6 +479,7 @@ def main():
             "roofline": roofline,
             "kernel_breakdown": breakdown,
             "cpu_baseline": cpu_baseline,
+            **({"eager_gpu_baseline": eager_gpu} if eager_gpu is not None else {}),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
             "gpu_launches": launches,

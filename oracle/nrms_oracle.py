@@ -189,7 +189,7 @@ def model_forward(sd: StateDict, batch: Dict[str, torch.Tensor], cfg: OracleConf
 
 def cross_entropy_vs_zero(logits):
     """train_eval.py:181,194-195 — nn.CrossEntropyLoss()(outputs, zeros(B).long())."""
-    y = torch.zeros(len(logits), dtype=torch.long)
+    y = torch.zeros(len(logits), dtype=torch.long, device=logits.device)
     return F.cross_entropy(logits, y)
 
 
