@@ -119,3 +119,20 @@ def test_rank_known_answers_numpy_restatement():
         r = np.zeros(n, np.int64)
         r[order] = np.arange(1, n + 1)
         assert np.array_equal(r, ranks[i, :n]) and not ranks[i, n:].any()
+
+
+def test_checkpoint_name_scheme_and_best_checkpoint(tmp_path):
+    """train_eval.py:142 file names and the selection rule of train_eval.py:296-303 (highest AUC in
+    the name, only above 0.5, only this model's files)."""
+    from pytorch_news_recommender_b200 import train_eval as TE
+    from pytorch_news_recommender_b200.config import Config
+    cfg = Config("NRMS_V0_DEMO")
+    cfg.save_path = str(tmp_path) + "/"
+    name = TE.checkpoint_name(cfg, 1200, 0.6789)
+    assert name.startswith("T") and name.endswith("_NRMS_V0_DEMO_epoch%d_iter_1200_auc_0.679.ckpt" % cfg.num_epochs)
+    assert TE.best_checkpoint(cfg) is None
+    for fn in ("T01-01_00.00_NRMS_V0_DEMO_epoch5_iter_10_auc_0.612.ckpt", "T01-01_00.01_NRMS_V0_DEMO_epoch5_iter_20_auc_0.655.ckpt",
+               "T01-01_00.02_OTHER_epoch5_iter_30_auc_0.900.ckpt", "T01-01_00.03_NRMS_V0_DEMO_epoch5_iter_40_auc_0.480.ckpt",
+               "notes_NRMS_V0_DEMO.txt"):
+        (tmp_path / fn).write_bytes(b"")
+    assert TE.best_checkpoint(cfg) == "T01-01_00.01_NRMS_V0_DEMO_epoch5_iter_20_auc_0.655.ckpt"
