@@ -356,8 +356,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     // 2. Q|K|V projections (nrms_v0.py:53-58)
     if (tcm && hp) {
         // head-padded projection: weight image rows in padded order, output = split-bf16 planes
-        NRMS_CHECK_CUDA(ig::img_pack(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, s, D, dk));
-        NRMS_CHECK_CUDA(ig::img_pack(pv.Wa, Q, D, D, sv.wa_img, s));
+        NRMS_CHECK_CUDA(ig::img_pack2(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, D, dk, pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, nullptr, NP, M, NP);
         g.Chi = reinterpret_cast<uint16_t*>(sv.qkv);
         g.Clo = g.Chi + (long long)d.n_seq * hp_rows(d) * NP;
@@ -368,8 +367,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.k_steps = ceil_div(D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
         NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT>(g, s, "gemm_fwd_qkv")));
     } else if (tcm) {
-        NRMS_CHECK_CUDA(ig::img_pack(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, s));
-        NRMS_CHECK_CUDA(ig::img_pack(pv.Wa, Q, D, D, sv.wa_img, s));
+        NRMS_CHECK_CUDA(ig::img_pack2(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, 0, 0, pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, sv.qkv, 3 * D, M, 3 * D);
         g.terms = terms;
         g.bias = pv.bqkv;

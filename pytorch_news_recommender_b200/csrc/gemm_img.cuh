@@ -132,6 +132,38 @@ __global__ void img_pack_kernel(const float* __restrict__ src, int R, int C, int
         img_store8(im, r, g, x);
     }
 }
+// two weight matrices of an encoder in ONE launch (the packs are launch-latency-sized kernels): the
+// second matrix's units follow the first's in the flattened index space
+__global__ void img_pack2_kernel(const float* __restrict__ src0, int R0, int C0, int ld0, Img im0, int hp_D, int hp_dk,
+                                 const float* __restrict__ src1, int R1, int C1, int ld1, Img im1) {
+    const long long t0 = (long long)im0.rows_pad * im0.chunks * 8, t1 = (long long)im1.rows_pad * im1.chunks * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t0 + t1;
+         i += (long long)gridDim.x * blockDim.x) {
+        const bool first = i < t0;
+        const Img& im = first ? im0 : im1;
+        const long long k = first ? i : i - t0;
+        const int groups = im.chunks * 8;
+        const int g = (int)(k % groups);
+        const long long r = k / groups;
+        const long long sr = first ? (hp_dk > 0 ? hp_unpad((int)r, hp_D, hp_dk) : (r < R0 ? r : -1)) : (r < R1 ? r : -1);
+        const float* src = first ? src0 : src1;
+        const int C = first ? C0 : C1, ld = first ? ld0 : ld1;
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            x[j] = (sr >= 0 && c < C) ? __ldg(src + sr * ld + c) : 0.f;
+        }
+        img_store8(im, r, g, x);
+    }
+}
+inline cudaError_t img_pack2(const float* src0, int R0, int C0, int ld0, const Img& im0, int hp_D, int hp_dk,
+                             const float* src1, int R1, int C1, int ld1, const Img& im1, cudaStream_t s) {
+    const long long total = (long long)im0.rows_pad * im0.chunks * 8 + (long long)im1.rows_pad * im1.chunks * 8;
+    NRMS_LAUNCH("img_pack", s, img_pack2_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(
+        src0, R0, C0, ld0, im0, hp_D, hp_dk, src1, R1, C1, ld1, im1));
+    return cudaGetLastError();
+}
 inline cudaError_t img_pack(const float* src, int R, int C, int ld, const Img& im, cudaStream_t s, int hp_D = 0,
                             int hp_dk = 0) {
     const long long total = (long long)im.rows_pad * im.chunks * 8;
