@@ -43,6 +43,18 @@ import torch  # noqa: E402
 
 WORKLOAD = dict(batch_per_gpu=64, n_words_title=30, history_len=50, n_neg=4, vocab=70000,
                 d_model=300, n_heads=10, d_query=200, dropout=0.2, n_news=65000)
+# BASELINE.json configs (cfg4, cached-vector scoring, is scripts/eval_bench.py).  cfg2 is the default
+# line the driver records; the others are selected with --config and name themselves in
+# config.workload.  cfg5's per-GPU batch is not fixed by BASELINE.json: 128 keeps its activations
+# (5.1 k token rows per impression) at ~20 GB per GPU.
+CONFIGS = {
+    "cfg2": dict(batch_per_gpu=64, n_words_title=30, history_len=50, n_neg=4, gemm_mode=1,
+                 label="cfg2: NRMS training fp32 on 1xB200, batch 64"),
+    "cfg3": dict(batch_per_gpu=512, n_words_title=30, history_len=50, n_neg=4, gemm_mode=2,
+                 label="cfg3: NRMS training bf16 data-parallel, batch 512/GPU, 70k-word vocab"),
+    "cfg5": dict(batch_per_gpu=128, n_words_title=48, history_len=200, n_neg=8, gemm_mode=2,
+                 label="cfg5: long-history stress, history 200, title 48, 8 negatives (bf16 products, batch 128/GPU)"),
+}
 METRIC = "train_impressions_per_sec"
 UNIT = "impressions/s"
 
@@ -186,18 +198,76 @@ def cpu_step_time(batch_size, steps, warmup, budget_s, device="cpu"):
     return bs / t, info
 
 
+def reference_step_time(batch_size, steps, warmup, budget_s, device="cpu"):
+    """Times the UNMODIFIED reference model file (oracle/_ref/nrms_v0.py, staged by
+    oracle/stage_ref.py) stepped with the literal statements of train_eval.py:189-205
+    (oracle/ref_runner.py) — on the host cores (device="cpu": `torch.device('cuda')` answered with
+    the CPU device, the only injection) or as torch eager on the GPU (the file exactly as it is).
+    Returns (impressions/s, info), or None when the reference is not staged."""
+    from oracle import ref_runner as R
+    if not R.available():
+        return None
+    from pytorch_news_recommender_b200 import synthetic as S
+    w = WORKLOAD
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tmp = os.path.join(tempfile.gettempdir(), "nrms_bench")
+    os.makedirs(tmp, exist_ok=True)
+    path = os.path.join(tmp, "emb.npz")
+    if not os.path.exists(path):
+        S.save_embedding_npz(path, S.make_embedding_table(w["vocab"], w["d_model"], seed=0))
+    dev = torch.device(device)
+    on_gpu = dev.type == "cuda"
+    rcfg = R.RefConfig(tmp + "/", "emb.npz", w["d_model"], w["n_heads"], w["d_query"], w["dropout"], dev)
+    tr = R.ReferenceTrainer(rcfg, 1e-3, seed=42)
+    pool = S.make_news_pool(w["n_news"], w["n_words_title"], w["vocab"], seed=0)
+
+    def run(bs, i):
+        batch = S.make_train_batch(pool, bs, w["history_len"], w["n_neg"], seed=i)
+        if on_gpu:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr.train_step(batch)          # the model owns the H2D copy (nrms_v0.py:248-250,272); loss.item() syncs
+        if on_gpu:
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    bs = batch_size
+    t_first = run(bs, 0)
+    est = t_first * (steps + max(warmup - 1, 0))
+    if est > budget_s:
+        bs = max(8, int(batch_size * budget_s / est))
+    for i in range(1, warmup):
+        run(bs, i)
+    ts = [run(bs, 100 + i) for i in range(steps)]
+    t = float(np.mean(ts))
+    info = {"cores": cores, "threads": torch.get_num_threads(), "kind": "reference",
+            "sample": f"{steps} timed train steps of {bs} impressions: the unmodified reference model/nrms_v0.py "
+                      f"(oracle/_ref, sha256-checked) + Adam + CrossEntropyLoss stepped as train_eval.py:189-205, "
+                      f"torch {'eager on ' + str(device) if on_gpu else 'CPU, ' + str(cores) + ' threads'}, fp32, "
+                      f"dropout {w['dropout']}, dense Adam over V={w['vocab']}",
+            "batch": bs, "s_per_step": t}
+    return bs / t, info
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, info = cpu_step_time(WORKLOAD["batch_per_gpu"], args.steps, max(args.warmup, 1), budget_s=200.0)
+    got = None
+    try:
+        got = reference_step_time(WORKLOAD["batch_per_gpu"], args.steps, max(args.warmup, 1), budget_s=200.0)
+    except Exception as e:      # a broken staging must not lose the arm: fall back to the port, and say so
+        print(f"[bench] staged reference failed ({e!r}); timing the oracle port instead", file=sys.stderr)
+    if got is None:
+        got = cpu_step_time(WORKLOAD["batch_per_gpu"], args.steps, max(args.warmup, 1), budget_s=200.0)
+    val, info = got
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["s_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "cfg2: NRMS train step fp32, batch 64, T=30 H=50 K=4 D=300 V=70k (CPU reference arm)",
-                   "sample_batch": info["batch"]},
+        "config": {"workload": workload_label(args), "sample_batch": info["batch"], "arm": "CPU reference arm"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                          "sample": info["sample"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -241,8 +311,18 @@ KERNEL_WORK = {
 }
 
 
-def kernel_work(name, B):
+def workload_label(args):
+    """The same string for both arms (the driver compares them)."""
     w = WORKLOAD
+    base = CONFIGS[args.config]["label"] if not args.custom else "custom"
+    return (f"{base}: NRMS train step (fwd + CE + bwd + dense Adam), batch {w['batch_per_gpu']} per GPU, "
+            f"T={w['n_words_title']} H={w['history_len']} K={w['n_neg']} D={w['d_model']} heads={w['n_heads']} "
+            f"Q={w['d_query']} V={w['vocab'] // 1000}k, dropout {w['dropout']}")
+
+
+def kernel_work(name, B, gemm_mode=1):
+    w = WORKLOAD
+    e = 2.0 if gemm_mode == 2 else 4.0      # bytes per activation element (bf16 plane / fp32 or hi+lo pair)
     T, H, D, Qd, C, V = w["n_words_title"], w["history_len"], w["d_model"], w["d_query"], w["n_neg"] + 1, w["vocab"]
     M_news, M_user = B * (H + C) * T, B * H
     # the profiler aggregates news + user launches under one name: work is their sum
@@ -256,14 +336,19 @@ def kernel_work(name, B):
         "gemm_wgrad_additive": ("tensor", 2.0 * M * Qd * D),
         # bytes per token row (4 B per element: fp32, or a split-bf16 hi + lo pair): fwd reads Q|K|V
         # (3D), writes the context image (D); bwd reads Q|K|V + d_ctx (4D), writes the dQ|dK|dV image (3D)
-        "attn_fwd": ("hbm", 4.0 * M * (3 * D + D)),
-        "attn_bwd": ("hbm", 4.0 * M * (4 * D + 3 * D)),
+        "attn_fwd": ("hbm", e * M * (3 * D + D)),
+        "attn_bwd": ("hbm", e * M * 3 * D + 4.0 * M * D + e * M * 3 * D),
         "adam": ("hbm", 7.0 * 4 * (V * D + 662600)),
-        "pool_fwd": ("hbm", 4.0 * M * (D + Qd)),
-        "pool_bwd": ("hbm", 4.0 * M * (2 * D + 2 * Qd)),
+        "pool_fwd": ("hbm", M * (e * D + 4.0)),
+        "pool_bwd": ("hbm", M * (e * D + 4.0 * Qd + e * Qd)),
+        "gather": ("hbm", M_news * (8.0 + 4.0 * D + e * D)),
         "embgrad_reduce": ("hbm", 4.0 * M_news * D + 4.0 * V * D),
     }
     return table.get(name)
+
+
+GEMM_LABELS = ("gemm_fwd_qkv", "gemm_fwd_additive", "gemm_dgrad_qkv", "gemm_dgrad_additive",
+               "gemm_wgrad_qkv", "gemm_wgrad_additive")
 
 
 def main():
@@ -272,25 +357,34 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("NRMS_GEMM_MODE", "1")),
-                    help="1 = tcgen05 split-bf16 GEMMs (default), 0 = exact-fp32 CUDA-core GEMMs")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS),
+                    help="BASELINE.json config: cfg2 (default, the driver's line), cfg3 (bf16, 512/GPU), cfg5 (long history)")
+    ap.add_argument("--gemm-mode", type=int, default=None,
+                    help="override the config's GEMM mode: 1 = tcgen05 split-bf16 (fp32-grade), 2 = tcgen05 plain bf16, "
+                         "0 = exact-fp32 CUDA-core GEMMs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--eager-gpu-baseline", action="store_true",
-                    help="also time the reference-style torch-eager step (oracle port, per-slot loops) on cuda:0")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the eager-on-GPU reference, the loader arm and the drop-in arm (N=1 only anyway)")
+    ap.add_argument("--eager-gpu-baseline", action="store_true", help="(kept for compatibility: on by default at N=1)")
     ap.add_argument("--zipf", action="store_true", help="Zipf(1.0) token distribution instead of uniform")
-    ap.add_argument("--batch-per-gpu", type=int, default=None,
-                    help="other BASELINE configs (not the default bench line): e.g. 512 with --gemm-mode 2 = cfg3's per-GPU shape")
-    ap.add_argument("--table-sync", default="dense", choices=["dense", "sparse"],
+    ap.add_argument("--batch-per-gpu", type=int, default=None, help="override the config's batch per GPU")
+    ap.add_argument("--table-sync", default="dense", choices=["dense", "sharded"],
                     help="exchange of the embedding-table gradient under data parallelism (engine.FusedTrainer)")
-    ap.add_argument("--title-len", type=int, default=None, help="with --history-len / --negatives: cfg5 is 48 / 200 / 8")
+    ap.add_argument("--title-len", type=int, default=None)
     ap.add_argument("--history-len", type=int, default=None)
     ap.add_argument("--negatives", type=int, default=None)
     args = ap.parse_args()
-    if args.batch_per_gpu:
-        WORKLOAD["batch_per_gpu"] = args.batch_per_gpu
-    for key, val in (("n_words_title", args.title_len), ("history_len", args.history_len), ("n_neg", args.negatives)):
-        if val:
+    c = CONFIGS[args.config]
+    for key in ("batch_per_gpu", "n_words_title", "history_len", "n_neg"):
+        WORKLOAD[key] = c[key]
+    if args.gemm_mode is None:
+        args.gemm_mode = int(os.environ.get("NRMS_GEMM_MODE", c["gemm_mode"]))
+    args.custom = False
+    for key, val in (("batch_per_gpu", args.batch_per_gpu), ("n_words_title", args.title_len),
+                     ("history_len", args.history_len), ("n_neg", args.negatives)):
+        if val and val != WORKLOAD[key]:
             WORKLOAD[key] = val
+            args.custom = True
     if args.impl == "reference":
         run_reference(args)
         return
@@ -381,7 +475,7 @@ def main():
     losses = []
 
     def step_e2e(i):
-        loss = trainer.step(pinned[i % len(pinned)])
+        trainer.step(pinned[i % len(pinned)])
         trainer.prefetch(pinned[(i + 1) % len(pinned)])   # next batch's H2D runs underneath this step
         losses.append(trainer.last_loss())  # D2H read of the step's result (train_eval.py:198), every step
 
@@ -394,11 +488,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel breakdown (separate profiled pass, CUDA events per launch) ---------------
-    roofline, breakdown = None, {}
+    roofline, roofline_gemm, breakdown = None, None, {}
     nprof = min(K, 5)
     if rank == 0:
         lib.nrms_profile_enable(1)
-    for i in range(nprof):          # every rank steps: the step contains the gradient allreduce
+    for i in range(nprof):          # every rank steps: the step contains the gradient exchange
         step_resident(i)
     sync_all()
     if rank == 0:
@@ -412,44 +506,86 @@ def main():
             nm, cnt, tms = ln.split()
             breakdown[nm] = {"launches_per_step": int(cnt) / nprof, "ms_per_step": float(tms) / nprof}
             total += float(tms) / nprof
-        top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])
-        name, rec = top
-        kw = kernel_work(name, B)
-        if kw:
+
+        def roof(name, rec):
+            kw = kernel_work(name, B, args.gemm_mode)
+            if not kw:
+                return None
             bound, work = kw
             sec = rec["ms_per_step"] / 1e3
             if bound == "tensor":
                 achieved, peak, unit = work / sec / 1e12, peaks["tflops_sustained"], "TFLOP/s"
             else:
                 achieved, peak, unit = work / sec / 1e9, peaks["hbm_gbs"], "GB/s"
-            roofline = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                        "frac": achieved / peak, "traffic": ncu_traffic(name), "peak_source": peaks["source"] +
-                        (" sustained bf16 (kernel timed inside the step)" if bound == "tensor" else " copy bandwidth"),
-                        "share_of_step": rec["ms_per_step"] / total if total else None,
-                        "ms_per_launch_group": rec["ms_per_step"]}
+            return {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                    "frac": achieved / peak, "traffic": ncu_traffic(name) if args.config == "cfg2" and not args.custom else None,
+                    "peak_source": peaks["source"] + (" sustained bf16 (kernel timed inside the step)" if bound == "tensor"
+                                                      else " copy bandwidth"),
+                    "share_of_step": rec["ms_per_step"] / total if total else None,
+                    "ms_per_launch_group": rec["ms_per_step"]}
+        # (1) the largest single kernel of the step ...
+        name, rec = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])
+        roofline = roof(name, rec)
+        # ... (2) and the tcgen05 GEMM family as ONE entry (the same template under six labels would
+        # otherwise never be the largest label although it owns half of the step): USEFUL flops of the six
+        # contractions (2*M*N*K with the model's own dims, no padding, one product per multiply) over their
+        # summed time, against the sustained bf16 peak.  gemm_mode 1 issues three bf16 MMAs per useful
+        # product (fp32-grade split), so its ceiling on this scale is 1/3.
+        fam = [(nm, breakdown[nm]) for nm in GEMM_LABELS if nm in breakdown]
+        if fam:
+            flops = sum(kernel_work(nm, B, args.gemm_mode)[1] for nm, _ in fam)
+            msf = sum(r["ms_per_step"] for _, r in fam)
+            ach = flops / (msf / 1e3) / 1e12
+            roofline_gemm = {"kernel": "ig_gemm_kernel family (6 labels)", "bound": "tensor", "achieved": ach,
+                             "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
+                             "mma_terms_per_product": 1 if args.gemm_mode == 2 else 3,
+                             "frac_of_issued_mma_peak": ach * (1 if args.gemm_mode == 2 else 3) / peaks["tflops_sustained"],
+                             "share_of_step": msf / total if total else None, "ms_per_step": msf,
+                             "peak_source": peaks["source"] + " sustained bf16"}
         for nm in breakdown:
             breakdown[nm]["share"] = breakdown[nm]["ms_per_step"] / total if total else None
 
-    # ---- CPU baseline (oracle port) on this box's host cores, rank 0 at N=1 only ----------------
+    # ---- CPU baseline on this box's host cores, rank 0 at N=1 only: the unmodified reference file when it
+    # is staged (oracle/_ref), else the oracle port ---------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            v, info = cpu_step_time(B, steps=2, warmup=1, budget_s=40.0)
+            got = None
+            try:
+                got = reference_step_time(B, steps=2, warmup=1, budget_s=40.0)
+            except Exception as e:
+                print(f"[bench] staged reference failed ({e!r}); timing the oracle port", file=sys.stderr)
+            if got is None:
+                got = cpu_step_time(B, steps=2, warmup=1, budget_s=40.0)
+            v, info = got
             cpu_baseline = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
                             "sample": info["sample"]}
         except Exception as e:  # the GPU numbers stand on their own
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                             "sample": f"failed: {e!r}"}
 
-    # ---- optional: the reference-style torch-eager step on THIS GPU (oracle port, per-slot loops)
-    eager_gpu = None
-    if rank == 0 and world == 1 and args.eager_gpu_baseline:
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # ---- the reference in torch eager on THIS GPU (SURVEY.md §8d "the real bar"): the unmodified file
         try:
-            v, info = cpu_step_time(B, steps=5, warmup=2, budget_s=60.0, device=f"cuda:{local_rank}")
-            eager_gpu = {"value": v, "unit": UNIT, "kind": "port", "ms_per_step": info["s_per_step"] * 1e3,
-                         "sample": info["sample"]}
+            got = reference_step_time(B, steps=5, warmup=2, budget_s=60.0, device=f"cuda:{local_rank}")
+            if got is None:
+                got = cpu_step_time(B, steps=5, warmup=2, budget_s=60.0, device=f"cuda:{local_rank}")
+            v, info = got
+            extras["eager_gpu_baseline"] = {"value": v, "unit": UNIT, "kind": info["kind"],
+                                            "ms_per_step": info["s_per_step"] * 1e3, "sample": info["sample"]}
         except Exception as e:
-            eager_gpu = {"value": None, "unit": UNIT, "kind": "port", "sample": f"failed: {e!r}"}
+            extras["eager_gpu_baseline"] = {"value": None, "unit": UNIT, "sample": f"failed: {e!r}"}
+        # ---- loader arm: DeviceBatcher (batch assembly on the GPU from resident id tables) -> step
+        try:
+            extras["e2e_loader"] = loader_arm(cfg, trainer, B, K)
+        except Exception as e:
+            extras["e2e_loader"] = {"value": None, "unit": UNIT, "note": f"failed: {e!r}"}
+        # ---- drop-in arm: the literal reference lines over the nn.Module (autograd + torch.optim.Adam)
+        try:
+            extras["dropin"] = dropin_arm(cfg, pinned, B, min(K, 20))
+        except Exception as e:
+            extras["dropin"] = {"value": None, "unit": UNIT, "note": f"failed: {e!r}"}
 
     if rank == 0:
         alg = algorithmic_counts()
@@ -460,15 +596,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.gemm_mode == 2 else "f32", "data": "synthetic",
-            "config": {"workload": ("cfg2" if (B, WORKLOAD["n_words_title"], WORKLOAD["history_len"], WORKLOAD["n_neg"], args.gemm_mode != 2)
-                                    == (64, 30, 50, 4, True) else "cfg3-shape" if B == 512 else "custom") +
-                                   ": NRMS train step (fwd + CE + bwd + dense Adam), " +
-                                   ("bf16 tensor-core products" if args.gemm_mode == 2 else "fp32") +
-                                   f", batch {B} per GPU, T={WORKLOAD['n_words_title']} H={WORKLOAD['history_len']} "
-                                   f"K={WORKLOAD['n_neg']} D=300 heads=10 Q=200 V=70k, dropout 0.2",
+            "config": {"workload": workload_label(args),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "gemm_mode": args.gemm_mode, "tokens": "zipf" if args.zipf else "uniform",
-                       "l2": "per-step working set (~1.5 GB activations + 607 MB Adam state) exceeds the 126 MB L2; "
+                       "table_sync": args.table_sync,
+                       "l2": "per-step working set (>= 1.5 GB activations + 607 MB Adam state) exceeds the 126 MB L2; "
                              "4 distinct batches rotated"},
             "news_encodes_per_sec": value * alg["titles_per_impr"],
             "step_model": {"algorithmic_flop_per_step_per_gpu": step_flops,
@@ -477,9 +609,10 @@ def main():
                            "hbm_floor_ms": step_bytes / peaks["hbm_gbs"] / 1e6,
                            "tensor_floor_ms": step_flops / peaks["tflops"] / 1e9},
             "roofline": roofline,
+            "roofline_gemm_family": roofline_gemm,
             "kernel_breakdown": breakdown,
             "cpu_baseline": cpu_baseline,
-            **({"eager_gpu_baseline": eager_gpu} if eager_gpu is not None else {}),
+            **extras,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
@@ -489,6 +622,77 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def loader_arm(cfg, trainer, B, K):
+    """`for datas in DeviceBatcher(...): trainer.step(datas)` — the loop train_eval.train_demo runs when
+    it is given the GPU loader: per step one batch-assembly launch (news ids -> title tokens, masks;
+    data_handler.py:185-250 semantics) and the fused step; the loss is read back every step."""
+    from pytorch_news_recommender_b200 import synthetic as S
+    from pytorch_news_recommender_b200.data_handler import DeviceBatcher
+    w = WORKLOAD
+    pool = S.make_news_pool(w["n_news"], w["n_words_title"], w["vocab"], seed=0)
+    titles = {i: pool.titles[i].tolist() for i in range(pool.n_news)}
+    S_ = w["n_neg"] + 1
+    n = B * min(K, 50)
+    datas = S.make_sample_lists(pool, n, w["history_len"], S_, S_, seed=0)
+    db = DeviceBatcher(cfg, datas, type=0, batch_size=B, shuffle=True, drop_last=True, seed=1, words_infos=(titles, {}))
+    it = iter(db)
+    for _ in range(3):
+        trainer.step(next(it))
+        trainer.last_loss()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 0
+    e0.record()
+    for datas_b in db:
+        trainer.step(datas_b)
+        trainer.last_loss()
+        steps += 1
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": B * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "note": "DeviceBatcher (one assembly launch per batch from resident id / title tables) -> FusedTrainer.step -> last_loss()"}
+
+
+def dropin_arm(cfg, pinned, B, K):
+    """The literal statements of train_eval.py:189-205 over OUR nn.Module with HOST batches:
+    outputs = model(datas); model.zero_grad(); loss = criterion(outputs, zeros); loss.item();
+    loss.backward(); torch.optim.Adam.step() — what a user gets by only swapping the model import."""
+    import torch.nn as nn
+    from pytorch_news_recommender_b200.model import NRMS_V0
+    torch.manual_seed(42)
+    model = NRMS_V0(cfg).to(cfg.device)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.learning_rate)
+    crit = nn.CrossEntropyLoss()
+
+    def step(i):
+        datas = pinned[i % len(pinned)]
+        outputs = model(datas)
+        model.zero_grad()
+        y = torch.zeros(len(outputs)).long().to(outputs.device)
+        loss = crit(outputs, y)
+        v = loss.item()
+        loss.backward()
+        opt.step()
+        return v
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del opt, model
+    return {"value": B * K / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / K, "steps": K,
+            "note": "model(datas) / criterion / loss.backward() / torch.optim.Adam over the drop-in nn.Module "
+                    "(autograd Functions over the same kernels; dense table gradient + torch Adam as in the reference)"}
 
 
 if __name__ == "__main__":

@@ -129,13 +129,16 @@ int nrms_score_bwd(int32_t B, int32_t C, int32_t D, const float* cand, const flo
                    const uint8_t* mask, const float* d_logits, float* d_cand, float* d_user,
                    nrms_stream_t stream);
 /* Fused scorer + nn.CrossEntropyLoss vs label 0 (train_eval.py:181,194-195) + its backward.
- * loss_per_row [B] receives logsumexp(s_b)-s_b0; the mean over B is *loss_mean (sum of the
- * per-row values times 1/B_global, atomically added: zero it first).  d_cand / d_user are
- * the gradients of the MEAN loss over B_global rows. */
+ * loss_per_row [B] receives logsumexp(s_b)-s_b0.  loss_mean (optional, may be NULL) receives the
+ * mean over the B rows of this call — the `loss` of train_eval.py:195 — written by the last CTA
+ * to finish, which sums loss_per_row in index order (no floating-point atomics: bitwise
+ * repeatable); `ticket` is one uint32 of device memory, zero before the first call and re-armed
+ * by the kernel (required when loss_mean is given).  d_cand / d_user are the gradients of the
+ * MEAN loss over B_global rows. */
 int nrms_score_ce_fwd_bwd(int32_t B, int32_t C, int32_t D, int32_t B_global, const float* cand,
                           const float* user, const uint8_t* mask, float* logits,
                           float* loss_per_row, float* d_cand, float* d_user,
-                          nrms_stream_t stream);
+                          float* loss_mean, uint32_t* ticket, nrms_stream_t stream);
 
 /* Deduplicated sparse scatter-add of the embedding-row gradients (the replacement of the 55
  * dense embedding_dense_backward calls).  plan = counting sort of the n_rows

@@ -57,7 +57,7 @@ SIGNATURES = {
     "nrms_user_encoder_bwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P]),
     "nrms_score_fwd": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "nrms_score_bwd": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
-    "nrms_score_ce_fwd_bwd": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "nrms_score_ce_fwd_bwd": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nrms_embedding_plan_bytes": (_I64, [_I64, _I32]),
     "nrms_embedding_plan": (C.c_int, [_P, _I64, _I32, _P, _I64, _P]),
     "nrms_embedding_grad_dense": (C.c_int, [_P, _I64, _P, _I64, _I32, _I32, _P, _P]),

@@ -848,14 +848,16 @@ int nrms_score_bwd(int32_t B, int32_t C, int32_t D, const float* cand, const flo
 int nrms_score_ce_fwd_bwd(int32_t B, int32_t C, int32_t D, int32_t B_global, const float* cand,
                           const float* user, const uint8_t* mask, float* logits,
                           float* loss_per_row, float* d_cand, float* d_user,
-                          nrms_stream_t stream) {
+                          float* loss_mean, uint32_t* ticket, nrms_stream_t stream) {
     int rc = score_check(B, C, D);
     if (rc) return rc;
     if (B_global < 1) return fail(NRMS_ERR_BAD_SHAPE, "B_global=%d", B_global);
     NRMS_REQUIRE_PTR(cand); NRMS_REQUIRE_PTR(user); NRMS_REQUIRE_PTR(logits);
     NRMS_REQUIRE_PTR(d_cand); NRMS_REQUIRE_PTR(d_user);
     if (!loss_per_row) return fail(NRMS_ERR_NULL, "loss_per_row is NULL");
+    if (loss_mean && !ticket) return fail(NRMS_ERR_NULL, "ticket is NULL (required with loss_mean)");
     ScoreArgs a{};
+    a.loss_mean = loss_mean; a.ticket = ticket;
     a.cand = cand; a.user = user; a.mask = mask; a.logits = logits; a.loss_rows = loss_per_row;
     a.d_cand = d_cand; a.d_user = d_user; a.B = B; a.C = C; a.D = D;
     a.inv_batch = 1.f / (float)B_global;

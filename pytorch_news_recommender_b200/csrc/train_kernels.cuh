@@ -17,6 +17,8 @@ struct ScoreArgs {
     float* logits;       // [B, C]
     const float* d_logits; // [B, C] (score_bwd only)
     float* loss_rows;    // [B]    (fused only)
+    float* loss_mean;    // [1]    (fused, optional): mean of loss_rows, summed in index order by the last CTA
+    unsigned int* ticket;  // [1]  (fused, with loss_mean): zero before the first call; the kernel resets it
     float* d_cand;       // [B, C, D]
     float* d_user;       // [B, D]
     int B, C, D;
@@ -81,6 +83,33 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a) {
             a.d_cand[((long long)b * C + c) * D + d] = g * ud;
         }
         a.d_user[(long long)b * D + d] = du;
+    }
+    if (MODE == 1 && a.loss_mean != nullptr) {
+        // mean over the B rows without a second launch and without floating-point atomics: the CTA that
+        // draws the last ticket sums loss_rows in index order (bitwise repeatable) and re-arms the ticket
+        __shared__ unsigned int s_last;
+        __shared__ float s_part[8];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(a.ticket, 1u) == (unsigned)a.B - 1u ? 1u : 0u;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            // fixed assignment of rows to lanes and a fixed shuffle tree: the same bits every run
+            float acc = 0.f;
+            for (int i = threadIdx.x; i < a.B; i += blockDim.x) acc += __ldcg(a.loss_rows + i);
+            acc = warp_sum(acc);
+            if (lane == 0) s_part[warp] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float t = 0.f;
+                for (int w = 0; w < nw; ++w) t += s_part[w];
+                *a.loss_mean = t / (float)a.B;
+                *a.ticket = 0u;
+            }
+        }
     }
 }
 

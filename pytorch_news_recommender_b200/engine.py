@@ -62,6 +62,52 @@ def _next_seed(module) -> int:
     return (int(getattr(cfg, "dropout_seed", 0)) + step) & (2**63 - 1)
 
 
+def weights_version(model) -> int:
+    """Changes whenever the model's weights do: torch's in-place version counters (torch optimizers,
+    load_state_dict) plus the counter `FusedTrainer.step` bumps (its Adam kernel writes the
+    parameters through raw pointers, which torch's counters cannot see)."""
+    return sum(int(p._version) for p in model.parameters()) + 1_000_003 * int(getattr(model, "_nrms_weights_version", 0))
+
+
+# Inference (torch.no_grad()): nothing is saved for a backward, so every encoder call reuses ONE
+# activation blob and long title lists are encoded in chunks of at most this many token rows — the
+# reference's dev shape (512 impressions x 350 titles x 20 words = 3.6 M rows, train_eval.py:238-251)
+# would otherwise allocate ~40 GB of never-read saved state per batch.
+INFER_ROWS_PER_CHUNK = 1 << 19
+
+
+def news_encode_nograd(ids, table, gemm_mode, n_heads, params) -> torch.Tensor:
+    """Eval-mode NewsEncoder.forward (nrms_v0.py:154-176, dropout off) without autograd state."""
+    ids = ids.contiguous()
+    n_seq, L = ids.shape
+    D, Q = table.shape[1], params[8].numel()
+    flat = pack_params(params)
+    out = torch.empty((n_seq, D), dtype=torch.float32, device=table.device)
+    per = max(1, INFER_ROWS_PER_CHUNK // L)
+    for lo in range(0, n_seq, per):
+        n = min(per, n_seq - lo)
+        shape = EncoderShape(n, L, D, n_heads, Q, table.shape[0])
+        blob = _blobs.get("infer_saved", ops.saved_bytes(shape, gemm_mode), table.device)
+        ops.news_encoder_fwd(shape, ids[lo:lo + n], table, flat, blob, 0.0, 0, gemm_mode, out=out[lo:lo + n])
+    return out
+
+
+def user_encode_nograd(x, gemm_mode, n_heads, params) -> torch.Tensor:
+    """UserEncoder.forward (nrms_v0.py:188-199) without autograd state."""
+    x = x.contiguous()
+    n_seq, L, D = x.shape
+    Q = params[8].numel()
+    flat = pack_params(params)
+    out = torch.empty((n_seq, D), dtype=torch.float32, device=x.device)
+    per = max(1, INFER_ROWS_PER_CHUNK // L)
+    for lo in range(0, n_seq, per):
+        n = min(per, n_seq - lo)
+        shape = EncoderShape(n, L, D, n_heads, Q, 0)
+        blob = _blobs.get("infer_saved", ops.saved_bytes(shape, gemm_mode), x.device)
+        ops.user_encoder_fwd(shape, x[lo:lo + n], flat, blob, gemm_mode, out=out[lo:lo + n])
+    return out
+
+
 class NewsEncodeFn(torch.autograd.Function):
     """NewsEncoder.forward (nrms_v0.py:154-176) over a flat list of titles."""
 
@@ -179,8 +225,9 @@ class FusedTrainer:
         self.pg = process_group
         self.exchange = GradientExchange(process_group)
         self.world = self.exchange.world
-        if table_sync not in ("dense", "sparse"):
-            raise ValueError("table_sync must be 'dense' or 'sparse'")
+        if table_sync not in ("dense", "sharded"):
+            raise ValueError("table_sync must be 'dense' (all-reduce + replicated Adam) or 'sharded' "
+                             "(reduce-scatter + Adam on V/G rows + all-gather)")
         self.table_sync = table_sync
         self.step_count = 0
         self.table = model.news_encoder.word_embedding[0].weight
@@ -209,11 +256,39 @@ class FusedTrainer:
         self.flat_grad = torch.zeros_like(flat)
         self.flat_m = torch.zeros_like(flat)
         self.flat_v = torch.zeros_like(flat)
-        self.table_grad = torch.empty_like(self.table.data)
-        self.table_m = torch.zeros_like(self.table.data)
-        self.table_v = torch.zeros_like(self.table.data)
+        V, D = self.table.shape
+        if self.world > 1 and table_sync == "sharded":
+            # ZeRO-1 style: the table gradient is reduce-SCATTERED, every rank runs Adam on its V/G rows
+            # only (moments exist for those rows only) and the updated rows are all-gathered.  Both
+            # collectives need world equal slices: table and gradient live in buffers padded to
+            # V_pad = G * ceil(V / G) rows; the nn.Embedding weight is re-pointed at the first V rows.
+            self.v_shard = (V + self.world - 1) // self.world
+            v_pad = self.v_shard * self.world
+            self.table_pad = torch.zeros((v_pad, D), dtype=torch.float32, device=dev)
+            self.table_pad[:V].copy_(self.table.data)
+            self.table.data = self.table_pad[:V]
+            self.table_grad_pad = torch.zeros((v_pad, D), dtype=torch.float32, device=dev)
+            self.table_grad = self.table_grad_pad[:V]
+            lo = self.exchange.rank * self.v_shard
+            self.table_shard = self.table_pad[lo:lo + self.v_shard]
+            self.grad_shard = torch.empty((self.v_shard, D), dtype=torch.float32, device=dev)
+            self.table_m = torch.zeros((self.v_shard, D), dtype=torch.float32, device=dev)
+            self.table_v = torch.zeros((self.v_shard, D), dtype=torch.float32, device=dev)
+            self._comm = torch.cuda.Stream(device=dev)
+        else:
+            self.table_grad = torch.empty_like(self.table.data)
+            self.table_m = torch.zeros_like(self.table.data)
+            self.table_v = torch.zeros_like(self.table.data)
         self.blobs = BlobCache()
         self._bufs: Dict[Tuple, Dict[str, torch.Tensor]] = {}
+        if self.world > 1:
+            # replicas must START identical: rank 0's weights win (a rank that seeded differently would
+            # otherwise diverge silently; the updates are identical by construction afterwards)
+            dist.broadcast(self.flat, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+            dist.broadcast(self.table.data, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+        # last-CTA ticket of the scorer's loss mean (include/nrms_b200.h) and the loss itself
+        self._ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
 
     # -- persistent device buffers per batch shape ----------------------------------------
     def _buffers(self, B, C, H, T):
@@ -304,9 +379,12 @@ class FusedTrainer:
         training = self.model.training
         p = float(cfg.dropout) if training else 0.0
         self.step_count += 1
-        seed = (int(getattr(cfg, "dropout_seed", 0)) + self.step_count) & (2**63 - 1)
+        # every rank draws its own masks: the kernels address the Philox stream by LOCAL row, so the rank is
+        # mixed into the key (identical masks on every shard would correlate the noise across ranks)
+        seed = (int(getattr(cfg, "dropout_seed", 0)) + self.step_count
+                + 0x9E3779B97F4A7C15 * self.exchange.rank) & (2**63 - 1)
         if b_global is None:
-            b_global = B * self.world
+            b_global = B * self.world              # even shards; see `global_batch` for ragged last batches
         n_titles = B * (C + H)
         # shapes and blob sizes depend only on (batch shape, GEMM mode): looked up once, not per step
         # (a step that follows a host read-back has this prologue on its critical path)
@@ -341,12 +419,15 @@ class FusedTrainer:
         # ---- scorer + CE + their backward ---------------------------------------------------
         d_cand = b["d_news_vec"][:B * C].view(B, C, D)
         d_hist = b["d_news_vec"][B * C:].view(B, H, D)
+        if getattr(self, "_loss_event", None) is not None:
+            main.wait_event(self._loss_event)     # the previous step's 4-byte read-back of _loss_dev is done
         ops.score_ce_fwd_bwd(cand_vec, b["user_vec"], b["mask"], b_global, b["logits"],
-                             b["loss_rows"], d_cand, b["d_user_vec"])
+                             b["loss_rows"], d_cand, b["d_user_vec"], loss_mean=self._loss_dev,
+                             ticket=self._ticket)
         # The loss is final here, half a step before the optimizer is: it starts its way to the host
         # now, so that `last_loss()` (the `loss.item()` of train_eval.py:198) does not wait for the
         # backward and Adam — and the host can already enqueue the next step while they run.
-        loss = b["loss_rows"].mean()
+        loss = self._loss_dev[0]     # the mean over the shard, summed in index order by the scorer's last CTA
         if getattr(self, "_loss_host", None) is None:
             self._loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
             self._loss_event, self._loss_ready = torch.cuda.Event(), torch.cuda.Event()
@@ -355,7 +436,7 @@ class FusedTrainer:
         self._loss_ready.record(torch.cuda.current_stream(dev))
         self._loss_stream.wait_event(self._loss_ready)
         with torch.cuda.stream(self._loss_stream):
-            self._loss_host.copy_(loss.reshape(1), non_blocking=True)
+            self._loss_host.copy_(self._loss_dev, non_blocking=True)
             self._loss_event.record(self._loss_stream)
         # ---- backward -----------------------------------------------------------------------
         ops.user_encoder_bwd(user_shape, hist_vec, user_flat, b["d_user_vec"], user_saved,
@@ -369,8 +450,17 @@ class FusedTrainer:
         main.wait_stream(self._side)
         ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
         # ---- gradient exchange (data parallel): SUM-allreduce, gradients already carry 1/B_global
-        if self.world > 1 and self.table_sync == "sparse":
-            self._exchange_table_sparse(V, D)
+        b1, b2 = self.betas
+        sharded = self.world > 1 and self.table_sync == "sharded"
+        if sharded:
+            # reduce-scatter -> Adam on this rank's rows -> all-gather, all on a side stream underneath the
+            # weight-gradient GEMMs: the same bytes on the wire as the all-reduce, a G times smaller Adam
+            self._comm.wait_stream(main)
+            with torch.cuda.stream(self._comm):
+                self.exchange.reduce_scatter(self.table_grad_pad, self.grad_shard)
+                ops.adam_step(self.table_shard, self.grad_shard, self.table_m, self.table_v, self.step_count,
+                              self.lr, b1, b2, self.eps)
+                self.exchange.all_gather(self.table_pad, self.table_shard)
             pending = []
         else:
             pending = self.exchange.allreduce([self.table_grad], async_op=True)
@@ -379,36 +469,29 @@ class FusedTrainer:
         for h_ in pending:
             h_.wait()
         # ---- Adam ---------------------------------------------------------------------------
-        b1, b2 = self.betas
         ops.adam_step(self.flat, self.flat_grad, self.flat_m, self.flat_v, self.step_count, self.lr,
                       b1, b2, self.eps)
-        ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
-                      b1, b2, self.eps)
+        if sharded:
+            main.wait_stream(self._comm)          # the gathered table is what the next forward reads
+        else:
+            ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
+                          b1, b2, self.eps)
+        self.model._nrms_weights_version = getattr(self.model, "_nrms_weights_version", 0) + 1
         if "slot_free" in b:                      # this step's input slot may be overwritten from here on
             ev = torch.cuda.Event()
             ev.record(main)
             b["slot_free"][b["slot"]] = ev
         return loss
 
-    def _exchange_table_sparse(self, V: int, D: int) -> None:
-        """table_sync="sparse" (SURVEY.md §8e): instead of all-reducing the dense 84 MB table gradient,
-        all-gather only the rows this step touched — (ids, rows) per rank — and rebuild the dense sum
-        locally with the same deduplicating kernels that built the local gradient (counting sort of the
-        gathered ids + segmented reduce, fixed order: identical bits on every rank).  Pays off when
-        the ranks together touch well under V rows (small batches, skewed tokens, many GPUs); with
-        uniform tokens at 64 impressions per GPU a rank already touches ~60 % of the rows and the dense
-        all-reduce moves less.  Reading the row counts synchronises the host once per step."""
-        tg = self.table_grad
-        ids = torch.nonzero(tg.abs().amax(dim=1) > 0).squeeze(1)          # touched rows with a non-zero gradient
-        rows = ops.gather_rows(tg, ids, base=0) if ids.numel() else tg[:0]
-        ids_all, rows_all = self.exchange.allgather_rows(ids, rows)
-        n = ids_all.numel()
-        if n == 0:
-            tg.zero_()
-            return
-        plan = self.blobs.get("plan_sparse", ops.embedding_plan_bytes(n, V), self.device)
-        ops.embedding_plan(ids_all, V, plan)
-        ops.embedding_grad_dense(plan, rows_all, n, V, D, tg)
+    def global_batch(self, B: int) -> int:
+        """Sum of the ranks' shard sizes (one small all-reduce + host read).  `step` assumes even
+        shards (`B * world`); a loader with drop_last=False (the reference's, data_handler.py) leaves a
+        ragged last batch, for which the caller passes `b_global=trainer.global_batch(B)`."""
+        if self.world == 1:
+            return int(B)
+        t = torch.tensor([B], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+        return int(t.item())
 
     def last_loss(self) -> float:
         """The mean loss of the last `step` as a Python float: waits only for the forward + loss of
@@ -418,7 +501,13 @@ class FusedTrainer:
 
     def grads_as_state_dict(self) -> Dict[str, torch.Tensor]:
         """Last step's gradients keyed like model.state_dict() (for parity tests)."""
-        out = {"news_encoder.word_embedding.0.weight": self.table_grad}
+        tg = self.table_grad
+        if self.world > 1 and self.table_sync == "sharded":
+            # the reduced gradient exists as one shard per rank: gather it (collective: every rank calls)
+            full = torch.empty_like(self.table_grad_pad)
+            self.exchange.all_gather(full, self.grad_shard)
+            tg = full[:self.table.shape[0]]
+        out = {"news_encoder.word_embedding.0.weight": tg}
         for prefix, lo in (("news_encoder.", 0), ("user_encoder.", self.n_enc)):
             block = self.flat_grad[lo:lo + self.n_enc]
             plist = self.news_params if lo == 0 else self.user_params

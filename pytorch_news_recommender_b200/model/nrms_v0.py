@@ -85,6 +85,10 @@ class NewsEncoder(nn.Module):
             raise NrmsError("NewsEncoder runs on a CUDA device only (no CPU fallback); move the model with .to('cuda')")
         ids = news.to(table.device, dtype=torch.int64)
         p = float(self.config.dropout) if self.training else 0.0
+        if p == 0.0 and not torch.is_grad_enabled():
+            # inference: one shared activation blob, chunked (engine.news_encode_nograd)
+            return engine.news_encode_nograd(ids, table, _gemm_mode(self.config), self.config.num_attention_heads,
+                                             engine.encoder_param_list(self))
         seed = engine._next_seed(self) if p > 0 else 0
         return engine.NewsEncodeFn.apply(ids, table, p, seed, _gemm_mode(self.config),
                                          self.config.num_attention_heads,
@@ -104,6 +108,9 @@ class UserEncoder(nn.Module):
         """user_vector: [B, num_clicked, D] -> [B, D]."""
         if not user_vector.is_cuda:
             raise NrmsError("UserEncoder runs on a CUDA device only (no CPU fallback)")
+        if not torch.is_grad_enabled():
+            return engine.user_encode_nograd(user_vector, _gemm_mode(self.config), self.config.num_attention_heads,
+                                             engine.encoder_param_list(self))
         return engine.UserEncodeFn.apply(user_vector, _gemm_mode(self.config),
                                          self.config.num_attention_heads,
                                          *engine.encoder_param_list(self))

@@ -158,12 +158,16 @@ def score_bwd(cand, user, mask, d_logits, d_cand=None, d_user=None):
     return d_cand, d_user
 
 
-def score_ce_fwd_bwd(cand, user, mask, b_global, logits, loss_rows, d_cand, d_user):
-    _require_cuda(cand, user, mask, logits, loss_rows, d_cand, d_user)
+def score_ce_fwd_bwd(cand, user, mask, b_global, logits, loss_rows, d_cand, d_user, loss_mean=None,
+                     ticket=None):
+    """loss_mean [1] float32 (optional) receives mean(loss_rows); ticket [1] int32, zero-initialised
+    once by the caller, is the kernel's last-CTA counter (include/nrms_b200.h)."""
+    _require_cuda(cand, user, mask, logits, loss_rows, d_cand, d_user, loss_mean, ticket)
     B, Cn, D = cand.shape
     check(_lib.load().nrms_score_ce_fwd_bwd(B, Cn, D, int(b_global), ptr(cand), ptr(user),
                                             ptr(mask), ptr(logits), ptr(loss_rows), ptr(d_cand),
-                                            ptr(d_user), _stream()), "nrms_score_ce_fwd_bwd")
+                                            ptr(d_user), ptr(loss_mean), ptr(ticket), _stream()),
+          "nrms_score_ce_fwd_bwd")
 
 
 def embedding_plan_bytes(n_rows: int, vocab: int) -> int:

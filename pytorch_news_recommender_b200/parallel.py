@@ -80,27 +80,43 @@ class GradientExchange:
                 handles.append(h)
         return handles
 
-    def allgather_rows(self, ids: torch.Tensor, rows: torch.Tensor):
-        """The sparse form of the table-gradient exchange: every rank contributes
-        its touched vocabulary rows `ids` [U_r] int64 and their gradient `rows` [U_r, D]; returns
-        (ids_all [G*U_max], rows_all [G*U_max, D]) in rank order, ranks with fewer rows padded
-        with id 0 / zero rows (id 0 is the padding row, whose gradient is dropped anyway).  The
-        row counts differ per rank, so one tiny all-gather of the counts comes first."""
+    # -- sharded form of the table exchange: reduce-scatter -> Adam on this rank's rows -> all-gather -----
+    def _backend(self) -> str:
+        return dist.get_backend(self.group) if self.world > 1 else "none"
+
+    def reduce_scatter(self, full: torch.Tensor, out: torch.Tensor) -> None:
+        """out [n] = this rank's slice of the SUM over ranks of full [world*n] (rank r owns
+        [r*n, (r+1)*n)).  NCCL: one reduce-scatter; gloo (CPU tests) has none: all-reduce + slice."""
+        if full.numel() != self.world * out.numel():
+            raise ValueError("reduce_scatter: full must hold world * out.numel() elements")
         if self.world == 1:
-            return ids, rows
-        n = torch.tensor([ids.numel()], dtype=torch.int64, device=ids.device)
-        counts = torch.empty(self.world, dtype=torch.int64, device=ids.device)
-        dist.all_gather_into_tensor(counts, n, group=self.group)
-        u_max = int(counts.max().item())
-        ids_pad = torch.zeros(u_max, dtype=torch.int64, device=ids.device)
-        rows_pad = torch.zeros((u_max, rows.shape[1]), dtype=rows.dtype, device=rows.device)
-        ids_pad[:ids.numel()] = ids
-        rows_pad[:rows.shape[0]] = rows
-        ids_all = torch.empty(self.world * u_max, dtype=torch.int64, device=ids.device)
-        rows_all = torch.empty((self.world * u_max, rows.shape[1]), dtype=rows.dtype, device=rows.device)
-        dist.all_gather_into_tensor(ids_all, ids_pad, group=self.group)
-        dist.all_gather_into_tensor(rows_all, rows_pad, group=self.group)
-        return ids_all, rows_all
+            out.copy_(full.view(-1))
+            return
+        if self._backend() == "nccl":
+            dist.reduce_scatter_tensor(out.view(-1), full.view(-1), op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            tmp = full.view(-1).clone()
+            dist.all_reduce(tmp, op=dist.ReduceOp.SUM, group=self.group)
+            n = out.numel()
+            out.view(-1).copy_(tmp[self.rank * n:(self.rank + 1) * n])
+
+    def all_gather(self, full: torch.Tensor, shard: torch.Tensor) -> None:
+        """full [world*n] <- every rank's shard [n], in rank order.  `shard` may be the rank's own slice
+        of `full` (the in-place form NCCL supports)."""
+        if full.numel() != self.world * shard.numel():
+            raise ValueError("all_gather: full must hold world * shard.numel() elements")
+        if self.world == 1:
+            if full.data_ptr() != shard.data_ptr():
+                full.view(-1).copy_(shard.view(-1))
+            return
+        if self._backend() == "nccl":
+            dist.all_gather_into_tensor(full.view(-1), shard.view(-1), group=self.group)
+        else:
+            n = shard.numel()
+            parts = [torch.empty(n, dtype=shard.dtype, device=shard.device) for _ in range(self.world)]
+            dist.all_gather(parts, shard.reshape(-1).clone(), group=self.group)
+            for r, part in enumerate(parts):
+                full.view(-1)[r * n:(r + 1) * n].copy_(part)
 
     def max_over_ranks(self, value: float, device) -> float:
         """Timing helper: the slowest rank defines the step time."""

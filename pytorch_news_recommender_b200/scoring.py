@@ -35,6 +35,7 @@ class CachedScorer:
         self.titles = title_table.to(self.device, dtype=torch.int64).contiguous()
         self.chunk = chunk
         self.news_vecs: Optional[torch.Tensor] = None
+        self._cache_version = None      # engine.weights_version(model) the cache was built from
 
     @torch.no_grad()
     def build_cache(self, rank: int = 0, world: int = 1) -> torch.Tensor:
@@ -54,6 +55,8 @@ class CachedScorer:
             dist.all_gather(bufs, mine)
             mine = torch.cat(bufs, 0)
         self.news_vecs = mine
+        from .engine import weights_version
+        self._cache_version = weights_version(self.model)
         self.model.train(was_training)
         return mine
 
@@ -61,8 +64,9 @@ class CachedScorer:
     def score(self, browsed_ids: torch.Tensor, candidate_ids: torch.Tensor,
               candidate_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[B, H] and [B, S] news ids (+ optional uint8 mask) -> logits [B, S] (padded = -1e9)."""
-        if self.news_vecs is None:
-            self.build_cache()
+        from .engine import weights_version
+        if self.news_vecs is None or self._cache_version != weights_version(self.model):
+            self.build_cache()          # first use, or the weights changed since the cache was built
         dev = self.device
         b_ids = browsed_ids.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
         c_ids = candidate_ids.to(dev, dtype=torch.int64, non_blocking=True).contiguous()

@@ -46,10 +46,112 @@ def set_y_true(y_true: Sequence[Sequence[int]]) -> None:
     _y_true = [list(map(int, y)) for y in y_true]
 
 
+def log_res(config, step, auc):
+    """train_eval.py:274-278, same signature and file format (`<time>_<auc>_:auc_<step>` appended to
+    config.log_path/res.txt).  The reference calls it as `log_res(config, auc, total_batch)`, i.e.
+    with the two values swapped; `train` below makes the same call, so the files read the same."""
+    import os
+    os.makedirs(config.log_path, exist_ok=True)
+    with open(config.log_path + '/res.txt', 'a+') as f:
+        f.write('{}_{}_:auc_{}\n'.format(time.strftime('%m-%d_%H.%M'), auc, step))
+
+
+def warmup_lr(base_lr: float, i: int, warm_up_steps: int) -> float:
+    """Learning rate of warm-up iteration i in the reference's loop (train_eval.py:64-98):
+    GradualWarmupScheduler(multiplier=1, total_epoch=warm_up_steps) is stepped with `i` AFTER
+    iteration i (lr_scheduler.py:39-40: base_lr * last_epoch / total_epoch), so iteration i runs
+    with the rate set after iteration i-1: base_lr * max(i-1, 0) / warm_up_steps."""
+    e = max(i - 1, 0)
+    return base_lr if e > warm_up_steps else base_lr * float(e) / warm_up_steps
+
+
+def train(config, model, train_iter, dev_iter, y_true: Optional[Sequence[Sequence[int]]] = None,
+          fused: bool = True, restore_train_mode: bool = False, log=print):
+    """The reference's main loop (train_eval.py:34-153, entered from run_v0.py): optional warm-up
+    (`config.warm_up`: 502 iterations with a linearly rising learning rate), then
+    `config.num_epochs` epochs with an evaluation every `config.eval_step` batches and after every
+    epoch, `log_res` after each evaluation, and a checkpoint whenever the dev AUC improves on
+    `AUC_best` (initially 0.56) and `config.save_flag` is set.  `y_true` replaces the hard-coded
+    read of './data_processed/dev_behaviors.csv'.
+
+    Deviation kept from the reference on purpose: `evaluate` puts the model in eval mode and the
+    reference never switches back (train_eval.py:230), so everything after the first evaluation
+    trains WITHOUT dropout.  `restore_train_mode=True` opts out of that.  `plot_loss` (matplotlib,
+    tools.py) is out of scope; the loss records are returned instead."""
+    if y_true is not None:
+        set_y_true(y_true)
+    elif _y_true is None:
+        set_y_true(load_y_true(config.data_path + 'dev_behaviors.csv'))
+    start_time = time.time()
+    model.train()
+    trainer = FusedTrainer(model, lr=config.learning_rate) if fused else None
+    optimizer = None if fused else torch.optim.Adam(model.parameters(), lr=config.learning_rate)
+    criterion = nn.CrossEntropyLoss()
+    total_batch, AUC_best, loss_list, STEP_SIZE, improve = 0, 0.56, [], 100, '*'
+    loss_records: List[float] = []
+
+    def one_step(datas, lr):
+        if fused:
+            trainer.lr = lr
+            trainer.step(datas)
+            return trainer.last_loss()
+        for g in optimizer.param_groups:
+            g['lr'] = lr
+        outputs = model(datas)
+        model.zero_grad()
+        y = torch.zeros(len(outputs)).long().to(outputs.device)
+        loss = criterion(outputs, y)
+        loss.backward()
+        optimizer.step()
+        return loss.item()
+
+    def after_eval(auc, tag):
+        nonlocal AUC_best
+        log_res(config, auc, tag)                 # (sic: the reference passes them in this order)
+        if auc > AUC_best:
+            AUC_best = auc
+            if config.save_flag:
+                save_checkpoint(config, model, total_batch, AUC_best)
+        if restore_train_mode:
+            model.train()
+
+    if getattr(config, 'warm_up', False):
+        log('warm-up training...')
+        for i, datas in enumerate(train_iter):
+            loss_list.append(one_step(datas, warmup_lr(config.learning_rate, i, config.warm_up_steps)))
+            if i % 100 == 0:
+                msg = 'Warm-up Steps: {0:>6},  Train Loss: {1:>5.6},  Time: {2} {3}'
+                log(msg.format(i, np.mean(loss_list), get_time_dif(start_time), improve))
+                loss_list = []
+            if i > 500:
+                break
+    auc = float('nan')
+    for epoch in range(config.num_epochs):
+        log('Epoch [{}/{}]'.format(epoch + 1, config.num_epochs))
+        loss_records = []
+        for i, datas in enumerate(train_iter):
+            loss = one_step(datas, config.learning_rate)
+            loss_list.append(loss)
+            loss_records.append(loss)
+            if total_batch % STEP_SIZE == 0:
+                msg = 'Iter: {0:>6},  Train Loss: {1:>5.6},  Time: {2} {3}'
+                log(msg.format(total_batch, np.mean(loss_list), get_time_dif(start_time), improve))
+                loss_list = []
+            total_batch += 1
+            if total_batch % config.eval_step == 0 and total_batch > 0:
+                auc = evaluate(config, model, dev_iter, AUC_best, log=log)
+                after_eval(auc, total_batch)
+        auc = evaluate(config, model, dev_iter, AUC_best, log=log)
+        after_eval(auc, 'epoch_{}'.format(epoch))
+    return {"auc": auc, "auc_best": AUC_best, "total_batch": total_batch, "loss_records": loss_records}
+
+
 def train_demo(config, model, train_iter, dev_iter, y_true: Optional[Sequence[Sequence[int]]] = None,
-               fused: bool = True, log=print):
+               fused: bool = True, restore_train_mode: bool = False, log=print):
     """train_eval.py:156-215.  `y_true` replaces the hard-coded read of
-    './data_processed/small_dev_behaviors.csv' when given."""
+    './data_processed/small_dev_behaviors.csv' when given.  As in the reference, the model is left
+    in eval mode by `evaluate` (train_eval.py:230), so epochs after the first train without dropout;
+    `restore_train_mode=True` switches back to train mode after each evaluation instead."""
     if y_true is not None:
         set_y_true(y_true)
     elif _y_true is None:
@@ -81,7 +183,8 @@ def train_demo(config, model, train_iter, dev_iter, y_true: Optional[Sequence[Se
                 loss_list = []
             total_batch += 1
         auc = evaluate(config, model, dev_iter, AUC_best, log=log)
-        model.train()
+        if restore_train_mode:
+            model.train()
     return auc
 
 
@@ -150,10 +253,14 @@ def test(config, model, data_iter, ckpt_file=None, test_list_nums: Optional[Sequ
     from . import ops
     if ckpt_file is None:
         ckpt_file = best_checkpoint(config)
-    if ckpt_file is not None:
-        path = ckpt_file if os.path.isabs(ckpt_file) or os.path.exists(ckpt_file) else config.save_path + ckpt_file
-        model.load_state_dict(torch.load(path, map_location='cpu'))
-        log('load the ckpt_file:{}'.format(ckpt_file))
+    if ckpt_file is None:
+        # the reference fails here too (train_eval.py:309: torch.load(save_path + None)); scoring the
+        # current weights silently would write a submission nobody trained
+        raise FileNotFoundError("test(): no checkpoint of '{}' with auc > 0.5 under {} and no ckpt_file given"
+                                .format(config.model_name, config.save_path))
+    path = ckpt_file if os.path.isabs(ckpt_file) or os.path.exists(ckpt_file) else config.save_path + ckpt_file
+    model.load_state_dict(torch.load(path, map_location='cpu'))
+    log('load the ckpt_file:{}'.format(ckpt_file))
     if test_list_nums is None:
         import pickle
         with open(config.data_path + 'test_imps_list.pkl', 'rb') as f:

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Data-parallel equivalence on real GPUs (run under torchrun, one rank per GPU):
 every rank takes its shard of a global batch through `FusedTrainer.step` (NCCL sum-allreduce of
-the gradient buffers, chunked table exchange pipelined with Adam) for a few steps; the resulting
+the gradient buffers; TABLE_SYNC=sharded: reduce-scatter + Adam on V/G rows + all-gather) for a few steps; the resulting
 parameters must equal a single-process run over the whole batch (dropout off: the masks are
 addressed by local row numbers).  Prints one JSON line on rank 0 and exits non-zero on mismatch.
 

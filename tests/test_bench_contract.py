@@ -1,5 +1,5 @@
 """CPU test of the bench contract's reference arm: `bench.py --impl reference` prints ONE JSON line
-with the keys the driver reads, times the oracle port of the reference step on the host cores
+with the keys the driver reads, times the reference step (the staged unmodified model file, else the oracle port) on the host cores
 and launches nothing on a GPU."""
 import json
 import os
@@ -20,7 +20,12 @@ def test_reference_arm_prints_the_contract_line():
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["vs_baseline"] is None
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["gpu_launches"] == 0
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "train_eval.py" in cb["sample"]
+    # the unmodified reference file when oracle/_ref is staged (build() does it where /root/reference exists),
+    # else the oracle port
+    staged = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "nrms_v0.py"))
+    assert cb["kind"] == ("reference" if staged else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "train_eval.py" in cb["sample"]
+    assert d["config"]["workload"].startswith("cfg2")
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

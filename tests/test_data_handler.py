@@ -136,3 +136,32 @@ def test_checkpoint_name_scheme_and_best_checkpoint(tmp_path):
                "notes_NRMS_V0_DEMO.txt"):
         (tmp_path / fn).write_bytes(b"")
     assert TE.best_checkpoint(cfg) == "T01-01_00.01_NRMS_V0_DEMO_epoch5_iter_20_auc_0.655.ckpt"
+
+
+from pytorch_news_recommender_b200 import train_eval as TE  # noqa: E402
+from pytorch_news_recommender_b200.config import Config  # noqa: E402
+
+
+def test_warmup_lr_follows_the_reference_scheduler():
+    """Values printed by the reference's own GradualWarmupScheduler(optimizer, multiplier=1,
+    total_epoch=500) stepped as in train_eval.py:64-98 (optimizer lr 1e-3; run in the build container
+    with /root/reference/MIND_2020/lr_scheduler.py): the rate iteration i trains with."""
+    ref = {0: 0.0, 1: 0.0, 2: 2e-06, 3: 4e-06, 100: 0.000198, 250: 0.000498, 500: 0.000998, 501: 0.001, 502: 0.001}
+    for i, lr in ref.items():
+        assert abs(TE.warmup_lr(1e-3, i, 500) - lr) < 1e-12, i
+
+
+def test_log_res_appends_the_reference_line_format(tmp_path):
+    cfg = Config("NRMS_V0_DEMO").__nrms__()
+    cfg.log_path = str(tmp_path / "logs" / "NRMS_V0_DEMO")
+    TE.log_res(cfg, 0.6123, 5000)      # called (auc, total_batch) like train_eval.py:139
+    TE.log_res(cfg, 0.65, "epoch_0")
+    lines = open(cfg.log_path + "/res.txt").read().splitlines()
+    assert len(lines) == 2 and lines[0].endswith("_5000_:auc_0.6123") and lines[1].endswith("_epoch_0_:auc_0.65")
+
+
+def test_test_without_a_checkpoint_raises(tmp_path):
+    cfg = Config("NRMS_V0_DEMO").__nrms__()
+    cfg.save_path = str(tmp_path) + "/"
+    with pytest.raises(FileNotFoundError):
+        TE.test(cfg, None, [], None, test_list_nums=[1])
