@@ -13,6 +13,7 @@
 #include "attention_mma.cuh"
 #include "attention_hp.cuh"
 #include "attention_hpn.cuh"
+#include "attention_hpl.cuh"
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gather.cuh"
@@ -96,14 +97,18 @@ constexpr int kWqkvRows = 1024, kWaRows = 256;
 
 inline int mask_bytes_for(int D) { return (int)align_up(ceil_div(D, 8), 4); }
 
-// Head-padded Q|K|V ("HP", gemm_img.cuh: hp_unpad; attention_hp.cuh, attention_hpn.cuh): tensor-core
-// GEMM modes, sequences of at most 64 tokens, even head dim <= 32, 3*32*h <= 960 projection columns.
+// Head-padded Q|K|V ("HP", gemm_img.cuh: hp_unpad; attention_hp.cuh, attention_hpn.cuh, attention_hpl.cuh):
+// tensor-core GEMM modes, sequences of at most 256 tokens, even head dim <= 32, 3*32*h <= 960 projection
+// columns.
 inline bool use_hp(const nrms_encoder_dims& d) {
     const int dk = d.d_model / d.n_heads;
-    return d.gemm_mode >= 1 && d.seq_len <= 64 && dk % 2 == 0 && dk <= 32 && 96 * d.n_heads <= 960;
+    return d.gemm_mode >= 1 && d.seq_len <= 256 && dk % 2 == 0 && dk <= 32 && 96 * d.n_heads <= 960;
 }
 inline int hp_cols(const nrms_encoder_dims& d) { return 96 * d.n_heads; }
-inline int hp_rows(const nrms_encoder_dims& d) { return d.seq_len <= 32 ? 32 : 64; }   // rows per head block
+// rows per head block: 32 / 64 (one- and several-warp kernels), a multiple of 16 beyond (key-tiled kernels)
+inline int hp_rows(const nrms_encoder_dims& d) {
+    return d.seq_len <= 32 ? 32 : d.seq_len <= 64 ? 64 : (int)align_up(d.seq_len, 16);
+}
 
 struct Saved {
     float* qkv;      // [M, 3D] fp32; HP: bf16 planes hi [M, NP] then lo [M, NP]
@@ -395,7 +400,20 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
             a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
             const long long items = (long long)d.n_seq * h;
-            if (L > 32) {
+            if (L > 64) {
+                // one CTA per (sequence, head), a warp per 16 rows, keys in tiles of 64 with an online softmax
+                // (attention_hpl.cuh)
+                const size_t smem = attn_hpl_fwd_smem_bytes(L);
+                const unsigned grid = (unsigned)std::min<long long>(items, 8ll * kNumSMs);
+                const int threads = hpl_warps(L) * 32;
+                if (terms == 3) {
+                    if ((rc = set_smem(attn_hpl_fwd_kernel<3>, smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_hpl_fwd_kernel<3><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
+                } else {
+                    if ((rc = set_smem(attn_hpl_fwd_kernel<1>, smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_hpl_fwd_kernel<1><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
+                }
+            } else if (L > 32) {
                 // four warps per (sequence, head) over 64-row blocks (attention_hpn.cuh)
                 using C = HpN<64>;
                 const size_t smem = (size_t)C::ITEMS_FWD * C::ITEM_FWD;
@@ -573,8 +591,21 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
                     a.cmask = nullptr;   // d_ctx arrives with the context-dropout mask applied (dgrad GEMM epilogue)
                 const long long items = (long long)d.n_seq * h;
-                // two (sequences of <= 32 tokens) or four warps per (sequence, head): attention_hpn.cuh
-                if (L > 32) {
+                // two (sequences of <= 32 tokens) or four warps per (sequence, head): attention_hpn.cuh;
+                // beyond 64 tokens one CTA per item in two key-/query-tiled phases: attention_hpl.cuh
+                if (L > 64) {
+                    a.ctx_img = sv.ctx_img;     // delta = dO . O comes from the saved context image
+                    const size_t smem = attn_hpl_bwd_smem_bytes(L);
+                    const unsigned grid = (unsigned)std::min<long long>(items, 8ll * kNumSMs);
+                    const int threads = hpl_warps(L) * 32;
+                    if (terms == 3) {
+                        if ((rc = set_smem(attn_hpl_bwd_kernel<3>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpl_bwd_kernel<3><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
+                    } else {
+                        if ((rc = set_smem(attn_hpl_bwd_kernel<1>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpl_bwd_kernel<1><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
+                    }
+                } else if (L > 32) {
                     using C = HpN<64>;
                     const size_t smem = (size_t)C::ITEMS_BWD * C::ITEM_BWD;
                     const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), 2 * kNumSMs);

@@ -203,25 +203,45 @@ struct IgArgs {
     int terms;                  // 3 = bf16x3 (fp32-grade), 1 = plain bf16 (hi planes only)
 };
 
-// loader warp + MMA warp + epilogue warps.  The 320-column variants have a single TMEM accumulator
-// (2 x 320 > 512 columns), so their epilogue is NOT hidden behind the next tile's main loop: they
-// run EIGHT epilogue warps, two per TMEM lane quadrant, each pair splitting the tile's columns.
-__host__ __device__ constexpr int ig_epi_warps(int n_t) { return n_t > 256 ? 8 : 4; }
+// loader warp + MMA warp + EIGHT epilogue warps: two per TMEM lane quadrant, each pair splitting the
+// tile's 32-column blocks between them (one epilogue warp per quadrant could not keep up with the main
+// loop: the split-plane and tanh epilogues are ALU-bound on a single warp per scheduler).
+//   * N_T <= 256: two accumulators (TMEM columns [0,N_T) and [256,256+N_T)), the epilogue of a tile
+//     overlaps the main loop of the next;
+//   * N_T  > 256: two accumulators do not fit 512 columns.  They are placed at columns [0,N_T) and
+//     [512-N_T,512) instead and OVERLAP in [512-N_T, N_T): the epilogue drains the overlap first and
+//     releases the accumulator then, so the next tile's main loop runs underneath the rest of the drain.
+__host__ __device__ constexpr int ig_epi_warps(int) { return 8; }
 __host__ __device__ constexpr int ig_threads(int n_t) { return 64 + 32 * ig_epi_warps(n_t); }
 
 __host__ __device__ constexpr int ig_stage_bytes(int n_t) { return 2 * A_TILE_B + 2 * n_t * IMG_ROW_B; }
 __host__ __device__ constexpr int ig_stages(int n_t) {
     return (227 * 1024 - 1280) / ig_stage_bytes(n_t) >= 4 ? 4 : (227 * 1024 - 1280) / ig_stage_bytes(n_t);
 }
-// tail after the ring: 256 B of mbarriers + TMEM slot, then 2*N_T floats of epilogue staging
-// (bias / query vector; only the N_T <= 256 variants stage anything)
-// + (N_T <= 256 only: the 320-column variants have no shared memory left) one 32x36-float
-// transposition buffer per epilogue warp for coalesced stores
-constexpr int IG_XPOSE_STRIDE = 36;
-constexpr int IG_XPOSE_BYTES = 32 * IG_XPOSE_STRIDE * 4;
-__host__ __device__ constexpr int ig_tail_bytes(int n_t) { return n_t <= 256 ? 256 + 2 * 256 * 4 + 4 * IG_XPOSE_BYTES : 384; }
+// tail after the ring: 256 B of mbarriers + TMEM slot; N_T <= 256 only (the wider variants have no shared
+// memory left): N_T floats of bias + N_T floats of query vector (EPI_TANH_DOT) + 128 floats of row-dot
+// exchange between the two warps of a quadrant + one 32 x 128-byte staging buffer per epilogue warp
+// (16-byte units XOR-swizzled by row: conflict-free without padding) for coalesced stores
+constexpr int IG_XPOSE_BYTES = 32 * 128;
+// (the query-vector and row-dot areas exist only where they fit: EPI_TANH_DOT runs with N_T = 208)
+__host__ __device__ constexpr int ig_epi_floats(int n_t) {
+    return n_t > 256 ? 0 : (n_t + 3) / 4 * 4 + (n_t <= 224 ? (n_t + 3) / 4 * 4 + 128 : 0);
+}
+__host__ __device__ constexpr int ig_tail_bytes(int n_t) {
+    return n_t <= 256 ? 256 + 4 * ig_epi_floats(n_t) + ig_epi_warps(n_t) * IG_XPOSE_BYTES : 384;
+}
 __host__ __device__ constexpr int ig_smem_bytes(int n_t) {
     return ig_stages(n_t) * ig_stage_bytes(n_t) + 1024 /*alignment slack*/ + ig_tail_bytes(n_t);
+}
+static_assert(ig_smem_bytes(256) <= 227 * 1024 && ig_smem_bytes(320) <= 227 * 1024 && ig_smem_bytes(208) <= 227 * 1024,
+              "shared-memory budget of the GEMM variants");
+
+// fp32-grade tanh for the additive-attention epilogue: 1 - 2 / (exp(2x) + 1) on ex2.approx / rcp.approx
+// (absolute error < 3e-7 over the whole range, exact limits +-1; libdevice's tanhf costs ~4x the
+// instructions, and this epilogue runs on one warp per scheduler)
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, e + 1.f);
 }
 
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -244,22 +264,30 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
     constexpr int STAGES = ig_stages(N_T);
     constexpr int STAGE_B = ig_stage_bytes(N_T);
     constexpr int B_PLANE_B = N_T * IMG_ROW_B;
-    constexpr bool DOUBLE_ACC = 2 * N_T <= 512 && !A_MN;
-    constexpr int ACC_STRIDE = 256;            // TMEM column offset of the second accumulator
+    constexpr bool DOUBLE_ACC = 2 * N_T <= 512;   // two disjoint accumulators
+    // TMEM column of the second accumulator: disjoint at 256, else as far right as it fits (overlapping
+    // the first in [ACC2, N_T))
+    constexpr int ACC2 = DOUBLE_ACC ? 256 : 512 - N_T;
     constexpr int N1 = N_T > 256 ? 256 : N_T;  // first / second UMMA of a k-step (N <= 256 each)
     constexpr int N2 = N_T - N1;
+    constexpr int EW = ig_epi_warps(N_T);
+    constexpr int N_BLK = (N_T + 31) / 32;     // 32-column blocks of a tile
+    constexpr int OV_BLK = DOUBLE_ACC ? 0 : (N_T - ACC2) / 32;   // blocks inside the overlap of the two accumulators
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(N_T % 16 == 0 && N1 % 16 == 0 && N2 % 16 == 0, "UMMA N granularity for M=128");
     static_assert(!B_MN || N_T % 64 == 0, "MN-major operands come in 64-wide blocks");
     static_assert(N_T <= 512, "TMEM has 512 columns");
+    static_assert(DOUBLE_ACC || (ACC2 % 32 == 0 && N_T % 32 == 0 && OV_BLK % 2 == 0 && (N_BLK - OV_BLK) % 2 == 0),
+                  "overlapping accumulators: whole 32-column blocks, split evenly between the two warps of a quadrant");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_B);
     // bars: [0,S) hi planes full | [S,2S) empty | [2S,2S+2) acc full | [2S+2,2S+4) acc empty | [2S+4,3S+4) lo planes full
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
-    float* s_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_B + 256);   // [2][256] floats (N_T <= 256 only)
+    float* s_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_B + 256);   // bias | query vector | row dots (N_T <= 256 only)
     constexpr bool XPOSE = N_T <= 256;   // stage the tile through shared memory for full-line stores
+    constexpr int NPAD = (N_T + 3) / 4 * 4;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = tc::smem_u32(smem);
@@ -278,7 +306,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(accf_bar(b), 1);
-            tc::mbar_init(acce_bar(b), ig_epi_warps(N_T));
+            tc::mbar_init(acce_bar(b), EW);
         }
         tc::fence_barrier_init();
     }
@@ -355,11 +383,18 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
             for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
                 const int split = w / (a.m_tiles * a.n_tiles);
                 const int c0 = split * cps, c1 = min(a.k_chunks, c0 + cps);
-                const int buf = DOUBLE_ACC ? (int)(tile_it & 1u) : 0;
-                const uint32_t use = DOUBLE_ACC ? (tile_it >> 1) : tile_it;
-                tc::mbar_wait(acce_bar(buf), (use & 1u) ^ 1u);   // epilogue has drained this accumulator
+                const int buf = (int)(tile_it & 1u);
+                if (DOUBLE_ACC) {
+                    // the epilogue of the tile two back has drained this accumulator
+                    tc::mbar_wait(acce_bar(buf), ((tile_it >> 1) & 1u) ^ 1u);
+                } else {
+                    // overlapping accumulators: the PREVIOUS tile's epilogue has drained the overlap columns (it
+                    // drains them first); the rest of that tile lies outside this tile's columns, and the tile
+                    // two back was fully drained before the previous tile's epilogue began
+                    tc::mbar_wait(acce_bar(0), (tile_it & 1u) ^ 1u);
+                }
                 tc::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC_STRIDE);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * ACC2);
                 for (int kc = c0; kc < c1; ++kc, ++it) {
                     const int s = it % STAGES;
                     tc::mbar_wait(full_bar(s), (it / STAGES) & 1u);
@@ -399,28 +434,31 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                     }
                     tc::umma_commit(empty_bar(s));   // frees the stage when these MMAs retire
                 }
-                tc::umma_commit(accf_bar(buf));      // accumulator complete
+                tc::umma_commit(accf_bar(DOUBLE_ACC ? buf : 0));      // accumulator complete
             }
         }
         __syncwarp();
     } else {
-        // =============================== epilogue (warps 2..5) =================================
+        // =============================== epilogue (warps 2..9) =================================
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
-        const int et = (warp - 2) * 32 + lane;        // 0..127 within the epilogue group
+        const int half = (warp - 2) >> 2;             // which of the quadrant's two warps
+        const int et = (warp - 2) * 32 + lane;        // 0..255 within the epilogue group
         static_assert(!(EPI == EPI_BIAS || EPI == EPI_TANH_DOT || EPI == EPI_BIAS_SPLIT) || N_T <= 256,
                       "epilogue staging holds 256 columns");
-        float* s_bias = s_epi;                        // [256]
-        float* s_qv = s_epi + 256;                    // [256] (EPI_TANH_DOT)
+        static_assert(EPI != EPI_TANH_DOT || N_T <= 224, "query-vector / row-dot staging exists for N_T <= 224 only");
+        float* s_bias = s_epi;                        // [NPAD]
+        float* s_qv = s_epi + NPAD;                   // [NPAD] (EPI_TANH_DOT)
+        float* s_dot = s_epi + 2 * NPAD;              // [128]  (EPI_TANH_DOT: second warp's partial row dots)
+        uint8_t* const s_xb = reinterpret_cast<uint8_t*>(s_epi + ig_epi_floats(N_T)) + (warp - 2) * IG_XPOSE_BYTES;
         uint32_t tile_it = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
             const int tile = w % (a.m_tiles * a.n_tiles), split = w / (a.m_tiles * a.n_tiles);
             const int m_tile = A_MN ? tile / a.n_tiles : a.m_tiles - 1 - tile / a.n_tiles, n_tile = tile % a.n_tiles;
             const int n0 = n_tile * N_T;
-            const int buf = DOUBLE_ACC ? (int)(tile_it & 1u) : 0;
-            const uint32_t use = DOUBLE_ACC ? (tile_it >> 1) : tile_it;
+            const int buf = (int)(tile_it & 1u);
             if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT || EPI == EPI_BIAS_SPLIT) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");     // previous tile's readers are done
-                for (int i = et; i < N_T; i += 128) {
+                asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's readers are done
+                for (int i = et; i < N_T; i += 256) {
                     const int n = n0 + i;
                     if (EPI == EPI_BIAS_SPLIT) {
                         const int ns = n < a.N ? hp_unpad(n, a.hp_D, a.hp_dk) : -1;
@@ -430,7 +468,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                     s_bias[i] = n < a.N ? __ldg(a.bias + n) : 0.f;
                     if (EPI == EPI_TANH_DOT) s_qv[i] = n < a.N ? __ldg(a.qv + n) : 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const int m = m_tile * 128 + q * 32 + lane;
             const bool row_ok = m < a.M;
@@ -442,31 +480,49 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
             }
             float* cbase = a.C + (EPI == EPI_PARTIAL ? (long long)split * a.c_split_stride : 0ll);
             float* crow = cbase + (long long)m * a.ldc + n0;
-            float* s_x = s_epi + 2 * 256 + (warp - 2) * (IG_XPOSE_BYTES / 4);
-            // EPI_BIAS_SPLIT: element offset of the four block rows this lane stores (row 8i + lane/4 of the
+            // EPI_BIAS_SPLIT: element offset of the four block rows this lane stores (row 8i + lane%8 of the
             // warp's 32), without the head part: ((seq * 3 * heads) * rows_per_block + l) * 32; -1 past M
             long long split_row_off[4] = {-1, -1, -1, -1};
             if (EPI == EPI_BIAS_SPLIT) {
                 const int nh = a.hp_D / a.hp_dk;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int mm = m_tile * 128 + q * 32 + 8 * i + (lane >> 2);
+                    const int mm = m_tile * 128 + q * 32 + 8 * i + (lane & 7);
                     if (mm < a.M) {
                         const int sq = mm / a.seq_len, l = mm - sq * a.seq_len;
                         split_row_off[i] = ((long long)sq * 3 * nh * a.hp_rows + l) * 32;
                     }
                 }
             }
-            tc::mbar_wait(accf_bar(buf), use & 1u);
+            tc::mbar_wait(accf_bar(DOUBLE_ACC ? buf : 0), (DOUBLE_ACC ? (tile_it >> 1) : tile_it) & 1u);
             tc::tc_fence_after();
-            const uint32_t t_row = tmem_base + (uint32_t)(buf * ACC_STRIDE) + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_row = tmem_base + (uint32_t)(buf * ACC2) + ((uint32_t)(q * 32) << 16);
             float dot = 0.f;
-            // (eight epilogue warps: warps 6..9 take the upper half of the columns)
-            constexpr int CB_SPAN = ig_epi_warps(N_T) == 8 ? N_T / 2 : N_T;
-            static_assert(ig_epi_warps(N_T) == 4 || CB_SPAN % 32 == 0, "column halves in 32-column blocks");
-            const int cb0 = ig_epi_warps(N_T) == 8 ? ((warp - 2) >> 2) * CB_SPAN : 0;
+            // Block schedule of this warp.  Disjoint accumulators: its share of the blocks in order.
+            // Overlapping accumulators: first its share of the OVERLAP blocks (local blocks [N_BLK-OV_BLK, N_BLK)
+            // of an even tile = TMEM columns [ACC2, N_T); local blocks [0, OV_BLK) of an odd tile), then the
+            // accumulator is released, then its share of the rest.
+            constexpr int H0 = (N_BLK + 1) / 2;                 // blocks of the first warp (disjoint case)
+            constexpr int MY_OV = OV_BLK / 2, MY_REST = (N_BLK - OV_BLK) / 2;
+            static_assert(DOUBLE_ACC || MY_REST >= 1, "the release point sits before the first non-overlap block");
+            const int n_mine = DOUBLE_ACC ? (half == 0 ? H0 : N_BLK - H0) : MY_OV + MY_REST;
 #pragma unroll 1
-            for (int cb = cb0; cb < cb0 + CB_SPAN; cb += 32) {
+            for (int bi = 0; bi < n_mine; ++bi) {
+                int blk;
+                if (DOUBLE_ACC) {
+                    blk = half == 0 ? bi : H0 + bi;
+                } else {
+                    const int ov0 = buf == 0 ? N_BLK - OV_BLK : 0;      // first overlap block (local numbering)
+                    const int rest0 = buf == 0 ? 0 : OV_BLK;            // first block outside the overlap
+                    blk = bi < MY_OV ? ov0 + half * MY_OV + bi : rest0 + half * MY_REST + (bi - MY_OV);
+                    if (bi == MY_OV) {
+                        // the overlap columns are in registers / stored: the next tile's main loop may start
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(acce_bar(0));
+                    }
+                }
+                const int cb = 32 * blk;
                 // keep bits of this row's 32 columns [n0 + cb, +32): one word (n0 and cb are multiples of 32),
                 // requested before the TMEM read so that its latency hides behind it
                 uint32_t mword = 0xffffffffu;
@@ -477,11 +533,10 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                 if (EPI == EPI_BIAS_SPLIT) {
                     // TMEM gives a lane one output row; 32 columns = one head of the head-padded order, i.e.
                     // one 64-byte row of a head block per plane.  The rows go through the warp's staging
-                    // buffer so that a store instruction writes 8 consecutive block rows = 512 contiguous
-                    // bytes (a direct store would touch 32 rows x 16 bytes: measured, the epilogue then
-                    // costs more than the main loop)
+                    // buffer (row = 128 bytes: 4 hi units, 4 lo units, unit index XOR row%8) so that a store
+                    // instruction writes 8 consecutive block rows = 512 contiguous bytes (a direct store would
+                    // touch 32 rows x 16 bytes: measured, the epilogue then costs more than the main loop)
                     if (n0 + cb < a.N) {
-                        uint8_t* sb = reinterpret_cast<uint8_t*>(s_x);
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -489,21 +544,25 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                             split2(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, hi[2 * j], lo[2 * j]);
                             split2(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w, hi[2 * j + 1], lo[2 * j + 1]);
                         }
+                        const int l7 = lane & 7;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            *reinterpret_cast<uint4*>(sb + lane * (IG_XPOSE_STRIDE * 4) + 16 * j) =
+                            *reinterpret_cast<uint4*>(s_xb + lane * 128 + ((j ^ l7) << 4)) =
                                 make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            *reinterpret_cast<uint4*>(sb + lane * (IG_XPOSE_STRIDE * 4) + 64 + 16 * j) =
+                            *reinterpret_cast<uint4*>(s_xb + lane * 128 + (((4 + j) ^ l7) << 4)) =
                                 make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                         }
                         __syncwarp();
-                        const long long jpart = (long long)((n0 + cb) >> 5) * a.hp_rows * 32 + (lane & 3) * 8;
+                        // lane -> (row 8i + lane%8, unit lane/8): the 8 lanes of a shared-memory phase read 8
+                        // different rows of one unit = 8 different bank groups
+                        const int u = lane >> 3;
+                        const long long jpart = (long long)((n0 + cb) >> 5) * a.hp_rows * 32 + u * 8;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             if (split_row_off[i] >= 0) {
-                                const int rr = 8 * i + (lane >> 2);
-                                const uint4 h4 = *reinterpret_cast<const uint4*>(sb + rr * (IG_XPOSE_STRIDE * 4) + 16 * (lane & 3));
-                                const uint4 l4 = *reinterpret_cast<const uint4*>(sb + rr * (IG_XPOSE_STRIDE * 4) + 64 + 16 * (lane & 3));
+                                const int rr = 8 * i + l7;      // rr % 8 == l7
+                                const uint4 h4 = *reinterpret_cast<const uint4*>(s_xb + rr * 128 + ((u ^ l7) << 4));
+                                const uint4 l4 = *reinterpret_cast<const uint4*>(s_xb + rr * 128 + (((4 + u) ^ l7) << 4));
                                 *reinterpret_cast<uint4*>(a.Chi + split_row_off[i] + jpart) = h4;
                                 *reinterpret_cast<uint4*>(a.Clo + split_row_off[i] + jpart) = l4;
                             }
@@ -534,7 +593,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         o.x += s_bias[n]; o.y += s_bias[n + 1]; o.z += s_bias[n + 2]; o.w += s_bias[n + 3];
                     }
                     if (EPI == EPI_TANH_DOT) {
-                        o.x = tanhf(o.x); o.y = tanhf(o.y); o.z = tanhf(o.z); o.w = tanhf(o.w);
+                        o.x = tanh_fast(o.x); o.y = tanh_fast(o.y); o.z = tanh_fast(o.z); o.w = tanh_fast(o.w);
                         dot = fmaf(o.x, s_qv[n], dot); dot = fmaf(o.y, s_qv[n + 1], dot);
                         dot = fmaf(o.z, s_qv[n + 2], dot); dot = fmaf(o.w, s_qv[n + 3], dot);
                     }
@@ -553,14 +612,14 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         o.w = (bits & 8u) ? o.w * a.mask_scale : 0.f;
                     }
                     if (XPOSE) {
-                        *reinterpret_cast<float4*>(s_x + lane * IG_XPOSE_STRIDE + 4 * g) = o;
+                        *reinterpret_cast<float4*>(s_xb + lane * 128 + ((g ^ (lane & 7)) << 4)) = o;
                     } else {
                         if (row_ok && n0 + n < a.N) *reinterpret_cast<float4*>(crow + n) = o;
                     }
                 }
                 if (XPOSE) {
                     // TMEM gives a lane one ROW; a direct store would touch 32 lines per instruction.
-                    // Through the warp's 32x36 buffer a store instruction writes 4 rows x 128 B.
+                    // Through the warp's swizzled 32 x 128-byte buffer a store instruction writes 4 rows x 128 B.
                     __syncwarp();
                     const int cc = lane & 7;
                     const int n = cb + 4 * cc;
@@ -570,19 +629,27 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                             const int rr = 4 * i + (lane >> 3);
                             const int mm = m_tile * 128 + q * 32 + rr;
                             if (mm < a.M) {
-                                const float4 v = *reinterpret_cast<const float4*>(s_x + rr * IG_XPOSE_STRIDE + 4 * cc);
-                                *reinterpret_cast<float4*>(cbase + (long long)mm * a.ldc + n0 + n) = v;
+                                const float4 v4 = *reinterpret_cast<const float4*>(s_xb + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                                *reinterpret_cast<float4*>(cbase + (long long)mm * a.ldc + n0 + n) = v4;
                             }
                         }
                     }
                     __syncwarp();
                 }
             }
-            if (EPI == EPI_TANH_DOT && row_ok) a.dot_out[m] = dot;
-            // release the accumulator
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acce_bar(buf));
+            if (EPI == EPI_TANH_DOT) {
+                // a row's dot with the query vector = the partials of the quadrant's two warps, added in a fixed order
+                if (half == 1) s_dot[q * 32 + lane] = dot;
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+                if (half == 0 && row_ok) a.dot_out[m] = dot + s_dot[q * 32 + lane];
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // s_dot may be rewritten by the next tile
+            }
+            if (DOUBLE_ACC) {
+                // release the accumulator
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(acce_bar(buf));
+            }
         }
     }
     tc::tc_fence_before();
