@@ -115,6 +115,13 @@ int nrms_news_encoder_bwd_phase(const nrms_encoder_dims* d, const int64_t* ids, 
 /* UserEncoder.forward (nrms_v0.py:188-199): x [n_seq, seq_len, d_model] -> out [n_seq, d_model] */
 int nrms_user_encoder_fwd(const nrms_encoder_dims* d, const float* x, const float* params,
                           float* out, void* saved, int64_t saved_bytes, nrms_stream_t stream);
+/* The same encoder with its input rows GATHERED by id from a vector table (cached-vector scoring,
+ * BASELINE cfg4: the clicked-news vectors are rows of the news-vector cache built once with
+ * get_news_vector, nrms_v0.py:278-299): x[s, l, :] = table[ids[s, l], :], table [d->vocab, d_model].
+ * Needs gemm_mode >= 1 (the gather writes the GEMM operand image directly). */
+int nrms_user_encoder_fwd_gather(const nrms_encoder_dims* d, const int64_t* ids, const float* table,
+                                 const float* params, float* out, void* saved, int64_t saved_bytes,
+                                 nrms_stream_t stream);
 int nrms_user_encoder_bwd(const nrms_encoder_dims* d, const float* x, const float* params,
                           const float* d_out, const void* saved, int64_t saved_bytes,
                           void* scratch, int64_t scratch_bytes, float* d_params, float* d_x,
@@ -124,6 +131,12 @@ int nrms_user_encoder_bwd(const nrms_encoder_dims* d, const float* x, const floa
  *   cand [B,C,D], user [B,D], mask [B,C] uint8 (may be NULL) -> logits [B,C] (pad = -1e9) */
 int nrms_score_fwd(int32_t B, int32_t C, int32_t D, const float* cand, const float* user,
                    const uint8_t* mask, float* logits, nrms_stream_t stream);
+/* get_prediction over cached vectors (nrms_v0.py:301-312 + the -1e9 fill of :272-274):
+ *   logits[b, c] = vecs[cand_ids[b, c]] . user[b]; vecs [n_vecs, D], cand_ids [B,S] int64, mask [B,S]
+ *   uint8 or NULL.  No [B,S,D] candidate tensor is materialised. */
+int nrms_score_cached(int32_t B, int32_t S, int32_t D, const float* vecs, int64_t n_vecs,
+                      const int64_t* cand_ids, const float* user, const uint8_t* mask, float* logits,
+                      nrms_stream_t stream);
 /* its backward: d_logits [B,C] -> d_cand [B,C,D], d_user [B,D] (masked slots get 0) */
 int nrms_score_bwd(int32_t B, int32_t C, int32_t D, const float* cand, const float* user,
                    const uint8_t* mask, const float* d_logits, float* d_cand, float* d_user,
@@ -174,6 +187,11 @@ int nrms_rank_metrics(const float* scores, const uint8_t* labels, const int64_t*
 int nrms_rank_metrics_padded(const float* scores, int64_t row_stride, const uint8_t* labels,
                              const int64_t* offsets, int64_t n_impr, int32_t max_len,
                              double* out, nrms_stream_t stream);
+/* Same with BOTH sides padded, the layout an eval batch has (data_handler.py:174-177,236-250):
+ * impression i owns scores[i*row_stride ..] and labels[i*label_stride ..], lens[i] real candidates. */
+int nrms_rank_metrics_rows(const float* scores, int64_t row_stride, const uint8_t* labels,
+                           int64_t label_stride, const int64_t* lens, int64_t n_impr, int32_t max_len,
+                           double* out, nrms_stream_t stream);
 
 /* Batch assembly on the device: MyDataset.__getitem__ + default_collate of data_handler.py:185-250
  * for the keys the NRMS path reads, in ONE launch.  Inputs are the sample matrices packed once on

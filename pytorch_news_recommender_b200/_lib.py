@@ -54,8 +54,10 @@ SIGNATURES = {
     "nrms_news_encoder_bwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P]),
     "nrms_news_encoder_bwd_phase": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I32, _P]),
     "nrms_user_encoder_fwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P]),
+    "nrms_user_encoder_fwd_gather": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P]),
     "nrms_user_encoder_bwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P]),
     "nrms_score_fwd": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "nrms_score_cached": (C.c_int, [_I32, _I32, _I32, _P, _I64, _P, _P, _P, _P, _P]),
     "nrms_score_bwd": (C.c_int, [_I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "nrms_score_ce_fwd_bwd": (C.c_int, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nrms_embedding_plan_bytes": (_I64, [_I64, _I32]),
@@ -65,6 +67,7 @@ SIGNATURES = {
     "nrms_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _F, _F, _F, _F, _F, _P]),
     "nrms_rank_metrics": (C.c_int, [_P, _P, _P, _I64, _I32, _P, _P]),
     "nrms_rank_metrics_padded": (C.c_int, [_P, _I64, _P, _P, _I64, _I32, _P, _P]),
+    "nrms_rank_metrics_rows": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _I32, _P, _P]),
     "nrms_assemble_batch": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "nrms_rank_positions": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     "nrms_gather_rows_f32": (C.c_int, [_P, _I64, _I32, _P, _I64, _I64, _P, _P]),

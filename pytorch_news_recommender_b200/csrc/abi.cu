@@ -328,6 +328,7 @@ ig::IgArgs ig_args(const ig::Img& A, const ig::Img& B, float* C, int ldc, int M,
 int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_or_table,
                 const float* params, float* out, void* saved_blob, int64_t saved_bytes,
                 bool news, cudaStream_t s) {
+    const ProfileScope prof_scope(news ? "" : "@user");
     const Saved sv = saved_layout(saved_blob, d);
     if (saved_bytes < sv.bytes)
         return fail(NRMS_ERR_WORKSPACE, "saved blob %lld < %lld bytes", (long long)saved_bytes,
@@ -346,9 +347,13 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
     // 1. embedding gather + embedding dropout (nrms_v0.py:166) -> GEMM operand.  The user
     //    encoder's input is already a matrix: identity gather into an image (mode 1 only).
     const float* x_f32 = x_or_table;
+    if (!tcm && !news && ids != nullptr)
+        return fail(NRMS_ERR_BAD_SHAPE, "the gathering user encoder needs a tensor-core GEMM mode (gemm_mode >= 1)");
     if (news || tcm) {
         GatherArgs g{};
-        g.table = x_or_table; g.ids = news ? ids : nullptr; g.M = M; g.vocab = news ? d.vocab : M; g.D = D;
+        // ids == nullptr: identity (the user encoder over a dense [n_seq*L, D] input); the user encoder may also
+        // gather its rows from a vector table by id (cached-vector scoring: nrms_user_encoder_fwd_gather)
+        g.table = x_or_table; g.ids = ids; g.M = M; g.vocab = ids ? d.vocab : M; g.D = D;
         g.x_f32 = tcm ? nullptr : sv.x_f32;
         if (tcm) g.x_img = sv.x_img;
         g.mask = sv.xmask; g.mask_bytes = mb;
@@ -509,6 +514,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 int64_t saved_bytes, void* scratch_blob, int64_t scratch_bytes, float* d_params,
                 float* d_x, bool news, int phases, cudaStream_t s) {
     (void)ids;
+    const ProfileScope prof_scope(news ? "" : "@user");
     const Saved sv = saved_layout(const_cast<void*>(saved_blob), d);
     if (saved_bytes < sv.bytes)
         return fail(NRMS_ERR_WORKSPACE, "saved blob %lld < %lld bytes", (long long)saved_bytes,
@@ -830,6 +836,17 @@ int nrms_user_encoder_fwd(const nrms_encoder_dims* d, const float* x, const floa
     return encoder_fwd(dd, nullptr, x, params, out, saved, saved_bytes, false,
                        (cudaStream_t)stream);
 }
+int nrms_user_encoder_fwd_gather(const nrms_encoder_dims* d, const int64_t* ids, const float* table,
+                                 const float* params, float* out, void* saved, int64_t saved_bytes,
+                                 nrms_stream_t stream) {
+    int rc = check_dims(d, true);
+    if (rc) return rc;
+    NRMS_REQUIRE_PTR(ids); NRMS_REQUIRE_PTR(table); NRMS_REQUIRE_PTR(params); NRMS_REQUIRE_PTR(out);
+    NRMS_REQUIRE_PTR(saved);
+    nrms_encoder_dims dd = *d;
+    dd.dropout_p = 0.f;
+    return encoder_fwd(dd, ids, table, params, out, saved, saved_bytes, false, (cudaStream_t)stream);
+}
 int nrms_user_encoder_bwd(const nrms_encoder_dims* d, const float* x, const float* params,
                           const float* d_out, const void* saved, int64_t saved_bytes,
                           void* scratch, int64_t scratch_bytes, float* d_params, float* d_x,
@@ -859,6 +876,20 @@ int nrms_score_fwd(int32_t B, int32_t C, int32_t D, const float* cand, const flo
     ScoreArgs a{};
     a.cand = cand; a.user = user; a.mask = mask; a.logits = logits; a.B = B; a.C = C; a.D = D;
     NRMS_LAUNCH("score_0", (cudaStream_t)stream, score_kernel<0><<<B, 256, C * sizeof(float), (cudaStream_t)stream>>>(a));
+    NRMS_CHECK_CUDA(cudaGetLastError());
+    return NRMS_OK;
+}
+int nrms_score_cached(int32_t B, int32_t S, int32_t D, const float* vecs, int64_t n_vecs,
+                      const int64_t* cand_ids, const float* user, const uint8_t* mask, float* logits,
+                      nrms_stream_t stream) {
+    int rc = score_check(B, S, D);
+    if (rc) return rc;
+    if (D % 4 || n_vecs < 1) return fail(NRMS_ERR_BAD_SHAPE, "D=%d must be a multiple of 4, n_vecs=%lld >= 1", D, (long long)n_vecs);
+    NRMS_REQUIRE_PTR(vecs); NRMS_REQUIRE_PTR(user); NRMS_REQUIRE_PTR(logits);
+    if (!cand_ids) return fail(NRMS_ERR_NULL, "cand_ids is NULL");
+    ScoreCachedArgs a{vecs, n_vecs, cand_ids, user, mask, logits, B, S, D};
+    NRMS_LAUNCH("score_cached", (cudaStream_t)stream,
+                score_cached_kernel<<<B, 256, D * sizeof(float), (cudaStream_t)stream>>>(a));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -999,6 +1030,23 @@ int nrms_rank_metrics_padded(const float* scores, int64_t row_stride, const uint
                     max_len);
     return metrics_impl(scores, row_stride, labels, offsets, n_impr, max_len, out,
                         (cudaStream_t)stream);
+}
+
+int nrms_rank_metrics_rows(const float* scores, int64_t row_stride, const uint8_t* labels,
+                           int64_t label_stride, const int64_t* lens, int64_t n_impr, int32_t max_len,
+                           double* out, nrms_stream_t stream) {
+    if (n_impr < 1 || max_len < 1 || max_len > 8192 || row_stride < max_len || label_stride < max_len)
+        return fail(NRMS_ERR_BAD_SHAPE, "n_impr=%lld max_len=%d row_stride=%lld label_stride=%lld", (long long)n_impr,
+                    max_len, (long long)row_stride, (long long)label_stride);
+    if (!scores || !labels || !lens || !out) return fail(NRMS_ERR_NULL, "NULL argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t smem = (size_t)kMetricWarps * max_len * (sizeof(float) + 1);
+    NRMS_CHECK_CUDA(cudaFuncSetAttribute(rank_metrics_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = grid_for(n_impr * 32, kMetricWarps * 32, 8);
+    NRMS_LAUNCH("rank_metrics", s, rank_metrics_kernel<<<grid, kMetricWarps * 32, smem, s>>>(
+        scores, row_stride, labels, nullptr, n_impr, max_len, out, label_stride, lens));
+    NRMS_CHECK_CUDA(cudaGetLastError());
+    return NRMS_OK;
 }
 
 int nrms_assemble_batch(const int64_t* index, int32_t B, const int64_t* browsed_ids,

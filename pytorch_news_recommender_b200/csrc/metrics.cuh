@@ -16,7 +16,8 @@ constexpr int kMetricWarps = 8;
 __global__ void __launch_bounds__(kMetricWarps * 32) rank_metrics_kernel(
     const float* __restrict__ scores, long long row_stride /* <0: ragged by offsets */,
     const uint8_t* __restrict__ labels, const int64_t* __restrict__ offsets, long long n_impr,
-    int max_n, double* __restrict__ out) {
+    int max_n, double* __restrict__ out, long long label_stride = -1 /* >= 0: labels padded [n_impr, label_stride] */,
+    const int64_t* __restrict__ lens = nullptr /* with label_stride: candidates per impression */) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* s = reinterpret_cast<float*>(smraw) + (size_t)warp * max_n;
@@ -24,8 +25,8 @@ __global__ void __launch_bounds__(kMetricWarps * 32) rank_metrics_kernel(
     const double kNaN = __longlong_as_double(0x7ff8000000000000LL);
     for (long long imp = (long long)blockIdx.x * kMetricWarps + warp; imp < n_impr;
          imp += (long long)gridDim.x * kMetricWarps) {
-        const long long o0 = offsets[imp];
-        const int n = (int)(offsets[imp + 1] - o0);
+        const long long o0 = label_stride >= 0 ? imp * label_stride : offsets[imp];
+        const int n = (int)(label_stride >= 0 ? lens[imp] : offsets[imp + 1] - o0);
         double* res = out + imp * 4;
         if (n <= 0 || n > max_n) {
             if (lane < 4) res[lane] = kNaN;

@@ -14,9 +14,15 @@ namespace nrms {
 
 struct Profiler {
     struct Rec {
-        const char* name;
+        std::string name;
         cudaEvent_t a, b;
     };
+    // suffix appended to the names recorded by this thread ("" or "@user": the user encoder's launches
+    // of the shared kernels are reported separately from the news encoder's)
+    static const char*& scope() {
+        static thread_local const char* s = "";
+        return s;
+    }
     std::mutex mu;
     bool on = false;
     long long launches = 0;
@@ -41,7 +47,7 @@ struct Profiler {
         std::lock_guard<std::mutex> g(mu);
         ++launches;
         if (!on) return;
-        Rec r{name, ev(), ev()};
+        Rec r{std::string(name) + scope(), ev(), ev()};
         cudaEventRecord(r.a, s);
         recs.push_back(r);
     }
@@ -74,6 +80,12 @@ struct Profiler {
         }
         return out;
     }
+};
+
+struct ProfileScope {
+    const char* prev;
+    explicit ProfileScope(const char* s) : prev(Profiler::scope()) { Profiler::scope() = s; }
+    ~ProfileScope() { Profiler::scope() = prev; }
 };
 
 #define NRMS_LAUNCH(name, stream, ...)                \

@@ -114,6 +114,49 @@ __global__ void __launch_bounds__(256) score_kernel(const ScoreArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Cached-vector scoring (BASELINE cfg4; reference hooks get_prediction nrms_v0.py:301-312 over
+// get_news_vector :278-289): logits[b, c] = vecs[cand_ids[b, c]] . user[b] straight from the news-vector
+// cache — no [B, S, D] candidate tensor is materialised, padded slots (mask == 0) get -1e9
+// (nrms_v0.py:272-274) without touching the cache.  One CTA per impression, one warp per candidate
+// slot (looping); the cache (65 k x 1.2 KB) is L2-resident.
+// ---------------------------------------------------------------------------------------
+struct ScoreCachedArgs {
+    const float* vecs;        // [n_vecs, D]
+    long long n_vecs;
+    const int64_t* cand_ids;  // [B, S]
+    const float* user;        // [B, D]
+    const uint8_t* mask;      // [B, S] or nullptr
+    float* logits;            // [B, S]
+    int B, S, D;
+};
+__global__ void __launch_bounds__(256) score_cached_kernel(const ScoreCachedArgs a) {
+    extern __shared__ float su[];   // D floats: this impression's user vector
+    const int b = blockIdx.x, S = a.S, D = a.D;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) su[d] = __ldg(a.user + (long long)b * D + d);
+    __syncthreads();
+    const int d4 = D >> 2;          // D % 4 == 0
+    for (int c = warp; c < S; c += nw) {
+        const long long o = (long long)b * S + c;
+        float s = -1e9f;
+        if (a.mask == nullptr || a.mask[o] != 0) {
+            const long long id = a.cand_ids[o];
+            s = 0.f;
+            if (id >= 0 && id < a.n_vecs) {
+                const float4* row = reinterpret_cast<const float4*>(a.vecs + id * D);
+                for (int i = lane; i < d4; i += 32) {
+                    const float4 v = __ldg(row + i);
+                    const float4 u = *reinterpret_cast<const float4*>(su + 4 * i);
+                    s = fmaf(v.x, u.x, s); s = fmaf(v.y, u.y, s); s = fmaf(v.z, u.z, s); s = fmaf(v.w, u.w, s);
+                }
+            }
+            s = warp_sum(s);
+        }
+        if (lane == 0) a.logits[o] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Embedding gradient: counting sort of token rows by vocab id, then a load-balanced
 // segmented reduction (one warp per 32 sorted rows) into the dense table gradient.
 // Replaces 55 x (zero-fill [V,D] + scatter + accumulate) of the reference.

@@ -127,6 +127,20 @@ def user_encoder_fwd(shape: EncoderShape, x, params, saved, gemm_mode=0, out=Non
     return out
 
 
+def user_encoder_fwd_gather(shape: EncoderShape, ids, table, params, saved, gemm_mode=1, out=None):
+    """UserEncoder.forward over rows gathered by id from a vector table: x[s, l] = table[ids[s, l]]
+    (shape.vocab = rows of the table).  No [n_seq, L, D] input tensor is materialised."""
+    _require_cuda(ids, table, params, saved)
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        raise NrmsError("ids must be contiguous int64")
+    if out is None:
+        out = torch.empty((shape.n_seq, shape.d_model), dtype=torch.float32, device=table.device)
+    d = shape.dims(0.0, 0, gemm_mode)
+    check(_lib.load().nrms_user_encoder_fwd_gather(d, ptr(ids), ptr(table), ptr(params), ptr(out), ptr(saved),
+                                                   saved.numel(), _stream()), "nrms_user_encoder_fwd_gather")
+    return out
+
+
 def user_encoder_bwd(shape: EncoderShape, x, params, d_out, saved, scratch, d_params, d_x,
                      gemm_mode=0):
     _require_cuda(x, params, d_out, saved, scratch, d_params, d_x)
@@ -144,6 +158,18 @@ def score_fwd(cand, user, mask):
     check(_lib.load().nrms_score_fwd(B, Cn, D, ptr(cand), ptr(user), ptr(mask), ptr(logits),
                                      _stream()), "nrms_score_fwd")
     return logits
+
+
+def score_cached(vecs, cand_ids, user, mask, out=None):
+    """logits[b, c] = vecs[cand_ids[b, c]] . user[b] (padded slots -1e9) straight from the vector cache."""
+    _require_cuda(vecs, cand_ids, user, mask)
+    B, S = cand_ids.shape
+    D = vecs.shape[1]
+    if out is None:
+        out = torch.empty((B, S), dtype=torch.float32, device=vecs.device)
+    check(_lib.load().nrms_score_cached(B, S, D, ptr(vecs), vecs.shape[0], ptr(cand_ids), ptr(user), ptr(mask),
+                                        ptr(out), _stream()), "nrms_score_cached")
+    return out
 
 
 def score_bwd(cand, user, mask, d_logits, d_cand=None, d_user=None):
@@ -215,6 +241,18 @@ def rank_metrics(scores, labels, offsets, max_len: int, row_stride: Optional[int
         check(lib.nrms_rank_metrics_padded(ptr(scores), int(row_stride), ptr(labels), ptr(offsets), n,
                                            int(max_len), ptr(out), _stream()),
               "nrms_rank_metrics_padded")
+    return out
+
+
+def rank_metrics_rows(scores, labels, lens, out=None):
+    """Padded on both sides: scores float32 [N, S], labels uint8 [N, S], lens int64 [N] real candidates
+    per impression.  Returns float64 [N, 4] = AUC, MRR, nDCG@5, nDCG@10 (`out` may be a preallocated slice)."""
+    _require_cuda(scores, labels, lens)
+    n, S = scores.shape
+    if out is None:
+        out = torch.empty((n, 4), dtype=torch.float64, device=scores.device)
+    check(_lib.load().nrms_rank_metrics_rows(ptr(scores), scores.stride(0), ptr(labels), labels.stride(0), ptr(lens),
+                                             n, S, ptr(out), _stream()), "nrms_rank_metrics_rows")
     return out
 
 

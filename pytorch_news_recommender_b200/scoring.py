@@ -63,52 +63,91 @@ class CachedScorer:
     @torch.no_grad()
     def score(self, browsed_ids: torch.Tensor, candidate_ids: torch.Tensor,
               candidate_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """[B, H] and [B, S] news ids (+ optional uint8 mask) -> logits [B, S] (padded = -1e9)."""
-        from .engine import weights_version
+        """[B, H] and [B, S] news ids (+ optional uint8 mask) -> logits [B, S] (padded = -1e9).
+
+        Tensor-core GEMM modes: two C-ABI calls per batch — the user encoder gathers its rows from the
+        cache by id (`nrms_user_encoder_fwd_gather`), and the scorer dots the cached candidate vectors
+        with the user vector by id (`nrms_score_cached`); neither the [B, H, D] history tensor nor the
+        [B, S, D] candidate tensor (S = 300 padded slots) is materialised.  gemm_mode 0 keeps the three
+        explicit steps (gather, get_user_vector, score)."""
+        from .engine import _blobs, encoder_param_list, pack_params, weights_version
+        from .model.nrms_v0 import _gemm_mode
         if self.news_vecs is None or self._cache_version != weights_version(self.model):
             self.build_cache()          # first use, or the weights changed since the cache was built
         dev = self.device
         b_ids = browsed_ids.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
         c_ids = candidate_ids.to(dev, dtype=torch.int64, non_blocking=True).contiguous()
+        mask = None if candidate_mask is None else candidate_mask.to(dev, dtype=torch.uint8, non_blocking=True).contiguous()
         B, H = b_ids.shape
         S = c_ids.shape[1]
         D = self.news_vecs.shape[1]
+        cfg = self.model.config
+        gm = _gemm_mode(cfg)
+        if gm >= 1:
+            params = encoder_param_list(self.model.user_encoder)
+            shape = ops.EncoderShape(B, H, D, cfg.num_attention_heads, params[8].numel(), self.news_vecs.shape[0])
+            blob = _blobs.get("infer_saved", ops.saved_bytes(shape, gm), dev)
+            user = ops.user_encoder_fwd_gather(shape, b_ids, self.news_vecs, pack_params(params), blob, gm)
+            return ops.score_cached(self.news_vecs, c_ids, user, mask)
         hist = ops.gather_rows(self.news_vecs, b_ids.view(-1), base=0).view(B, H, D)
         cand = ops.gather_rows(self.news_vecs, c_ids.view(-1), base=0).view(B, S, D)
         was_training = self.model.training
         self.model.eval()
         user = self.model.get_user_vector(hist)
         self.model.train(was_training)
-        mask = None if candidate_mask is None else candidate_mask.to(dev, dtype=torch.uint8, non_blocking=True).contiguous()
         return ops.score_fwd(cand, user, mask)
 
     @torch.no_grad()
     def evaluate(self, impressions: Dict[str, torch.Tensor], batch: int = 4096, group=None) -> Dict[str, float]:
         """Scores `impressions` (browsed_ids, candidate_ids, candidate_mask, labels [N, S] uint8,
-        n_candidates [N]) in batches and returns the mean AUC / MRR / nDCG@5 / nDCG@10 over the
-        impressions whose metric is defined, plus counts.  Metrics never leave the GPU until the
-        final 4 sums; with a process group every rank evaluates its shard of impressions and the
-        sums are all-reduced."""
+        n_candidates [N]; host or device tensors) in batches and returns the mean AUC / MRR / nDCG@5 /
+        nDCG@10 over the impressions whose metric is defined, plus counts.  Per batch: the two scoring
+        calls above and one metrics launch that reads the padded score / label rows in place; the
+        per-impression metrics land in one [N, 4] float64 buffer that is reduced once at the end, so
+        nothing but the final 8 numbers leaves the GPU.  Host inputs are staged batch by batch on a copy
+        stream, the next batch's H2D running underneath the current batch's kernels.  With a process
+        group every rank evaluates its shard of impressions and the sums are all-reduced."""
         ex = GradientExchange(group)
         N = impressions["browsed_ids"].shape[0]
         lo, hi = shard_range(N, ex.rank, ex.world)
         dev = self.device
-        sums = torch.zeros(4, dtype=torch.float64, device=dev)
-        cnts = torch.zeros(4, dtype=torch.float64, device=dev)
-        for i in range(lo, hi, batch):
+        keys = ("browsed_ids", "candidate_ids", "candidate_mask", "labels", "n_candidates")
+        dtypes = dict(browsed_ids=torch.int64, candidate_ids=torch.int64, candidate_mask=torch.uint8,
+                      labels=torch.uint8, n_candidates=torch.int64)
+        metrics = torch.empty((max(hi - lo, 1), 4), dtype=torch.float64, device=dev)
+        main = torch.cuda.current_stream(dev)
+        copy = getattr(self, "_copy_stream", None)
+        if copy is None:
+            copy = self._copy_stream = torch.cuda.Stream(device=dev)
+
+        def stage(i):
+            """batch [i, j) on the device: slices of resident tensors, or an async copy of host slices"""
             j = min(i + batch, hi)
-            logits = self.score(impressions["browsed_ids"][i:j], impressions["candidate_ids"][i:j],
-                                impressions["candidate_mask"][i:j])
-            n_c = impressions["n_candidates"][i:j].to(dev, dtype=torch.int64)
-            S = logits.shape[1]
-            off = torch.zeros(j - i + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(n_c, 0, out=off[1:])
-            lab = impressions["labels"][i:j].to(dev)
-            keep = torch.arange(S, device=dev)[None, :] < n_c[:, None]
-            m = ops.rank_metrics(logits, lab[keep].contiguous(), off, max_len=S, row_stride=S)
-            ok = ~torch.isnan(m)
-            sums += torch.where(ok, m, torch.zeros_like(m)).sum(0)
-            cnts += ok.sum(0)
+            if all(impressions[k].is_cuda for k in keys):
+                return {k: impressions[k][i:j] for k in keys}, None
+            copy.wait_stream(main)       # the staging buffers of two batches back are free again
+            with torch.cuda.stream(copy):
+                out = {k: impressions[k][i:j].to(dev, dtype=dtypes[k], non_blocking=True) for k in keys}
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return out, ev
+
+        starts = list(range(lo, hi, batch))
+        nxt = stage(starts[0]) if starts else None
+        for n_b, i in enumerate(starts):
+            cur, ev = nxt
+            nxt = stage(starts[n_b + 1]) if n_b + 1 < len(starts) else None
+            if ev is not None:
+                main.wait_event(ev)
+                for t in cur.values():
+                    t.record_stream(main)
+            logits = self.score(cur["browsed_ids"], cur["candidate_ids"], cur["candidate_mask"])
+            ops.rank_metrics_rows(logits, cur["labels"].contiguous(), cur["n_candidates"].contiguous(),
+                                  out=metrics[i - lo:i - lo + logits.shape[0]])
+        m = metrics[:hi - lo]
+        ok = ~torch.isnan(m)
+        sums = torch.where(ok, m, torch.zeros_like(m)).sum(0)
+        cnts = ok.sum(0).to(torch.float64)
         both = ex.sum_over_ranks(torch.cat([sums, cnts]))
         sums, cnts = both[:4].cpu().numpy(), both[4:].cpu().numpy()
         mean = sums / np.maximum(cnts, 1)

@@ -1,10 +1,26 @@
 #!/usr/bin/env python
-"""Eval-only scoring throughput (BASELINE cfg4): synthetic impressions with ~37 candidates
-(clipped lognormal in [2, 300]) and 50-slot histories over a 65k-news pool, scored from cached
-news vectors with AUC / MRR / nDCG@5/10 computed on the device.
+"""Eval-only scoring throughput — BASELINE cfg4: 1,000,000 synthetic impressions with ~37 candidates
+each (clipped lognormal in [2, 300], PADDED to the 300 slots of max_candidate_size at the boundary, as
+MyDataset type=1 does: data_handler.py:174-177) and 50-slot histories over a 65k-news pool, scored from
+cached news vectors with AUC / MRR / nDCG@5/10 computed on the device.  It replaces the reference's
+`evaluate` (train_eval.py:229-273: 350 encoder calls per batch, scores to the host, a fork pool over
+sklearn).
 
-    python scripts/eval_bench.py [n_impressions=200000] [batch=8192]
-Prints one JSON line (impressions/s for cache build + scoring + metrics, device-resident ids)."""
+    python scripts/eval_bench.py [n_impressions=1000000] [batch=8192] [gemm_mode=1]
+
+Prints one JSON line:
+  value        impressions/s END TO END: the id / mask / label tensors start in PINNED HOST memory and
+               every batch's H2D copy (3.7 KB per impression at 300 padded slots) is inside the timed
+               region (staged on a copy stream under the previous batch's kernels), as is the final
+               read-back of the metric sums;
+  resident     the same with all inputs already in HBM;
+  cache_build  news vectors of the whole pool (encoded once; not part of `value`, reported beside it);
+  roofline     SURVEY.md §8(d): 105 KB algorithmic bytes per impression at C = 37 ((H + C) cached
+               vectors of 1.2 KB + ids) against the measured HBM copy bandwidth;
+  cpu_baseline the UNMODIFIED reference forward (oracle/_ref/nrms_v0.py, eval mode, 300 padded slots, the
+               loop of train_eval.py:238-251) + the reference's evaluation.py AUC on a bounded sample,
+               on this box's host cores.
+"""
 import json
 import os
 import sys
@@ -13,48 +29,129 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import bench  # noqa: E402
-from pytorch_news_recommender_b200 import synthetic as S  # noqa: E402
+from pytorch_news_recommender_b200 import _lib, synthetic as S  # noqa: E402
 from pytorch_news_recommender_b200.model import NRMS_V0  # noqa: E402
 from pytorch_news_recommender_b200.scoring import CachedScorer  # noqa: E402
 
+KEYS = ("browsed_ids", "candidate_ids", "candidate_mask", "labels", "n_candidates")
+
+
+def cpu_reference(pool, imp, n_sample, tmp):
+    """The reference's own evaluate arithmetic on `n_sample` impressions: model(datas) in eval mode over
+    300 padded candidate slots + 50 history slots (350 title encodes per impression), then
+    evaluation.auc_score per impression.  Returns (impressions/s, info) or None when not staged."""
+    from oracle import ref_runner as R
+    if not R.available():
+        return None
+    import importlib.util
+    w = bench.WORKLOAD
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rcfg = R.RefConfig(tmp + "/", "emb.npz", w["d_model"], w["n_heads"], w["d_query"], w["dropout"], torch.device("cpu"))
+    ref = R.load(cpu_proxy=True)
+    torch.manual_seed(42)
+    model = ref.Model(rcfg).to("cpu")
+    model.eval()
+    spec = importlib.util.spec_from_file_location("ref_evaluation_staged", os.path.join(R.REF_DIR, "evaluation.py"))
+    ev = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ev)
+    tt = torch.from_numpy(pool.title_table())
+    sl = slice(0, n_sample)
+    datas = {"browsed_titles": tt[imp["browsed_ids"][sl]], "candidate_titles": tt[imp["candidate_ids"][sl]],
+             "candidate_mask": imp["candidate_mask"][sl]}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        scores = model(datas).cpu().numpy()
+    aucs = [ev.auc_score(imp["y_true"][i], scores[i][:len(imp["y_true"][i])]) for i in range(n_sample)]
+    dt = time.perf_counter() - t0
+    return n_sample / dt, {"cores": cores, "kind": "reference", "auc_sample_mean": float(np.mean(aucs)),
+                           "sample": f"{n_sample} impressions x (300 padded candidate + 50 history) titles through the "
+                                     f"unmodified reference model/nrms_v0.py in eval mode (train_eval.py:238-251) + "
+                                     f"evaluation.py auc_score per impression, torch CPU {cores} threads"}
+
 
 def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
     batch = int(sys.argv[2]) if len(sys.argv) > 2 else 8192
+    gemm_mode = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     tmp = os.path.join(tempfile.gettempdir(), "nrms_bench")
     os.makedirs(tmp, exist_ok=True)
-    cfg = bench.make_config(tmp, dev, 1)
+    cfg = bench.make_config(tmp, dev, gemm_mode)
     w = bench.WORKLOAD
+    lib = _lib.load()
     torch.manual_seed(42)
     model = NRMS_V0(cfg).to(dev).eval()
     pool = S.make_news_pool(w["n_news"], w["n_words_title"], w["vocab"], seed=0)
     imp = S.make_eval_impressions(pool, n, w["history_len"], 300, seed=1)
-    # trim the padded candidate axis to the longest impression of this sample (the reference pads
-    # to max_candidate_size=300; slots beyond the longest impression are all padding)
-    smax = int(imp["n_candidates"].max())
-    dimp = {k: (v[:, :smax].contiguous().to(dev) if k in ("candidate_ids", "candidate_mask", "labels") else v.to(dev))
-            for k, v in imp.items() if torch.is_tensor(v)}
+    host = {k: imp[k].contiguous().pin_memory() for k in KEYS}
+    h2d_per_impr = sum(host[k][0:1].numel() * host[k].element_size() for k in KEYS)
     scorer = CachedScorer(model, torch.from_numpy(pool.title_table()))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     scorer.build_cache()
     torch.cuda.synchronize()
     t_cache = time.perf_counter() - t0
-    scorer.evaluate({k: v[:batch] for k, v in dimp.items()}, batch=batch)          # warm-up
+    warm = {k: v[:2 * batch] for k, v in host.items()}
+    scorer.evaluate(warm, batch=batch)          # warm-up (allocator, kernel attributes)
+    torch.cuda.synchronize()
+    # ---- end to end from pinned host memory -------------------------------------------------------
+    n0 = lib.nrms_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    res = scorer.evaluate(host, batch=batch)    # ends with the D2H read of the 8 metric sums
+    e1.record()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    launches = int(lib.nrms_launch_count() - n0)
+    # ---- the same with resident inputs (bounded to what fits comfortably: 3.7 GB per 1M impressions) --
+    dimp = {k: v.to(dev) for k, v in host.items()}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    res = scorer.evaluate(dimp, batch=batch)
+    res_r = scorer.evaluate(dimp, batch=batch)
     torch.cuda.synchronize()
-    t_eval = time.perf_counter() - t0
-    print(json.dumps({"metric": "eval_impressions_per_sec", "value": n / t_eval, "n_impressions": n,
-                      "candidate_slots": smax, "mean_candidates": float(imp["n_candidates"].float().mean()),
-                      "cache_build_s": t_cache, "news_encodes_per_sec": (pool.n_news + 1) / t_cache,
-                      "eval_s": t_eval, "metrics": res}))
+    t_res = time.perf_counter() - t0
+    assert abs(res_r["auc"] - res["auc"]) < 1e-12
+    # ---- roofline (SURVEY.md §8d): (H + C) cached vectors + ids + C scores per impression ------------
+    peaks = bench.load_peaks()
+    C = float(imp["n_candidates"].float().mean())
+    H, D = w["history_len"], w["d_model"]
+    alg_bytes = (H + C) * (D * 4 + 8) + C * 4
+    achieved = n * alg_bytes / t_res / 1e9
+    cpu = None
+    try:
+        got = cpu_reference(pool, imp, 32, tmp) if imp["y_true"] is not None or n <= 200000 else None
+        if got is None and imp["y_true"] is None:
+            small = S.make_eval_impressions(pool, 64, w["history_len"], 300, seed=1)
+            got = cpu_reference(pool, small, 32, tmp)
+        if got is not None:
+            cpu = {"value": got[0], "unit": "impressions/s", **got[1]}
+    except Exception as e:
+        cpu = {"value": None, "note": f"failed: {e!r}"}
+    print(json.dumps({
+        "metric": "eval_impressions_per_sec", "value": n / t_e2e, "unit": "impressions/s", "n_impressions": n,
+        "batch": batch, "gemm_mode": gemm_mode, "dtype": "bf16" if gemm_mode == 2 else "f32",
+        "config": {"workload": "cfg4: eval-only scoring of synthetic impressions from cached news vectors "
+                               "(T=30 H=50, 300 padded candidate slots, 65k-news pool, AUC/MRR/nDCG@5/10 on device)"},
+        "candidate_slots": 300, "mean_candidates": C,
+        "e2e": {"value": n / t_e2e, "unit": "impressions/s", "seconds": t_e2e, "h2d_bytes_per_impression": int(h2d_per_impr),
+                "h2d_bytes_total": int(h2d_per_impr) * n, "d2h_bytes_total": 64,
+                "note": "ids / masks / labels start in pinned host memory; per-batch H2D inside the timed region"},
+        "resident": {"value": n / t_res, "unit": "impressions/s", "seconds": t_res},
+        "gpu_launches": launches, "launches_per_batch": launches / max(1, (n + batch - 1) // batch),
+        "cache_build_s": t_cache, "news_encodes_per_sec": (pool.n_news + 1) / t_cache,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "algorithmic_bytes_per_impression": alg_bytes,
+                     "peak_source": peaks["source"] + " copy bandwidth", "traffic": None,
+                     "note": "resident arm; the user encoder's intermediates (projection planes, context image) still "
+                             "round-trip HBM, which is what separates this from the ceiling"},
+        "cpu_baseline": cpu, "metrics": res}))
 
 
 if __name__ == "__main__":
