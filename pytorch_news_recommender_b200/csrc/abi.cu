@@ -110,6 +110,14 @@ inline int hp_rows(const nrms_encoder_dims& d) {
     return d.seq_len <= 32 ? 32 : d.seq_len <= 64 ? 64 : (int)align_up(d.seq_len, 16);
 }
 
+// sequences of at least this many tokens take the key-tiled kernels of attention_hpl.cuh (experiment knobs:
+// NRMS_HPL_MIN_FWD / NRMS_HPL_MIN_BWD; the defaults are the measured cross-over points)
+inline int hpl_min(bool fwd) {
+    static const int f = getenv("NRMS_HPL_MIN_FWD") ? atoi(getenv("NRMS_HPL_MIN_FWD")) : 65;
+    static const int b = getenv("NRMS_HPL_MIN_BWD") ? atoi(getenv("NRMS_HPL_MIN_BWD")) : 65;
+    return fwd ? f : b;
+}
+
 struct Saved {
     float* qkv;      // [M, 3D] fp32; HP: bf16 planes hi [M, NP] then lo [M, NP]
     float* lse;      // [M, h]
@@ -405,7 +413,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
             a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
             const long long items = (long long)d.n_seq * h;
-            if (L > 64) {
+            if (L >= hpl_min(true)) {
                 // one CTA per (sequence, head), a warp per 16 rows, keys in tiles of 64 with an online softmax
                 // (attention_hpl.cuh)
                 const size_t smem = attn_hpl_fwd_smem_bytes(L);
@@ -599,7 +607,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 const long long items = (long long)d.n_seq * h;
                 // two (sequences of <= 32 tokens) or four warps per (sequence, head): attention_hpn.cuh;
                 // beyond 64 tokens one CTA per item in two key-/query-tiled phases: attention_hpl.cuh
-                if (L > 64) {
+                if (L >= hpl_min(false)) {
                     a.ctx_img = sv.ctx_img;     // delta = dO . O comes from the saved context image
                     const size_t smem = attn_hpl_bwd_smem_bytes(L);
                     const unsigned grid = (unsigned)std::min<long long>(items, 8ll * kNumSMs);

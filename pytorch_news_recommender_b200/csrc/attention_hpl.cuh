@@ -27,13 +27,14 @@ namespace nrms {
 
 constexpr int kHplMaxWarps = 16;   // 256 rows
 
-__host__ __device__ inline int hpl_rows_s(int L) { return (int)align_up(L, 64); }        // shared-memory rows
+// shared-memory rows of an operand: a whole number of key / query tiles (64 forward, 32 backward)
+__host__ __device__ inline int hpl_rows_s(int L, bool fwd) { return (int)align_up(L, fwd ? 64 : 32); }
 __host__ __device__ inline int hpl_warps(int L) { return ceil_div(L, 16); }
 __host__ __device__ inline size_t attn_hpl_fwd_smem_bytes(int L) {
-    return (size_t)hpl_rows_s(L) * (2 * 2 * kHpRowB + 8);          // K, V pairs + keep bytes
+    return (size_t)hpl_rows_s(L, true) * (2 * 2 * kHpRowB + 8);    // K, V pairs + keep bytes
 }
 __host__ __device__ inline size_t attn_hpl_bwd_smem_bytes(int L) {
-    return (size_t)hpl_rows_s(L) * (4 * 2 * kHpRowB + 8);          // Q, K, V, dO pairs + lse, delta
+    return (size_t)hpl_rows_s(L, false) * (4 * 2 * kHpRowB + 8);   // Q, K, V, dO pairs + lse, delta
 }
 
 __device__ __forceinline__ void cta_bar() { __syncthreads(); }
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(kHplMaxWarps * 32, 1) attn_hpl_fwd_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int m0 = 16 * warp, g = lane >> 2, t = lane & 3;
     const int L = a.L, D = a.D, dk = a.dk;
-    const int rows_s = hpl_rows_s(L), PLANE = rows_s * kHpRowB, PAIR = 2 * PLANE;
+    const int rows_s = hpl_rows_s(L, true), PLANE = rows_s * kHpRowB, PAIR = 2 * PLANE;
     const uint32_t Ks = (uint32_t)__cvta_generic_to_shared(sm), Vs = Ks + PAIR;
     uint8_t* smask = sm + 2 * PAIR;
     float* const stage = reinterpret_cast<float*>(sm);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kHplMaxWarps * 32, 1) attn_hpl_bwd_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const int m0 = 16 * warp, g = lane >> 2, t = lane & 3;
     const int L = a.L, D = a.D, dk = a.dk, DP = 32 * a.n_heads;
-    const int rows_s = hpl_rows_s(L), PLANE = rows_s * kHpRowB, PAIR = 2 * PLANE;
+    const int rows_s = hpl_rows_s(L, false), PLANE = rows_s * kHpRowB, PAIR = 2 * PLANE;
     const uint32_t Qs = (uint32_t)__cvta_generic_to_shared(sm), Ks = Qs + PAIR, Vs = Ks + PAIR, Gs = Vs + PAIR;
     float* const stageQ = reinterpret_cast<float*>(sm);               // dK goes over Q
     float* const stageK = reinterpret_cast<float*>(sm + PAIR);        // dQ goes over K

@@ -46,8 +46,10 @@ def test_cached_scores_equal_full_forward(gemm_mode, built_lib):
     cached = scorer.score(batch["browsed_ids"], batch["candidate_ids"], batch["candidate_mask"])
     real = batch["candidate_mask"].bool().cuda()
     assert torch.equal(cached[~real], full[~real])
+    # same arithmetic; only the summation order of the final 300-term dot differs between the by-id
+    # scorer (float4 per lane) and the [B,S,D] scorer (one column per lane)
     err = ((cached - full).abs()[real] / full.abs()[real].clamp_min(1e-3)).max().item()
-    assert err < 1e-5, err
+    assert err < 1e-4, err
 
 
 def test_eval_metrics_match_oracle(built_lib):
