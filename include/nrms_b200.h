@@ -237,6 +237,7 @@ int nrms_dropout_mask(uint64_t seed, uint32_t stream_id, float p, int64_t n_rows
  *   variant 0: C[M,N] = A[M,K] * B[N,K]^T   forward projection        (K-major  x K-major)
  *   variant 1: C[M,N] = A[M,K] * B[K,N]     data gradient, N <= 320   (K-major  x MN-major)
  *   variant 2: C[M,N] = A[K,M]^T * B[K,N]   weight gradient, N <= 320 (MN-major x MN-major, split-K)
+ *   variant 3: variant 0 on CTA pairs (tcgen05.mma.cta_group::2, M = 256 per pair of CTAs)
  * work: caller-owned scratch of nrms_gemm_selftest_bytes() bytes.  N % 4 == 0. */
 int64_t nrms_gemm_selftest_bytes(int32_t variant, int32_t M, int32_t N, int32_t K);
 int nrms_gemm_selftest(int32_t variant, const float* A, const float* B, float* C, int32_t M,

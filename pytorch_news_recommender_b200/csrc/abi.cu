@@ -110,10 +110,16 @@ inline int hp_rows(const nrms_encoder_dims& d) {
     return d.seq_len <= 32 ? 32 : d.seq_len <= 64 ? 64 : (int)align_up(d.seq_len, 16);
 }
 
+// CTA pairs (cta_group::2) for the K-major GEMMs (gemm_img.cuh: PAIR); NRMS_PAIRS=0 switches them off
+inline bool use_pairs() {
+    static const bool on = !(getenv("NRMS_PAIRS") && atoi(getenv("NRMS_PAIRS")) == 0);
+    return on;
+}
+
 // sequences of at least this many tokens take the key-tiled kernels of attention_hpl.cuh (experiment knobs:
 // NRMS_HPL_MIN_FWD / NRMS_HPL_MIN_BWD; the defaults are the measured cross-over points)
 inline int hpl_min(bool fwd) {
-    static const int f = getenv("NRMS_HPL_MIN_FWD") ? atoi(getenv("NRMS_HPL_MIN_FWD")) : 65;
+    static const int f = getenv("NRMS_HPL_MIN_FWD") ? atoi(getenv("NRMS_HPL_MIN_FWD")) : 33;
     static const int b = getenv("NRMS_HPL_MIN_BWD") ? atoi(getenv("NRMS_HPL_MIN_BWD")) : 65;
     return fwd ? f : b;
 }
@@ -383,7 +389,10 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.bias = pv.bqkv;
         g.m_tiles = sv.x_img.rows_pad / 128; g.n_tiles = ceil_div(NP, 256);
         g.k_steps = ceil_div(D, 16); g.k_chunks = ceil_div(g.k_steps, 4);
-        NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT>(g, s, "gemm_fwd_qkv")));
+        if (use_pairs())
+            NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT, true>(g, s, "gemm_fwd_qkv")));
+        else
+            NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT>(g, s, "gemm_fwd_qkv")));
     } else if (tcm) {
         NRMS_CHECK_CUDA(ig::img_pack2(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, 0, 0, pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, sv.qkv, 3 * D, M, 3 * D);
@@ -1145,9 +1154,10 @@ SelfTestLayout selftest_layout(void* blob, int variant, int M, int N, int K) {
         off += align_up(n, 1024);
         return r;
     };
-    if (variant == 0) {
+    if (variant == 0 || variant == 3) {
+        const int nt = variant == 0 ? 240 : 256;
         L.a_rows = M; L.a_chunks = ceil_div(K, 64);
-        L.b_rows = ceil_div(N, 240) * 240; L.b_chunks = L.a_chunks;
+        L.b_rows = ceil_div(N, nt) * nt; L.b_chunks = L.a_chunks;
     } else if (variant == 1) {
         L.a_rows = M; L.a_chunks = ceil_div(K, 64);
         L.b_rows = K; L.b_chunks = 5;
@@ -1166,14 +1176,14 @@ SelfTestLayout selftest_layout(void* blob, int variant, int M, int N, int K) {
 }  // namespace
 
 int64_t nrms_gemm_selftest_bytes(int32_t variant, int32_t M, int32_t N, int32_t K) {
-    if (variant < 0 || variant > 2 || M < 1 || N < 1 || K < 1) return -1;
+    if (variant < 0 || variant > 3 || M < 1 || N < 1 || K < 1) return -1;
     return selftest_layout(nullptr, variant, M, N, K).bytes;
 }
 int nrms_gemm_selftest(int32_t variant, const float* A, const float* B, float* C, int32_t M,
                        int32_t N, int32_t K, void* work, int64_t work_bytes, nrms_stream_t stream) {
-    if (variant < 0 || variant > 2 || M < 1 || N < 1 || K < 1 || N % 4)
+    if (variant < 0 || variant > 3 || M < 1 || N < 1 || K < 1 || N % 4)
         return fail(NRMS_ERR_BAD_SHAPE, "variant=%d M=%d N=%d K=%d", variant, M, N, K);
-    if (variant != 0 && N > 320) return fail(NRMS_ERR_BAD_SHAPE, "N=%d > 320 for variant %d", N, variant);
+    if (variant != 0 && variant != 3 && N > 320) return fail(NRMS_ERR_BAD_SHAPE, "N=%d > 320 for variant %d", N, variant);
     NRMS_REQUIRE_PTR(A); NRMS_REQUIRE_PTR(B); NRMS_REQUIRE_PTR(C); NRMS_REQUIRE_PTR(work);
     const SelfTestLayout L = selftest_layout(work, variant, M, N, K);
     if (work_bytes < L.bytes) return fail(NRMS_ERR_WORKSPACE, "work blob %lld < %lld", (long long)work_bytes, (long long)L.bytes);
@@ -1187,6 +1197,16 @@ int nrms_gemm_selftest(int32_t variant, const float* A, const float* B, float* C
         g.m_tiles = L.a.rows_pad / 128; g.n_tiles = ceil_div(N, 240);
         g.k_steps = ceil_div(K, 16); g.k_chunks = ceil_div(g.k_steps, 4);
         NRMS_CHECK_CUDA((ig::ig_launch<false, false, 240, ig::EPI_BIAS>(g, s, "selftest_nt")));
+    } else if (variant == 3) {
+        // variant 0's contraction on CTA pairs (cta_group::2, M = 256 per pair)
+        NRMS_CHECK_CUDA(ig::img_pack(A, M, K, K, L.a, s));
+        NRMS_CHECK_CUDA(ig::img_pack(B, N, K, K, L.b, s));
+        NRMS_CHECK_CUDA(cudaMemsetAsync(L.bias, 0, (size_t)N * 4, s));
+        ig::IgArgs g = ig_args(L.a, L.b, C, N, M, N);
+        g.bias = L.bias;
+        g.m_tiles = L.a.rows_pad / 128; g.n_tiles = ceil_div(N, 256);
+        g.k_steps = ceil_div(K, 16); g.k_chunks = ceil_div(g.k_steps, 4);
+        NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS, true>(g, s, "selftest_nt_pair")));
     } else if (variant == 1) {
         NRMS_CHECK_CUDA(ig::img_pack(A, M, K, K, L.a, s));
         NRMS_CHECK_CUDA(ig::img_pack(B, K, N, N, L.b, s));

@@ -214,9 +214,9 @@ struct IgArgs {
 __host__ __device__ constexpr int ig_epi_warps(int) { return 8; }
 __host__ __device__ constexpr int ig_threads(int n_t) { return 64 + 32 * ig_epi_warps(n_t); }
 
-__host__ __device__ constexpr int ig_stage_bytes(int n_t) { return 2 * A_TILE_B + 2 * n_t * IMG_ROW_B; }
-__host__ __device__ constexpr int ig_stages(int n_t) {
-    return (227 * 1024 - 1280) / ig_stage_bytes(n_t) >= 4 ? 4 : (227 * 1024 - 1280) / ig_stage_bytes(n_t);
+// pair = true: CTA pairs (cta_group::2) — a CTA stages its own 128 rows of A and HALF of the B tile
+__host__ __device__ constexpr int ig_stage_bytes(int n_t, bool pair = false) {
+    return 2 * A_TILE_B + 2 * (pair ? n_t / 2 : n_t) * IMG_ROW_B;
 }
 // tail after the ring: 256 B of mbarriers + TMEM slot; N_T <= 256 only (the wider variants have no shared
 // memory left): N_T floats of bias + N_T floats of query vector (EPI_TANH_DOT) + 128 floats of row-dot
@@ -230,8 +230,12 @@ __host__ __device__ constexpr int ig_epi_floats(int n_t) {
 __host__ __device__ constexpr int ig_tail_bytes(int n_t) {
     return n_t <= 256 ? 256 + 4 * ig_epi_floats(n_t) + ig_epi_warps(n_t) * IG_XPOSE_BYTES : 384;
 }
-__host__ __device__ constexpr int ig_smem_bytes(int n_t) {
-    return ig_stages(n_t) * ig_stage_bytes(n_t) + 1024 /*alignment slack*/ + ig_tail_bytes(n_t);
+__host__ __device__ constexpr int ig_stages(int n_t, bool pair = false) {
+    return (227 * 1024 - 1024 - ig_tail_bytes(n_t)) / ig_stage_bytes(n_t, pair) >= 4
+               ? 4 : (227 * 1024 - 1024 - ig_tail_bytes(n_t)) / ig_stage_bytes(n_t, pair);
+}
+__host__ __device__ constexpr int ig_smem_bytes(int n_t, bool pair = false) {
+    return ig_stages(n_t, pair) * ig_stage_bytes(n_t, pair) + 1024 /*alignment slack*/ + ig_tail_bytes(n_t);
 }
 static_assert(ig_smem_bytes(256) <= 227 * 1024 && ig_smem_bytes(320) <= 227 * 1024 && ig_smem_bytes(208) <= 227 * 1024,
               "shared-memory budget of the GEMM variants");
@@ -254,16 +258,24 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t
     return d;
 }
 // kind::f16 instruction descriptor: D=F32, A=B=BF16; major bits: 0 = K-major, 1 = MN-major
-__host__ __device__ constexpr uint32_t make_idesc2(int n, bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc2(int n, bool a_mn, bool b_mn, int m = 128) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-template <bool A_MN, bool B_MN, int N_T, int EPI>
+// PAIR = true (K-major operands only): the kernel runs as clusters of two CTAs on the two SMs of a TPC and
+// issues tcgen05.mma.cta_group::2 with M = 256: CTA r of a pair owns token tile 2p + r (its own A rows, its
+// own accumulator rows in its own TMEM, its own epilogue) and stages only HALF of the weight tile — a third
+// less operand traffic into each SM and stages small enough for a three-deep ring.  The 1-D bulk copies
+// signal mbarriers of their own CTA only, so the second CTA's MMA warp does not issue MMAs but RELAYS its
+// stage-full events to the leader (remote mbarrier arrive); the leader's tcgen05.commit multicasts the
+// stage-empty / accumulator-full events to both CTAs, and the second CTA's epilogue warps release the
+// accumulator on the leader's barrier.
+template <bool A_MN, bool B_MN, int N_T, int EPI, bool PAIR = false>
 __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArgs a) {
-    constexpr int STAGES = ig_stages(N_T);
-    constexpr int STAGE_B = ig_stage_bytes(N_T);
-    constexpr int B_PLANE_B = N_T * IMG_ROW_B;
+    constexpr int STAGES = ig_stages(N_T, PAIR);
+    constexpr int STAGE_B = ig_stage_bytes(N_T, PAIR);
+    constexpr int B_PLANE_B = (PAIR ? N_T / 2 : N_T) * IMG_ROW_B;   // B rows this CTA stages
     constexpr bool DOUBLE_ACC = 2 * N_T <= 512;   // two disjoint accumulators
     // TMEM column of the second accumulator: disjoint at 256, else as far right as it fits (overlapping
     // the first in [ACC2, N_T))
@@ -277,6 +289,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
     static_assert(N_T % 16 == 0 && N1 % 16 == 0 && N2 % 16 == 0, "UMMA N granularity for M=128");
     static_assert(!B_MN || N_T % 64 == 0, "MN-major operands come in 64-wide blocks");
     static_assert(N_T <= 512, "TMEM has 512 columns");
+    static_assert(!PAIR || (!A_MN && !B_MN && N1 % 32 == 0 && N2 % 32 == 0), "CTA pairs: K-major operands, N halves of 16 rows");
     static_assert(DOUBLE_ACC || (ACC2 % 32 == 0 && N_T % 32 == 0 && OV_BLK % 2 == 0 && (N_BLK - OV_BLK) % 2 == 0),
                   "overlapping accumulators: whole 32-column blocks, split evenly between the two warps of a quadrant");
 
@@ -284,7 +297,9 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_B);
     // bars: [0,S) hi planes full | [S,2S) empty | [2S,2S+2) acc full | [2S+2,2S+4) acc empty | [2S+4,3S+4) lo planes full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
+    //       | PAIR, leader only: [3S+4,4S+4) peer's hi planes full | [4S+4,5S+4) peer's lo planes full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5 * STAGES + 4);
+    static_assert(8 * (5 * STAGES + 4) + 4 <= 256, "barrier block");
     float* s_epi = reinterpret_cast<float*>(smem + STAGES * STAGE_B + 256);   // bias | query vector | row dots (N_T <= 256 only)
     constexpr bool XPOSE = N_T <= 256;   // stage the tile through shared memory for full-line stores
     constexpr int NPAD = (N_T + 3) / 4 * 4;
@@ -297,37 +312,51 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
     auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
     auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
     auto full_lo_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+    auto peer_hi_bar = [&](int s) { return bar_base + 8u * (3 * STAGES + 4 + s); };
+    auto peer_lo_bar = [&](int s) { return bar_base + 8u * (4 * STAGES + 4 + s); };
+    const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
+    const int worker = PAIR ? (int)tc::cluster_id_x() : (int)blockIdx.x;
+    const int n_workers = PAIR ? (int)tc::cluster_nclusters_x() : (int)gridDim.x;
+    const int m_tiles_w = PAIR ? ceil_div(a.m_tiles, 2) : a.m_tiles;     // token tiles per worker step
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(full_bar(s), 1);
             tc::mbar_init(full_lo_bar(s), 1);
             tc::mbar_init(empty_bar(s), 1);
+            tc::mbar_init(peer_hi_bar(s), 1);
+            tc::mbar_init(peer_lo_bar(s), 1);
         }
         for (int b = 0; b < 2; ++b) {
             tc::mbar_init(accf_bar(b), 1);
-            tc::mbar_init(acce_bar(b), EW);
+            tc::mbar_init(acce_bar(b), PAIR ? 2 * EW : EW);     // PAIR: both CTAs' epilogue warps release on the leader
         }
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc<512>(tc::smem_u32(tmem_slot));
+    if (warp == 1) {
+        if (PAIR) tc::tmem_alloc_pair<512>(tc::smem_u32(tmem_slot)); else tc::tmem_alloc<512>(tc::smem_u32(tmem_slot));
+    }
     tc::tc_fence_before();
     __syncthreads();
+    if (PAIR) tc::cluster_sync_all();     // the peer's barriers are initialised before anything arrives on them
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_work = a.m_tiles * a.n_tiles * a.splits;
+    const int total_work = m_tiles_w * a.n_tiles * a.splits;
     const int cps = ceil_div(a.k_chunks, a.splits);   // chunks per split
 
     if (warp == 0) {
         // =============================== loader ================================================
         if (lane == 0) {
             uint32_t it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-                const int tile = w % (a.m_tiles * a.n_tiles), split = w / (a.m_tiles * a.n_tiles);
+            for (int w = worker; w < total_work; w += n_workers) {
+                const int tile = w % (m_tiles_w * a.n_tiles), split = w / (m_tiles_w * a.n_tiles);
                 // K-major-A GEMMs walk the token tiles from the LAST one down: the producer kernel wrote the
                 // activation image in increasing row order, so its tail is what is still in the 126 MB L2
-                const int m_tile = A_MN ? tile / a.n_tiles : a.m_tiles - 1 - tile / a.n_tiles, n_tile = tile % a.n_tiles;
+                const int mt_w = A_MN ? tile / a.n_tiles : m_tiles_w - 1 - tile / a.n_tiles, n_tile = tile % a.n_tiles;
+                // PAIR: CTA r takes token tile 2p + r; an odd tile count leaves the last pair's second CTA
+                // without a tile: it re-loads the last one (its epilogue stores nothing: rows >= M)
+                const int m_tile = PAIR ? min(2 * mt_w + (int)rank, a.m_tiles - 1) : mt_w;
                 const int c0 = split * cps, c1 = min(a.k_chunks, c0 + cps);
                 for (int kc = c0; kc < c1; ++kc, ++it) {
                     const int s = it % STAGES;
@@ -361,6 +390,14 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                                 const long long off = (long long)(n_tile * (N_T / 64) + b) * a.B.chunk_stride + (long long)kc * IMG_BLOCK_B;
                                 tc::bulk_g2s(dstb + pl * B_PLANE_B + b * IMG_BLOCK_B, Bp + off, IMG_BLOCK_B, bar);
                             }
+                        } else if (PAIR) {
+                            // this CTA's half of the rows of each of the (one or two) UMMAs of a k-step
+                            const long long off = (long long)kc * a.B.chunk_stride + (long long)n_tile * N_T * IMG_ROW_B;
+                            tc::bulk_g2s(dstb + pl * B_PLANE_B, Bp + off + (long long)rank * (N1 / 2) * IMG_ROW_B,
+                                         (N1 / 2) * IMG_ROW_B, bar);
+                            if (N2 > 0)
+                                tc::bulk_g2s(dstb + pl * B_PLANE_B + (N1 / 2) * IMG_ROW_B,
+                                             Bp + off + (long long)(N1 + rank * (N2 / 2)) * IMG_ROW_B, (N2 / 2) * IMG_ROW_B, bar);
                         } else {
                             const long long off = (long long)kc * a.B.chunk_stride + (long long)n_tile * B_PLANE_B;
                             tc::bulk_g2s(dstb + pl * B_PLANE_B, Bp + off, B_PLANE_B, bar);
@@ -372,16 +409,40 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
         __syncwarp();
     } else if (warp == 1) {
         // =============================== MMA issuer ============================================
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc2(N1, A_MN, B_MN);
-            constexpr uint32_t idesc2 = make_idesc2(N2 > 0 ? N2 : 16, A_MN, B_MN);
+        if (PAIR && rank != 0) {
+            // second CTA of a pair: relay this CTA's stage-full events to the leader, which issues the MMAs
+            if (lane == 0) {
+                uint32_t it = 0;
+                for (int w = worker; w < total_work; w += n_workers) {
+                    const int split = w / (m_tiles_w * a.n_tiles);
+                    const int c0 = split * cps, c1 = min(a.k_chunks, c0 + cps);
+                    for (int kc = c0; kc < c1; ++kc, ++it) {
+                        const int s = it % STAGES;
+                        tc::mbar_wait(full_bar(s), (it / STAGES) & 1u);
+                        tc::mbar_arrive_cluster(tc::mapa_cluster(peer_hi_bar(s), 0));
+                        if (a.terms == 3) {
+                            tc::mbar_wait(full_lo_bar(s), (it / STAGES) & 1u);
+                            tc::mbar_arrive_cluster(tc::mapa_cluster(peer_lo_bar(s), 0));
+                        }
+                    }
+                }
+            }
+        } else if (lane == 0) {
+            constexpr uint32_t idesc1 = make_idesc2(N1, A_MN, B_MN, PAIR ? 256 : 128);
+            constexpr uint32_t idesc2 = make_idesc2(N2 > 0 ? N2 : 32, A_MN, B_MN, PAIR ? 256 : 128);
             constexpr uint32_t A_LBO = A_MN ? IMG_BLOCK_B : 16, B_LBO = B_MN ? IMG_BLOCK_B : 16;
             constexpr uint32_t A_ADV = A_MN ? 2048 : 32, B_ADV = B_MN ? 2048 : 32;   // bytes per K=16 step
             // second UMMA of a k-step covers columns [N1, N_T): its B rows/blocks start here
-            constexpr uint32_t B2_OFF = B_MN ? (N1 / 64) * IMG_BLOCK_B : N1 * IMG_ROW_B;
+            constexpr uint32_t B2_OFF = B_MN ? (N1 / 64) * IMG_BLOCK_B : (PAIR ? N1 / 2 : N1) * IMG_ROW_B;
+            auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+                if (PAIR) tc::umma_bf16_pair(d, ad, bd, idesc, acc); else tc::umma_bf16(d, ad, bd, idesc, acc);
+            };
+            auto commit = [&](uint32_t bar) {
+                if (PAIR) tc::umma_commit_pair(bar); else tc::umma_commit(bar);
+            };
             uint32_t it = 0, tile_it = 0;
-            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
-                const int split = w / (a.m_tiles * a.n_tiles);
+            for (int w = worker; w < total_work; w += n_workers, ++tile_it) {
+                const int split = w / (m_tiles_w * a.n_tiles);
                 const int c0 = split * cps, c1 = min(a.k_chunks, c0 + cps);
                 const int buf = (int)(tile_it & 1u);
                 if (DOUBLE_ACC) {
@@ -398,6 +459,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                 for (int kc = c0; kc < c1; ++kc, ++it) {
                     const int s = it % STAGES;
                     tc::mbar_wait(full_bar(s), (it / STAGES) & 1u);
+                    if (PAIR) tc::mbar_wait(peer_hi_bar(s), (it / STAGES) & 1u);
                     tc::tc_fence_after();
                     const uint32_t sa = smem_base + s * STAGE_B;
                     const uint32_t sb = sa + 2 * A_TILE_B;
@@ -407,34 +469,35 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         const uint64_t a_hi = make_sw128_desc(sa + j * A_ADV, A_LBO);
                         const uint64_t b_hi = make_sw128_desc(sb + j * B_ADV, B_LBO);
                         const uint32_t acc = (kc > c0 || j > 0) ? 1u : 0u;
-                        tc::umma_bf16(d_tmem, a_hi, b_hi, idesc1, acc);
+                        mma(d_tmem, a_hi, b_hi, idesc1, acc);
                         if (N2 > 0) {
                             const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
-                            tc::umma_bf16(d_tmem + N1, a_hi, b2_hi, idesc2, acc);
+                            mma(d_tmem + N1, a_hi, b2_hi, idesc2, acc);
                         }
                     }
                     // ... then the two cross terms, once the lo planes have landed
                     if (a.terms == 3) {
                         tc::mbar_wait(full_lo_bar(s), (it / STAGES) & 1u);
+                        if (PAIR) tc::mbar_wait(peer_lo_bar(s), (it / STAGES) & 1u);
                         tc::tc_fence_after();
                         for (int j = 0; j < steps; ++j) {
                             const uint64_t a_hi = make_sw128_desc(sa + j * A_ADV, A_LBO);
                             const uint64_t a_lo = make_sw128_desc(sa + A_TILE_B + j * A_ADV, A_LBO);
                             const uint64_t b_hi = make_sw128_desc(sb + j * B_ADV, B_LBO);
                             const uint64_t b_lo = make_sw128_desc(sb + B_PLANE_B + j * B_ADV, B_LBO);
-                            tc::umma_bf16(d_tmem, a_lo, b_hi, idesc1, 1u);
-                            tc::umma_bf16(d_tmem, a_hi, b_lo, idesc1, 1u);
+                            mma(d_tmem, a_lo, b_hi, idesc1, 1u);
+                            mma(d_tmem, a_hi, b_lo, idesc1, 1u);
                             if (N2 > 0) {
                                 const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
                                 const uint64_t b2_lo = make_sw128_desc(sb + B_PLANE_B + B2_OFF + j * B_ADV, B_LBO);
-                                tc::umma_bf16(d_tmem + N1, a_lo, b2_hi, idesc2, 1u);
-                                tc::umma_bf16(d_tmem + N1, a_hi, b2_lo, idesc2, 1u);
+                                mma(d_tmem + N1, a_lo, b2_hi, idesc2, 1u);
+                                mma(d_tmem + N1, a_hi, b2_lo, idesc2, 1u);
                             }
                         }
                     }
-                    tc::umma_commit(empty_bar(s));   // frees the stage when these MMAs retire
+                    commit(empty_bar(s));   // frees the stage (in both CTAs of a pair) when these MMAs retire
                 }
-                tc::umma_commit(accf_bar(DOUBLE_ACC ? buf : 0));      // accumulator complete
+                commit(accf_bar(DOUBLE_ACC ? buf : 0));      // accumulator complete
             }
         }
         __syncwarp();
@@ -451,9 +514,13 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
         float* s_dot = s_epi + 2 * NPAD;              // [128]  (EPI_TANH_DOT: second warp's partial row dots)
         uint8_t* const s_xb = reinterpret_cast<uint8_t*>(s_epi + ig_epi_floats(N_T)) + (warp - 2) * IG_XPOSE_BYTES;
         uint32_t tile_it = 0;
-        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++tile_it) {
-            const int tile = w % (a.m_tiles * a.n_tiles), split = w / (a.m_tiles * a.n_tiles);
-            const int m_tile = A_MN ? tile / a.n_tiles : a.m_tiles - 1 - tile / a.n_tiles, n_tile = tile % a.n_tiles;
+        auto release = [&](uint32_t bar) {      // PAIR: the leader's MMA warp waits for both CTAs' epilogues
+            if (PAIR && rank != 0) tc::mbar_arrive_cluster(tc::mapa_cluster(bar, 0)); else tc::mbar_arrive(bar);
+        };
+        for (int w = worker; w < total_work; w += n_workers, ++tile_it) {
+            const int tile = w % (m_tiles_w * a.n_tiles), split = w / (m_tiles_w * a.n_tiles);
+            const int mt_w = A_MN ? tile / a.n_tiles : m_tiles_w - 1 - tile / a.n_tiles, n_tile = tile % a.n_tiles;
+            const int m_tile = PAIR ? 2 * mt_w + (int)rank : mt_w;      // (may be one past the last tile: rows >= M)
             const int n0 = n_tile * N_T;
             const int buf = (int)(tile_it & 1u);
             if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT || EPI == EPI_BIAS_SPLIT) {
@@ -519,7 +586,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         // the overlap columns are in registers / stored: the next tile's main loop may start
                         tc::tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(acce_bar(0));
+                        if (lane == 0) release(acce_bar(0));
                     }
                 }
                 const int cb = 32 * blk;
@@ -648,28 +715,50 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                 // release the accumulator
                 tc::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(acce_bar(buf));
+                if (lane == 0) release(acce_bar(buf));
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+    if (PAIR) tc::cluster_sync_all();     // no CTA exits (or frees TMEM) while its peer may still signal it
+    if (warp == 1) {
+        if (PAIR) tc::tmem_dealloc_pair<512>(tmem_base); else tc::tmem_dealloc<512>(tmem_base);
+    }
 }
 
-template <bool A_MN, bool B_MN, int N_T, int EPI>
+template <bool A_MN, bool B_MN, int N_T, int EPI, bool PAIR = false>
 inline cudaError_t ig_launch(const IgArgs& a, cudaStream_t s, const char* name) {
-    constexpr int smem = ig_smem_bytes(N_T);
+    constexpr int smem = ig_smem_bytes(N_T, PAIR);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(ig_gemm_kernel<A_MN, B_MN, N_T, EPI>,
+        cudaError_t e = cudaFuncSetAttribute(ig_gemm_kernel<A_MN, B_MN, N_T, EPI, PAIR>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    if (PAIR) {
+        // clusters of two CTAs (the two SMs of a TPC); one pair per two token tiles
+        const int pairs = ceil_div(a.m_tiles, 2) * a.n_tiles * a.splits;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * (pairs < kNumSMs / 2 ? pairs : kNumSMs / 2));
+        cfg.blockDim = dim3(ig_threads(N_T));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e = cudaSuccess;
+        NRMS_LAUNCH(name, s, (e = cudaLaunchKernelEx(&cfg, ig_gemm_kernel<A_MN, B_MN, N_T, EPI, PAIR>, a)));
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
     const int total = a.m_tiles * a.n_tiles * a.splits;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    NRMS_LAUNCH(name, s, (ig_gemm_kernel<A_MN, B_MN, N_T, EPI><<<grid, ig_threads(N_T), smem, s>>>(a)));
+    NRMS_LAUNCH(name, s, (ig_gemm_kernel<A_MN, B_MN, N_T, EPI, PAIR><<<grid, ig_threads(N_T), smem, s>>>(a)));
     return cudaGetLastError();
 }
 

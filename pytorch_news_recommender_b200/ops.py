@@ -316,7 +316,7 @@ def gemm_selftest(variant: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tenso
     """tcgen05 GEMM layer self-test (see include/nrms_b200.h: nrms_gemm_selftest)."""
     _require_cuda(A, B)
     A, B = _cf32(A), _cf32(B)
-    if variant == 0:
+    if variant in (0, 3):
         (M, K), N = A.shape, B.shape[0]
     elif variant == 1:
         (M, K), N = A.shape, B.shape[1]

@@ -42,3 +42,15 @@ def test_weight_gradient_orientation(M, N, K, built_lib):
     A = torch.randn(K, M, device="cuda")
     B = torch.randn(K, N, device="cuda")
     _check(ops.gemm_selftest(2, A, B), A.double().t() @ B.double(), f"TN {M}x{N}x{K}", K)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 256, 64), (300, 900, 300), (1000, 200, 300), (77, 60, 20),
+                                   (4096, 960, 300), (105600, 960, 300)])
+def test_forward_orientation_on_cta_pairs(M, N, K, built_lib):
+    """The forward projection on clusters of two CTAs (tcgen05.mma.cta_group::2): odd and even token-tile
+    counts, a ragged last tile, several N tiles, and the benchmark's own shape."""
+    from pytorch_news_recommender_b200 import ops
+    torch.manual_seed(M + N + K + 3)
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    _check(ops.gemm_selftest(3, A, B), A.double() @ B.double().t(), f"NT pair {M}x{N}x{K}", K)
