@@ -110,9 +110,12 @@ inline int hp_rows(const nrms_encoder_dims& d) {
     return d.seq_len <= 32 ? 32 : d.seq_len <= 64 ? 64 : (int)align_up(d.seq_len, 16);
 }
 
-// CTA pairs (cta_group::2) for the K-major GEMMs (gemm_img.cuh: PAIR); NRMS_PAIRS=0 switches them off
+// CTA pairs (cta_group::2) for the forward Q|K|V projection (gemm_img.cuh: PAIR): opt-in with NRMS_PAIRS=1.
+// Correct (tests/test_gpu_gemm.py) but MEASURED SLOWER than one CTA per SM on this path (cfg2: 0.229 ms vs
+// 0.198 ms, cfg3: 1.26 vs 1.14 ms; profiles/r02_pairs_ab.txt): the projection's main loop already runs at
+// the 3-term tensor roofline, so halving the weight-tile traffic buys nothing and the pair's lock-step costs.
 inline bool use_pairs() {
-    static const bool on = !(getenv("NRMS_PAIRS") && atoi(getenv("NRMS_PAIRS")) == 0);
+    static const bool on = getenv("NRMS_PAIRS") && atoi(getenv("NRMS_PAIRS")) == 1;
     return on;
 }
 
