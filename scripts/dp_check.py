@@ -36,6 +36,14 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     rank, world, _ = parallel.init_from_env(device=dev)
+    # a one-rank group per rank (collective: every rank creates all of them): rank 0's single-process
+    # reference run must not join the job's collectives (FusedTrainer broadcasts its weights at construction)
+    solo = None
+    if world > 1:
+        for r in range(world):
+            g = dist.new_group(ranks=[r])
+            if r == rank:
+                solo = g
     vocab, B, steps = 5000, 16 * world, 3
     tmp = tempfile.mkdtemp()
     S.save_embedding_npz(os.path.join(tmp, "emb.npz"), S.make_embedding_table(vocab, 300, seed=0))
@@ -56,8 +64,8 @@ def main():
         # single-process reference on the same device: a fresh model, the whole batch, no exchange
         cfg1, ref = build(dev, tmp, vocab)
         ref.train()
-        tr1 = FusedTrainer(ref)
-        tr1.world, tr1.exchange.world = 1, 1          # no exchange: this rank alone sees the whole batch
+        tr1 = FusedTrainer(ref, process_group=solo)   # world 1: no exchange, this rank alone sees the whole batch
+        assert tr1.world == 1
         tr1.step(batches[0], b_global=B)
         g1 = {k: v.clone() for k, v in tr1.grads_as_state_dict().items()}
         for b in batches[1:]:

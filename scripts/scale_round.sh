@@ -33,6 +33,6 @@ run cfg5_n4 4 --config cfg5 --no-extras --no-cpu-baseline --steps 15 --table-syn
 run cfg5_n8 8 --config cfg5 --no-extras --no-cpu-baseline --steps 15 --table-sync sharded
 for mode in dense sharded; do
   port=$((port+1))
-  TABLE_SYNC=$mode timeout 200 $TR --nproc-per-node 8 --master-port $port scripts/dp_check.py > $OUT/r02_dp_check_${mode}_n8.json 2> $OUT/r02_dp_check_${mode}_n8.err
+  TABLE_SYNC=$mode timeout 120 $TR --nproc-per-node 8 --master-port $port scripts/dp_check.py > $OUT/r02_dp_check_${mode}_n8.json 2> $OUT/r02_dp_check_${mode}_n8.err
   echo "dp_check $mode rc=$? $(cat $OUT/r02_dp_check_${mode}_n8.json | tail -1)"
 done
