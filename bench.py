@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--eager-gpu-baseline", action="store_true", help="(kept for compatibility: on by default at N=1)")
     ap.add_argument("--zipf", action="store_true", help="Zipf(1.0) token distribution instead of uniform")
     ap.add_argument("--batch-per-gpu", type=int, default=None, help="override the config's batch per GPU")
-    ap.add_argument("--table-sync", default="dense", choices=["dense", "sharded"],
+    ap.add_argument("--table-sync", default="auto", choices=["auto", "dense", "sharded"],
                     help="exchange of the embedding-table gradient under data parallelism (engine.FusedTrainer)")
     ap.add_argument("--title-len", type=int, default=None)
     ap.add_argument("--history-len", type=int, default=None)
@@ -609,7 +609,7 @@ def main():
             "config": {"workload": workload_label(args),
                        "global_batch": world * B, "parallelism": f"dp{world}",
                        "gemm_mode": args.gemm_mode, "tokens": "zipf" if args.zipf else "uniform",
-                       "table_sync": args.table_sync,
+                       "table_sync": trainer.table_sync,
                        "l2": "per-step working set (>= 1.5 GB activations + 607 MB Adam state) exceeds the 126 MB L2; "
                              "4 distinct batches rotated"},
             "news_encodes_per_sec": value * alg["titles_per_impr"],

@@ -164,6 +164,9 @@ Saved saved_layout(void* blob, const nrms_encoder_dims& d) {
     if (d.gemm_mode >= 1) {
         s.x_img = ig::img_view(take_bytes(ig::img_bytes(M, kXChunks)), M, kXChunks);
         s.ctx_img = ig::img_view(take_bytes(ig::img_bytes(M, kXChunks)), M, kXChunks);
+        // gemm_mode 2 (plain bf16 products): activations and gradients are SINGLE-plane images — no kernel of
+        // that mode reads a lo plane, so none is written (the blob keeps the two-plane size)
+        if (d.gemm_mode == 2 && blob != nullptr) s.x_img.lo = s.ctx_img.lo = nullptr;
         s.wqkv_img = ig::img_view(take_bytes(ig::img_bytes(kWqkvRows, kXChunks)), kWqkvRows, kXChunks);
         s.wa_img = ig::img_view(take_bytes(ig::img_bytes(kWaRows, kXChunks)), kWaRows, kXChunks);
     } else {
@@ -220,6 +223,7 @@ Scratch scratch_layout(void* blob, const nrms_encoder_dims& d) {
     if (d.gemm_mode >= 1) {
         s.d_pre_img = ig::img_view(take_bytes(ig::img_bytes(M, kPreChunks)), M, kPreChunks);
         s.d_qkv_img = ig::img_view(take_bytes(ig::img_bytes(M, kQkvChunks)), M, kQkvChunks);
+        if (d.gemm_mode == 2 && blob != nullptr) s.d_pre_img.lo = s.d_qkv_img.lo = nullptr;
         const int kch = ig::img_rows_pad(M) / 64;
         const int64_t nq = use_hp(d) ? hp_cols(d) : 3 * D;   // output rows of dW_qkv (HP: padded order)
         const int64_t a = (int64_t)wgrad_splits_tc(ceil_div((int)nq, 128), kch) * nq * (D + 4);
@@ -386,7 +390,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         NRMS_CHECK_CUDA(ig::img_pack2(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, D, dk, pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, nullptr, NP, M, NP);
         g.Chi = reinterpret_cast<uint16_t*>(sv.qkv);
-        g.Clo = g.Chi + (long long)d.n_seq * hp_rows(d) * NP;
+        g.Clo = terms == 3 ? g.Chi + (long long)d.n_seq * hp_rows(d) * NP : nullptr;   // plain bf16: hi plane only
         g.hp_D = D; g.hp_dk = dk; g.seq_len = L; g.hp_rows = hp_rows(d);
         g.terms = terms;
         g.bias = pv.bqkv;

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kHplMaxWarps * 32, 1) attn_hpl_bwd_kernel(cons
                         const int c = col + d;
                         const long long off = ig::img_unit_off(a.ctx_img.chunk_stride, row0 + r, c >> 3) + (c & 7) * 2;
                         const uint32_t ch = __ldg(reinterpret_cast<const uint32_t*>(a.ctx_img.hi + off));
-                        const uint32_t cl = TERMS == 3 ? __ldg(reinterpret_cast<const uint32_t*>(a.ctx_img.lo + off)) : 0u;
+                        const uint32_t cl = (TERMS == 3 && a.ctx_img.lo) ? __ldg(reinterpret_cast<const uint32_t*>(a.ctx_img.lo + off)) : 0u;
                         const float ox = __uint_as_float(ch << 16) + __uint_as_float(cl << 16);
                         const float oy = __uint_as_float(ch & 0xffff0000u) + __uint_as_float(cl & 0xffff0000u);
                         dl[i & 1] = fmaf(v[ks][i].x, ox, fmaf(v[ks][i].y, oy, dl[i & 1]));

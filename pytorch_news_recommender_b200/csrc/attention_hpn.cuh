@@ -163,7 +163,7 @@ __device__ __forceinline__ void hpn_write_img(const float* tile, int m0, int L, 
             const int r7 = (int)(r & 7);
             const long long off = cbase + (r >> 3) * 1024 + r7 * 128 + (((gg & 7) ^ r7) << 4);
             *reinterpret_cast<uint4*>(img.hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(img.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            if (img.lo) *reinterpret_cast<uint4*>(img.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
 }

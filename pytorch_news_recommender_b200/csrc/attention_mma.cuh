@@ -99,12 +99,12 @@ __device__ __forceinline__ void warp_write_slot(const float* slot, int L, int dk
             split_pair(v.x, v.y, hi, lo);
             long long off = ch0 + rbase + (((ga & 7) ^ r7) << 4);
             *reinterpret_cast<uint32_t*>(img.hi + off) = hi;
-            *reinterpret_cast<uint32_t*>(img.lo + off) = lo;
+            if (img.lo) *reinterpret_cast<uint32_t*>(img.lo + off) = lo;
             if (act1) {
                 split_pair(v.z, v.w, hi, lo);
                 off = ch1 + rbase + (((gb & 7) ^ r7) << 4);
                 *reinterpret_cast<uint32_t*>(img.hi + off) = hi;
-                *reinterpret_cast<uint32_t*>(img.lo + off) = lo;
+                if (img.lo) *reinterpret_cast<uint32_t*>(img.lo + off) = lo;
             }
         }
     }
@@ -130,7 +130,7 @@ __device__ __forceinline__ void pad_image(const ig::Img& img, long long row0, in
             const int l = i / np, col = c0 + ((i - l * np) << 1);
             const long long off = ig::img_unit_off(img.chunk_stride, row0 + l, col >> 3) + (col & 7) * 2;
             *reinterpret_cast<uint32_t*>(img.hi + off) = (ones_col && col == c0) ? 0x00003F80u : 0u;   // bf16 {1.0, 0.0}
-            *reinterpret_cast<uint32_t*>(img.lo + off) = 0u;
+            if (img.lo) *reinterpret_cast<uint32_t*>(img.lo + off) = 0u;
         }
     }
     if (last_item) {

@@ -49,7 +49,7 @@ constexpr int A_TILE_B = 16384;     // 128 rows x 128 B (K-major) == 2 blocks (M
 
 struct Img {
     uint8_t* hi;
-    uint8_t* lo;
+    uint8_t* lo;             // nullptr: single-plane image (gemm_mode 2, plain bf16: nobody writes or reads lo)
     long long chunk_stride;  // rows_pad * 128
     int rows_pad;            // multiple of 128
     int chunks;
@@ -91,12 +91,12 @@ __device__ __forceinline__ void img_store8(const Img& im, long long r, int g, co
     for (int j = 0; j < 4; ++j) split2(x[2 * j], x[2 * j + 1], hi[j], lo[j]);
     const long long off = img_unit_off(im.chunk_stride, r, g);
     *reinterpret_cast<uint4*>(im.hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (im.lo) *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 __device__ __forceinline__ void img_store8_zero(const Img& im, long long r, int g) {
     const long long off = img_unit_off(im.chunk_stride, r, g);
     *reinterpret_cast<uint4*>(im.hi + off) = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(0u, 0u, 0u, 0u);
+    if (im.lo) *reinterpret_cast<uint4*>(im.lo + off) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ---- head-padded ("HP") row order of the Q|K|V projection ---------------------------------------
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                                 const uint4 h4 = *reinterpret_cast<const uint4*>(s_xb + rr * 128 + ((u ^ l7) << 4));
                                 const uint4 l4 = *reinterpret_cast<const uint4*>(s_xb + rr * 128 + (((4 + u) ^ l7) << 4));
                                 *reinterpret_cast<uint4*>(a.Chi + split_row_off[i] + jpart) = h4;
-                                *reinterpret_cast<uint4*>(a.Clo + split_row_off[i] + jpart) = l4;
+                                if (a.Clo) *reinterpret_cast<uint4*>(a.Clo + split_row_off[i] + jpart) = l4;
                             }
                         }
                         __syncwarp();

@@ -27,11 +27,11 @@ struct PoolArgs {
     int L, D, Q;
 };
 
-// columns [8u, 8u+8) of row r of a split-bf16 image as fp32 (hi + lo)
+// columns [8u, 8u+8) of row r of a split-bf16 image as fp32 (hi + lo; hi alone for a single-plane image)
 __device__ __forceinline__ void img_load8(const ig::Img& im, long long r, int u, float* x) {
     const long long off = ig::img_unit_off(im.chunk_stride, r, u);
     const uint4 h = __ldg(reinterpret_cast<const uint4*>(im.hi + off));
-    const uint4 l = __ldg(reinterpret_cast<const uint4*>(im.lo + off));
+    const uint4 l = im.lo ? __ldg(reinterpret_cast<const uint4*>(im.lo + off)) : make_uint4(0u, 0u, 0u, 0u);
     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -202,8 +202,9 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
                 const long long off = ig::img_unit_off(p.d_pre_img.chunk_stride, row0 + l, j >> 3) + (j & 7) * 2;
                 *reinterpret_cast<uint32_t*>(p.d_pre_img.hi + off) =
                     (uint32_t)__bfloat16_as_ushort(h0b) | ((uint32_t)__bfloat16_as_ushort(h1b) << 16);
-                *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) =
-                    (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
+                if (p.d_pre_img.lo)
+                    *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) =
+                        (uint32_t)__bfloat16_as_ushort(l0b) | ((uint32_t)__bfloat16_as_ushort(l1b) << 16);
             }
         }
         }
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
                 const int l = i / (cpad >> 1), j = Q + ((i - l * (cpad >> 1)) << 1);
                 const long long off = ig::img_unit_off(p.d_pre_img.chunk_stride, row0 + l, j >> 3) + (j & 7) * 2;
                 *reinterpret_cast<uint32_t*>(p.d_pre_img.hi + off) = 0u;
-                *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) = 0u;
+                if (p.d_pre_img.lo) *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) = 0u;
             }
             if (seq == (int)gridDim.x - 1) {
                 const int groups = p.d_pre_img.chunks * 8;

@@ -51,7 +51,7 @@ def main():
     batches = [S.make_train_batch(pool, B, 50, 4, seed=10 + i) for i in range(steps)]
     cfg, model = build(dev, tmp, vocab)
     model.train()
-    tr = FusedTrainer(model, table_sync=os.environ.get("TABLE_SYNC", "dense"))
+    tr = FusedTrainer(model, table_sync=os.environ.get("TABLE_SYNC", "auto"))
     # gradients of the FIRST step (before Adam's sign-like update amplifies rounding differences of
     # mathematically-zero gradients such as the W_K bias), then the remaining steps for the weights
     tr.step(parallel.shard_batch(batches[0], rank, world), b_global=B)
