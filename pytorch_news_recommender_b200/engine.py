@@ -278,6 +278,11 @@ class FusedTrainer:
             self.table_m = torch.zeros((self.v_shard, D), dtype=torch.float32, device=dev)
             self.table_v = torch.zeros((self.v_shard, D), dtype=torch.float32, device=dev)
             self._comm = torch.cuda.Stream(device=dev)
+            # The small dense-block all-reduce gets its OWN communicator: collectives of one NCCL communicator
+            # run in issue order on one stream, so behind the table's reduce-scatter / all-gather it would
+            # wait for both although it shares no data with them.
+            ranks = dist.get_process_group_ranks(self.pg) if self.pg is not None else list(range(dist.get_world_size()))
+            self.exchange_flat = GradientExchange(dist.new_group(ranks=ranks))
         else:
             self.table_grad = torch.empty_like(self.table.data)
             self.table_m = torch.zeros_like(self.table.data)
@@ -468,7 +473,7 @@ class FusedTrainer:
         else:
             pending = self.exchange.allreduce([self.table_grad], async_op=True)
         ops.news_encoder_bwd(*nb, phase=ops.BWD_PARAMS)
-        pending += self.exchange.allreduce([self.flat_grad], async_op=True)
+        pending += (self.exchange_flat if sharded else self.exchange).allreduce([self.flat_grad], async_op=True)
         for h_ in pending:
             h_.wait()
         # ---- Adam ---------------------------------------------------------------------------
