@@ -427,18 +427,26 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                     }
                 }
             }
-        } else if (lane == 0) {
+        } else {
+            // Every lane runs this loop with warp-uniform values; the elected lane's MMA / commit instructions
+            // are the only ones enabled (tc::umma_*_if).
+            const uint32_t issue = tc::elect_one();
             constexpr uint32_t idesc1 = make_idesc2(N1, A_MN, B_MN, PAIR ? 256 : 128);
             constexpr uint32_t idesc2 = make_idesc2(N2 > 0 ? N2 : 32, A_MN, B_MN, PAIR ? 256 : 128);
             constexpr uint32_t A_LBO = A_MN ? IMG_BLOCK_B : 16, B_LBO = B_MN ? IMG_BLOCK_B : 16;
-            constexpr uint32_t A_ADV = A_MN ? 2048 : 32, B_ADV = B_MN ? 2048 : 32;   // bytes per K=16 step
+            // descriptor arithmetic on the low word only: bits [0,14) = address / 16 (shared memory is < 256 KB,
+            // so adding a byte offset / 16 never carries out of the field), bits [16,30) = LBO / 16
+            constexpr uint32_t A_STEP = (A_MN ? 2048 : 32) >> 4, B_STEP = (B_MN ? 2048 : 32) >> 4;   // per K=16 step
+            constexpr uint32_t A_LO_OFF = A_TILE_B >> 4, B_LO_OFF = B_PLANE_B >> 4;                  // hi plane -> lo plane
             // second UMMA of a k-step covers columns [N1, N_T): its B rows/blocks start here
-            constexpr uint32_t B2_OFF = B_MN ? (N1 / 64) * IMG_BLOCK_B : (PAIR ? N1 / 2 : N1) * IMG_ROW_B;
-            auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
-                if (PAIR) tc::umma_bf16_pair(d, ad, bd, idesc, acc); else tc::umma_bf16(d, ad, bd, idesc, acc);
+            constexpr uint32_t B2_OFF = (B_MN ? (N1 / 64) * IMG_BLOCK_B : (PAIR ? N1 / 2 : N1) * IMG_ROW_B) >> 4;
+            auto desc = [](uint32_t lo) { return ((uint64_t)0x40004040u << 32) | lo; };   // SBO 1024, version 1, SWIZZLE_128B
+            auto mma = [&](uint32_t d, uint32_t a_lo32, uint32_t b_lo32, uint32_t idesc, uint32_t acc) {
+                if (PAIR) tc::umma_bf16_pair_if(issue, d, desc(a_lo32), desc(b_lo32), idesc, acc);
+                else tc::umma_bf16_if(issue, d, desc(a_lo32), desc(b_lo32), idesc, acc);
             };
             auto commit = [&](uint32_t bar) {
-                if (PAIR) tc::umma_commit_pair(bar); else tc::umma_commit(bar);
+                if (PAIR) tc::umma_commit_pair_if(issue, bar); else tc::umma_commit_if(issue, bar);
             };
             uint32_t it = 0, tile_it = 0;
             for (int w = worker; w < total_work; w += n_workers, ++tile_it) {
@@ -462,17 +470,16 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                     if (PAIR) tc::mbar_wait(peer_hi_bar(s), (it / STAGES) & 1u);
                     tc::tc_fence_after();
                     const uint32_t sa = smem_base + s * STAGE_B;
-                    const uint32_t sb = sa + 2 * A_TILE_B;
+                    const uint32_t a_hi = ((sa >> 4) & 0x3FFFu) | ((A_LBO >> 4) << 16);
+                    const uint32_t b_hi = (((sa + 2 * A_TILE_B) >> 4) & 0x3FFFu) | ((B_LBO >> 4) << 16);
                     const int steps = min(4, a.k_steps - 4 * kc);
                     // hi x hi of every k-step first (needs the hi planes only) ...
-                    for (int j = 0; j < steps; ++j) {
-                        const uint64_t a_hi = make_sw128_desc(sa + j * A_ADV, A_LBO);
-                        const uint64_t b_hi = make_sw128_desc(sb + j * B_ADV, B_LBO);
-                        const uint32_t acc = (kc > c0 || j > 0) ? 1u : 0u;
-                        mma(d_tmem, a_hi, b_hi, idesc1, acc);
-                        if (N2 > 0) {
-                            const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
-                            mma(d_tmem + N1, a_hi, b2_hi, idesc2, acc);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < steps) {
+                            const uint32_t acc = (kc > c0 || j > 0) ? 1u : 0u;
+                            mma(d_tmem, a_hi + j * A_STEP, b_hi + j * B_STEP, idesc1, acc);
+                            if (N2 > 0) mma(d_tmem + N1, a_hi + j * A_STEP, b_hi + B2_OFF + j * B_STEP, idesc2, acc);
                         }
                     }
                     // ... then the two cross terms, once the lo planes have landed
@@ -480,18 +487,16 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         tc::mbar_wait(full_lo_bar(s), (it / STAGES) & 1u);
                         if (PAIR) tc::mbar_wait(peer_lo_bar(s), (it / STAGES) & 1u);
                         tc::tc_fence_after();
-                        for (int j = 0; j < steps; ++j) {
-                            const uint64_t a_hi = make_sw128_desc(sa + j * A_ADV, A_LBO);
-                            const uint64_t a_lo = make_sw128_desc(sa + A_TILE_B + j * A_ADV, A_LBO);
-                            const uint64_t b_hi = make_sw128_desc(sb + j * B_ADV, B_LBO);
-                            const uint64_t b_lo = make_sw128_desc(sb + B_PLANE_B + j * B_ADV, B_LBO);
-                            mma(d_tmem, a_lo, b_hi, idesc1, 1u);
-                            mma(d_tmem, a_hi, b_lo, idesc1, 1u);
-                            if (N2 > 0) {
-                                const uint64_t b2_hi = make_sw128_desc(sb + B2_OFF + j * B_ADV, B_LBO);
-                                const uint64_t b2_lo = make_sw128_desc(sb + B_PLANE_B + B2_OFF + j * B_ADV, B_LBO);
-                                mma(d_tmem + N1, a_lo, b2_hi, idesc2, 1u);
-                                mma(d_tmem + N1, a_hi, b2_lo, idesc2, 1u);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (j < steps) {
+                                const uint32_t ah = a_hi + j * A_STEP, bh = b_hi + j * B_STEP;
+                                mma(d_tmem, ah + A_LO_OFF, bh, idesc1, 1u);
+                                mma(d_tmem, ah, bh + B_LO_OFF, idesc1, 1u);
+                                if (N2 > 0) {
+                                    mma(d_tmem + N1, ah + A_LO_OFF, bh + B2_OFF, idesc2, 1u);
+                                    mma(d_tmem + N1, ah, bh + B_LO_OFF + B2_OFF, idesc2, 1u);
+                                }
                             }
                         }
                     }

@@ -54,6 +54,66 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// 1 in exactly one lane of the (fully active) warp
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred;
+}
+// The MMA / commit wrappers below are executed by EVERY lane of the issuing warp with warp-uniform operands
+// and a per-lane `issue` flag that is 1 in the elected lane only: the instruction itself is predicated, the
+// code around it stays convergent, and the compiler can keep descriptors in uniform registers (issued from
+// inside an `if (lane == 0)` block, each MMA cost a ~35-instruction vector-to-uniform broadcast loop).
+__device__ __forceinline__ void umma_bf16_if(uint32_t issue, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair_if(uint32_t issue, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                  uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t issue, uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar),
+        "r"(issue)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_if(uint32_t issue, uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t"
+        "}" ::"r"(bar),
+        "r"(issue), "h"((uint16_t)3)
+        : "memory");
+}
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
