@@ -517,7 +517,9 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
         float* s_bias = s_epi;                        // [NPAD]
         float* s_qv = s_epi + NPAD;                   // [NPAD] (EPI_TANH_DOT)
         float* s_dot = s_epi + 2 * NPAD;              // [128]  (EPI_TANH_DOT: second warp's partial row dots)
-        uint8_t* const s_xb = reinterpret_cast<uint8_t*>(s_epi + ig_epi_floats(N_T)) + (warp - 2) * IG_XPOSE_BYTES;
+        // this warp's staging buffer and the bias vector as SHARED-space addresses (explicit ld/st.shared)
+        const uint32_t s_xb = tc::smem_u32(s_epi + ig_epi_floats(N_T)) + (uint32_t)(warp - 2) * IG_XPOSE_BYTES;
+        const uint32_t s_bias_a = tc::smem_u32(s_bias);
         uint32_t tile_it = 0;
         auto release = [&](uint32_t bar) {      // PAIR: the leader's MMA warp waits for both CTAs' epilogues
             if (PAIR && rank != 0) tc::mbar_arrive_cluster(tc::mapa_cluster(bar, 0)); else tc::mbar_arrive(bar);
@@ -612,17 +614,16 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + cb + 4 * j);
+                            const float4 b4 = tc::lds128f(s_bias_a + 4u * (uint32_t)(cb + 4 * j));
                             split2(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, hi[2 * j], lo[2 * j]);
                             split2(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w, hi[2 * j + 1], lo[2 * j + 1]);
                         }
                         const int l7 = lane & 7;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            *reinterpret_cast<uint4*>(s_xb + lane * 128 + ((j ^ l7) << 4)) =
-                                make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            *reinterpret_cast<uint4*>(s_xb + lane * 128 + (((4 + j) ^ l7) << 4)) =
-                                make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                            tc::sts128(s_xb + lane * 128 + ((j ^ l7) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                            tc::sts128(s_xb + lane * 128 + (((4 + j) ^ l7) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2],
+                                       lo[4 * j + 3]);
                         }
                         __syncwarp();
                         // lane -> (row 8i + lane%8, unit lane/8): the 8 lanes of a shared-memory phase read 8
@@ -633,8 +634,8 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         for (int i = 0; i < 4; ++i) {
                             if (split_row_off[i] >= 0) {
                                 const int rr = 8 * i + l7;      // rr % 8 == l7
-                                const uint4 h4 = *reinterpret_cast<const uint4*>(s_xb + rr * 128 + ((u ^ l7) << 4));
-                                const uint4 l4 = *reinterpret_cast<const uint4*>(s_xb + rr * 128 + (((4 + u) ^ l7) << 4));
+                                const uint4 h4 = tc::lds128(s_xb + rr * 128 + ((u ^ l7) << 4));
+                                const uint4 l4 = tc::lds128(s_xb + rr * 128 + (((4 + u) ^ l7) << 4));
                                 *reinterpret_cast<uint4*>(a.Chi + split_row_off[i] + jpart) = h4;
                                 if (a.Clo) *reinterpret_cast<uint4*>(a.Clo + split_row_off[i] + jpart) = l4;
                             }
@@ -662,12 +663,14 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                     if (n >= N_T) continue;
                     float4 o = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
                     if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT) {
-                        o.x += s_bias[n]; o.y += s_bias[n + 1]; o.z += s_bias[n + 2]; o.w += s_bias[n + 3];
+                        const float4 b4 = tc::lds128f(s_bias_a + 4u * (uint32_t)n);
+                        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
                     }
                     if (EPI == EPI_TANH_DOT) {
+                        const float4 q4 = tc::lds128f(s_bias_a + 4u * (uint32_t)(NPAD + n));   // s_qv follows s_bias
                         o.x = tanh_fast(o.x); o.y = tanh_fast(o.y); o.z = tanh_fast(o.z); o.w = tanh_fast(o.w);
-                        dot = fmaf(o.x, s_qv[n], dot); dot = fmaf(o.y, s_qv[n + 1], dot);
-                        dot = fmaf(o.z, s_qv[n + 2], dot); dot = fmaf(o.w, s_qv[n + 3], dot);
+                        dot = fmaf(o.x, q4.x, dot); dot = fmaf(o.y, q4.y, dot);
+                        dot = fmaf(o.z, q4.z, dot); dot = fmaf(o.w, q4.w, dot);
                     }
                     if (EPI == EPI_ACCUM) {
                         o.x += old[g].x; o.y += old[g].y; o.z += old[g].z; o.w += old[g].w;
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                         o.w = (bits & 8u) ? o.w * a.mask_scale : 0.f;
                     }
                     if (XPOSE) {
-                        *reinterpret_cast<float4*>(s_xb + lane * 128 + ((g ^ (lane & 7)) << 4)) = o;
+                        tc::sts128f(s_xb + lane * 128 + ((g ^ (lane & 7)) << 4), o);
                     } else {
                         if (row_ok && n0 + n < a.N) *reinterpret_cast<float4*>(crow + n) = o;
                     }
@@ -701,7 +704,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                             const int rr = 4 * i + (lane >> 3);
                             const int mm = m_tile * 128 + q * 32 + rr;
                             if (mm < a.M) {
-                                const float4 v4 = *reinterpret_cast<const float4*>(s_xb + rr * 128 + ((cc ^ (rr & 7)) << 4));
+                                const float4 v4 = tc::lds128f(s_xb + rr * 128 + ((cc ^ (rr & 7)) << 4));
                                 *reinterpret_cast<float4*>(cbase + (long long)mm * a.ldc + n0 + n) = v4;
                             }
                         }

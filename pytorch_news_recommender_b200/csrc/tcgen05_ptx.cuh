@@ -54,6 +54,25 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
         "l"(src), "r"(bytes), "r"(bar)
         : "memory");
 }
+// explicit shared-space 16-byte accesses (a pointer derived from the manually aligned dynamic shared-memory
+// base has lost its address space: the compiler would emit generic LD / ST, which go down the long-scoreboard
+// path)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 // 1 in exactly one lane of the (fully active) warp
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred;
