@@ -112,6 +112,13 @@ int nrms_news_encoder_bwd_phase(const nrms_encoder_dims* d, const int64_t* ids, 
                                 int64_t saved_bytes, void* scratch, int64_t scratch_bytes,
                                 float* d_params, float* d_rows, int32_t phase, nrms_stream_t stream);
 
+/* The user encoder's backward in the same two phases (its weight-gradient half then runs on a side
+ * stream underneath the news encoder's data-gradient path; needs a scratch blob of its own). */
+int nrms_user_encoder_bwd_phase(const nrms_encoder_dims* d, const float* x, const float* params,
+                                const float* d_out, const void* saved, int64_t saved_bytes, void* scratch,
+                                int64_t scratch_bytes, float* d_params, float* d_x, int32_t phase,
+                                nrms_stream_t stream);
+
 /* UserEncoder.forward (nrms_v0.py:188-199): x [n_seq, seq_len, d_model] -> out [n_seq, d_model] */
 int nrms_user_encoder_fwd(const nrms_encoder_dims* d, const float* x, const float* params,
                           float* out, void* saved, int64_t saved_bytes, nrms_stream_t stream);

@@ -53,6 +53,7 @@ SIGNATURES = {
     "nrms_news_encoder_fwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P]),
     "nrms_news_encoder_bwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P]),
     "nrms_news_encoder_bwd_phase": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I32, _P]),
+    "nrms_user_encoder_bwd_phase": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _I32, _P]),
     "nrms_user_encoder_fwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P]),
     "nrms_user_encoder_fwd_gather": (C.c_int, [_DIMS, _P, _P, _P, _P, _P, _I64, _P]),
     "nrms_user_encoder_bwd": (C.c_int, [_DIMS, _P, _P, _P, _P, _I64, _P, _I64, _P, _P, _P]),

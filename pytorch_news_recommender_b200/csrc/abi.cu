@@ -850,6 +850,21 @@ int nrms_news_encoder_bwd_phase(const nrms_encoder_dims* d, const int64_t* ids, 
     return encoder_bwd(*d, ids, table, params, d_out, saved, saved_bytes, scratch, scratch_bytes,
                        d_params, d_rows, true, phase, (cudaStream_t)stream);
 }
+int nrms_user_encoder_bwd_phase(const nrms_encoder_dims* d, const float* x, const float* params,
+                                const float* d_out, const void* saved, int64_t saved_bytes, void* scratch,
+                                int64_t scratch_bytes, float* d_params, float* d_x, int32_t phase,
+                                nrms_stream_t stream) {
+    int rc = check_dims(d, false);
+    if (rc) return rc;
+    if (phase != NRMS_BWD_DATA && phase != NRMS_BWD_PARAMS)
+        return fail(NRMS_ERR_BAD_SHAPE, "phase=%d (expected NRMS_BWD_DATA or NRMS_BWD_PARAMS)", phase);
+    NRMS_REQUIRE_PTR(x); NRMS_REQUIRE_PTR(params); NRMS_REQUIRE_PTR(d_out); NRMS_REQUIRE_PTR(saved);
+    NRMS_REQUIRE_PTR(scratch); NRMS_REQUIRE_PTR(d_params); NRMS_REQUIRE_PTR(d_x);
+    nrms_encoder_dims dd = *d;
+    dd.dropout_p = 0.f;
+    return encoder_bwd(dd, nullptr, x, params, d_out, saved, saved_bytes, scratch, scratch_bytes,
+                       d_params, d_x, false, phase, (cudaStream_t)stream);
+}
 int nrms_user_encoder_fwd(const nrms_encoder_dims* d, const float* x, const float* params,
                           float* out, void* saved, int64_t saved_bytes, nrms_stream_t stream) {
     int rc = check_dims(d, false);

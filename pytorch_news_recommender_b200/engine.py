@@ -447,43 +447,63 @@ class FusedTrainer:
             self._loss_host.copy_(self._loss_dev, non_blocking=True)
             self._loss_event.record(self._loss_stream)
         # ---- backward -----------------------------------------------------------------------
-        ops.user_encoder_bwd(user_shape, hist_vec, user_flat, b["d_user_vec"], user_saved,
-                             news_scratch, self.flat_grad[self.n_enc:], d_hist, gm)
-        # The news encoder's backward runs in two halves so that, under data parallelism, the big
-        # exchange (84 MB table gradient) overlaps the weight-gradient GEMMs instead of idling the SMs.
+        # The step is a serial chain of kernels that each load ONE resource (tensor pipe, HBM, or just
+        # latency); three pieces are off that chain and run on side streams next to it:
+        #   * the user encoder's weight gradients (a dozen tiny launches) underneath the news encoder's
+        #     data-gradient path;
+        #   * the table path — deduplicating reduction of the embedding-row gradients, then (one GPU) the
+        #     HBM-bound dense Adam over the 84 MB table, or (data parallel) reduce-scatter -> Adam on this
+        #     rank's rows -> all-gather — underneath the news encoder's tensor-bound weight-gradient GEMMs.
+        user_scratch = self.blobs.get("user_scratch", ops.scratch_bytes(user_shape, gm), dev)
+        ub = (user_shape, hist_vec, user_flat, b["d_user_vec"], user_saved, user_scratch,
+              self.flat_grad[self.n_enc:], d_hist, gm)
+        ops.user_encoder_bwd(*ub, phase=ops.BWD_DATA)
+        if getattr(self, "_side2", None) is None:
+            self._side2 = torch.cuda.Stream(device=dev)
+        self._side2.wait_stream(main)
+        with torch.cuda.stream(self._side2):
+            ops.user_encoder_bwd(*ub, phase=ops.BWD_PARAMS)
         M = n_titles * T
         nb = (news_shape, b["ids"], table, news_flat, b["d_news_vec"], news_saved, news_scratch,
               self.flat_grad[:self.n_enc], b["d_rows"], p, seed, gm)
         ops.news_encoder_bwd(*nb, phase=ops.BWD_DATA)
-        main.wait_stream(self._side)
-        ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
-        # ---- gradient exchange (data parallel): SUM-allreduce, gradients already carry 1/B_global
         b1, b2 = self.betas
         sharded = self.world > 1 and self.table_sync == "sharded"
-        if sharded:
-            # reduce-scatter -> Adam on this rank's rows -> all-gather, all on a side stream underneath the
-            # weight-gradient GEMMs: the same bytes on the wire as the all-reduce, a G times smaller Adam
-            self._comm.wait_stream(main)
-            with torch.cuda.stream(self._comm):
-                self.exchange.reduce_scatter(self.table_grad_pad, self.grad_shard)
-                ops.adam_step(self.table_shard, self.grad_shard, self.table_m, self.table_v, self.step_count,
-                              self.lr, b1, b2, self.eps)
-                self.exchange.all_gather(self.table_pad, self.table_shard)
-            pending = []
-        else:
+        pending = []
+        if self.world > 1 and not sharded:
+            # dense exchange: all-reduce of the whole table gradient underneath the weight-gradient GEMMs, then
+            # the replicated Adam
+            main.wait_stream(self._side)
+            ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
             pending = self.exchange.allreduce([self.table_grad], async_op=True)
+        else:
+            tstream = self._comm if sharded else self._side      # (the plan was computed on self._side)
+            tstream.wait_stream(main)
+            if sharded:
+                tstream.wait_stream(self._side)
+            with torch.cuda.stream(tstream):
+                ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
+                if sharded:
+                    self.exchange.reduce_scatter(self.table_grad_pad, self.grad_shard)
+                    ops.adam_step(self.table_shard, self.grad_shard, self.table_m, self.table_v, self.step_count,
+                                  self.lr, b1, b2, self.eps)
+                    self.exchange.all_gather(self.table_pad, self.table_shard)
+                else:
+                    ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
+                                  b1, b2, self.eps)
         ops.news_encoder_bwd(*nb, phase=ops.BWD_PARAMS)
+        main.wait_stream(self._side2)             # the user encoder's half of flat_grad
         pending += (self.exchange_flat if sharded else self.exchange).allreduce([self.flat_grad], async_op=True)
         for h_ in pending:
             h_.wait()
         # ---- Adam ---------------------------------------------------------------------------
         ops.adam_step(self.flat, self.flat_grad, self.flat_m, self.flat_v, self.step_count, self.lr,
                       b1, b2, self.eps)
-        if sharded:
-            main.wait_stream(self._comm)          # the gathered table is what the next forward reads
-        else:
+        if self.world > 1 and not sharded:
             ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
                           b1, b2, self.eps)
+        else:
+            main.wait_stream(self._comm if sharded else self._side)   # the updated table is what the next forward reads
         self.model._nrms_weights_version = getattr(self.model, "_nrms_weights_version", 0) + 1
         if "slot_free" in b:                      # this step's input slot may be overwritten from here on
             ev = torch.cuda.Event()

@@ -142,13 +142,20 @@ def user_encoder_fwd_gather(shape: EncoderShape, ids, table, params, saved, gemm
 
 
 def user_encoder_bwd(shape: EncoderShape, x, params, d_out, saved, scratch, d_params, d_x,
-                     gemm_mode=0):
+                     gemm_mode=0, phase: Optional[int] = None):
+    """phase None: the whole backward; BWD_DATA / BWD_PARAMS: its two halves (include/nrms_b200.h)."""
     _require_cuda(x, params, d_out, saved, scratch, d_params, d_x)
     d = shape.dims(0.0, 0, gemm_mode)
-    check(_lib.load().nrms_user_encoder_bwd(d, ptr(x), ptr(params), ptr(d_out), ptr(saved),
-                                            saved.numel(), ptr(scratch), scratch.numel(),
-                                            ptr(d_params), ptr(d_x), _stream()),
-          "nrms_user_encoder_bwd")
+    if phase is None:
+        check(_lib.load().nrms_user_encoder_bwd(d, ptr(x), ptr(params), ptr(d_out), ptr(saved),
+                                                saved.numel(), ptr(scratch), scratch.numel(),
+                                                ptr(d_params), ptr(d_x), _stream()),
+              "nrms_user_encoder_bwd")
+    else:
+        check(_lib.load().nrms_user_encoder_bwd_phase(d, ptr(x), ptr(params), ptr(d_out), ptr(saved),
+                                                      saved.numel(), ptr(scratch), scratch.numel(),
+                                                      ptr(d_params), ptr(d_x), int(phase), _stream()),
+              "nrms_user_encoder_bwd_phase")
 
 
 def score_fwd(cand, user, mask):
