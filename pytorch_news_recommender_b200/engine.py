@@ -416,8 +416,7 @@ class FusedTrainer:
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=dev)
         self._side.wait_stream(main)          # the ids are on the device; last step's use of the plan is over
-        with torch.cuda.stream(self._side):
-            ops.embedding_plan(b["ids"], V, plan)
+        ops.embedding_plan(b["ids"], V, plan, stream=self._side)
         # ---- forward ----------------------------------------------------------------------
         ops.news_encoder_fwd(news_shape, b["ids"], table, news_flat, news_saved, p, seed, gm,
                              out=b["news_vec"])
@@ -461,8 +460,7 @@ class FusedTrainer:
         if getattr(self, "_side2", None) is None:
             self._side2 = torch.cuda.Stream(device=dev)
         self._side2.wait_stream(main)
-        with torch.cuda.stream(self._side2):
-            ops.user_encoder_bwd(*ub, phase=ops.BWD_PARAMS)
+        ops.user_encoder_bwd(*ub, phase=ops.BWD_PARAMS, stream=self._side2)
         M = n_titles * T
         nb = (news_shape, b["ids"], table, news_flat, b["d_news_vec"], news_saved, news_scratch,
               self.flat_grad[:self.n_enc], b["d_rows"], p, seed, gm)
@@ -481,16 +479,16 @@ class FusedTrainer:
             tstream.wait_stream(main)
             if sharded:
                 tstream.wait_stream(self._side)
-            with torch.cuda.stream(tstream):
-                ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
-                if sharded:
+            ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad, stream=tstream)
+            if sharded:
+                with torch.cuda.stream(tstream):      # (torch.distributed takes the current stream)
                     self.exchange.reduce_scatter(self.table_grad_pad, self.grad_shard)
                     ops.adam_step(self.table_shard, self.grad_shard, self.table_m, self.table_v, self.step_count,
                                   self.lr, b1, b2, self.eps)
                     self.exchange.all_gather(self.table_pad, self.table_shard)
-                else:
-                    ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
-                                  b1, b2, self.eps)
+            else:
+                ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
+                              b1, b2, self.eps, stream=tstream)
         ops.news_encoder_bwd(*nb, phase=ops.BWD_PARAMS)
         main.wait_stream(self._side2)             # the user encoder's half of flat_grad
         pending += (self.exchange_flat if sharded else self.exchange).allreduce([self.flat_grad], async_op=True)
@@ -506,9 +504,10 @@ class FusedTrainer:
             main.wait_stream(self._comm if sharded else self._side)   # the updated table is what the next forward reads
         self.model._nrms_weights_version = getattr(self.model, "_nrms_weights_version", 0) + 1
         if "slot_free" in b:                      # this step's input slot may be overwritten from here on
-            ev = torch.cuda.Event()
+            ev = b["slot_free"][b["slot"]]
+            if ev is None:
+                ev = b["slot_free"][b["slot"]] = torch.cuda.Event()
             ev.record(main)
-            b["slot_free"][b["slot"]] = ev
         return loss
 
     def global_batch(self, B: int) -> int:

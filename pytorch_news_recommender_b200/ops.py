@@ -18,8 +18,10 @@ DROP_EMBEDDING = 1
 DROP_CONTEXT = 2
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(stream=None) -> int:
+    """cudaStream_t of `stream` (a torch.cuda.Stream), or of the current stream.  The fused step passes its
+    side streams explicitly: a `with torch.cuda.stream(...)` block costs more host time than the launch."""
+    return torch.cuda.current_stream().cuda_stream if stream is None else stream.cuda_stream
 
 
 def _require_cuda(*tensors) -> None:
@@ -142,19 +144,19 @@ def user_encoder_fwd_gather(shape: EncoderShape, ids, table, params, saved, gemm
 
 
 def user_encoder_bwd(shape: EncoderShape, x, params, d_out, saved, scratch, d_params, d_x,
-                     gemm_mode=0, phase: Optional[int] = None):
+                     gemm_mode=0, phase: Optional[int] = None, stream=None):
     """phase None: the whole backward; BWD_DATA / BWD_PARAMS: its two halves (include/nrms_b200.h)."""
     _require_cuda(x, params, d_out, saved, scratch, d_params, d_x)
     d = shape.dims(0.0, 0, gemm_mode)
     if phase is None:
         check(_lib.load().nrms_user_encoder_bwd(d, ptr(x), ptr(params), ptr(d_out), ptr(saved),
                                                 saved.numel(), ptr(scratch), scratch.numel(),
-                                                ptr(d_params), ptr(d_x), _stream()),
+                                                ptr(d_params), ptr(d_x), _stream(stream)),
               "nrms_user_encoder_bwd")
     else:
         check(_lib.load().nrms_user_encoder_bwd_phase(d, ptr(x), ptr(params), ptr(d_out), ptr(saved),
                                                       saved.numel(), ptr(scratch), scratch.numel(),
-                                                      ptr(d_params), ptr(d_x), int(phase), _stream()),
+                                                      ptr(d_params), ptr(d_x), int(phase), _stream(stream)),
               "nrms_user_encoder_bwd_phase")
 
 
@@ -207,16 +209,16 @@ def embedding_plan_bytes(n_rows: int, vocab: int) -> int:
     return int(_lib.load().nrms_embedding_plan_bytes(n_rows, vocab))
 
 
-def embedding_plan(ids, vocab: int, plan):
+def embedding_plan(ids, vocab: int, plan, stream=None):
     _require_cuda(ids, plan)
     check(_lib.load().nrms_embedding_plan(ptr(ids), ids.numel(), vocab, ptr(plan), plan.numel(),
-                                          _stream()), "nrms_embedding_plan")
+                                          _stream(stream)), "nrms_embedding_plan")
 
 
-def embedding_grad_dense(plan, d_rows, n_rows: int, vocab: int, D: int, d_table):
+def embedding_grad_dense(plan, d_rows, n_rows: int, vocab: int, D: int, d_table, stream=None):
     _require_cuda(plan, d_rows, d_table)
     check(_lib.load().nrms_embedding_grad_dense(ptr(plan), plan.numel(), ptr(d_rows), n_rows, vocab,
-                                                D, ptr(d_table), _stream()),
+                                                D, ptr(d_table), _stream(stream)),
           "nrms_embedding_grad_dense")
 
 
@@ -227,11 +229,11 @@ def embedding_plan_unique(plan, vocab: int) -> torch.Tensor:
     return out
 
 
-def adam_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+def adam_step(p, g, m, v, step: int, lr: float, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0, stream=None):
     _require_cuda(p, g, m, v)
     check(_lib.load().nrms_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), int(step), float(lr),
                                      float(beta1), float(beta2), float(eps), float(grad_scale),
-                                     _stream()), "nrms_adam_step")
+                                     _stream(stream)), "nrms_adam_step")
 
 
 def rank_metrics(scores, labels, offsets, max_len: int, row_stride: Optional[int] = None):
