@@ -6,6 +6,7 @@ PyTorch/CPU fallback — a non-CUDA tensor or a missing library raises.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
@@ -47,8 +48,15 @@ class EncoderShape:
     vocab: int = 0
 
     def dims(self, dropout_p: float = 0.0, seed: int = 0, gemm_mode: int = 0) -> EncoderDims:
-        return EncoderDims(self.n_seq, self.seq_len, self.d_model, self.n_heads, self.d_query,
-                           self.vocab, float(dropout_p), int(gemm_mode), int(seed) & (2**64 - 1))
+        return _dims_cached(self, float(dropout_p), int(seed) & (2**64 - 1), int(gemm_mode))
+
+
+@functools.lru_cache(maxsize=256)
+def _dims_cached(shape: "EncoderShape", dropout_p: float, seed: int, gemm_mode: int) -> EncoderDims:
+    """One ctypes struct per (shape, step): a step passes the same dims to its forward and both backward
+    phases, and the host side of the fused step is on the critical path of the end-to-end loop."""
+    return EncoderDims(shape.n_seq, shape.seq_len, shape.d_model, shape.n_heads, shape.d_query,
+                       shape.vocab, dropout_p, gemm_mode, seed)
 
 
 def encoder_param_count(d_model: int, d_query: int) -> int:
