@@ -233,6 +233,9 @@ class FusedTrainer:
                              "(reduce-scatter + Adam on V/G rows + all-gather)")
         self.table_sync = table_sync
         self.step_count = 0
+        # False: every kernel of the step on the caller's stream, in order (bench.py's per-kernel timing pass:
+        # CUDA events around a launch on a side stream would also count the time it waits for SMs)
+        self.overlap = True
         self.table = model.news_encoder.word_embedding[0].weight
         if not self.table.is_cuda:
             raise NrmsError("FusedTrainer needs the model on a CUDA device (no CPU fallback)")
@@ -415,8 +418,12 @@ class FusedTrainer:
         main = torch.cuda.current_stream(dev)
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=dev)
-        self._side.wait_stream(main)          # the ids are on the device; last step's use of the plan is over
-        ops.embedding_plan(b["ids"], V, plan, stream=self._side)
+            self._side2 = torch.cuda.Stream(device=dev)
+        side = self._side if self.overlap else main
+        side2 = self._side2 if self.overlap else main
+        if side is not main:
+            side.wait_stream(main)            # the ids are on the device; last step's use of the plan is over
+        ops.embedding_plan(b["ids"], V, plan, stream=side)
         # ---- forward ----------------------------------------------------------------------
         ops.news_encoder_fwd(news_shape, b["ids"], table, news_flat, news_saved, p, seed, gm,
                              out=b["news_vec"])
@@ -457,10 +464,9 @@ class FusedTrainer:
         ub = (user_shape, hist_vec, user_flat, b["d_user_vec"], user_saved, user_scratch,
               self.flat_grad[self.n_enc:], d_hist, gm)
         ops.user_encoder_bwd(*ub, phase=ops.BWD_DATA)
-        if getattr(self, "_side2", None) is None:
-            self._side2 = torch.cuda.Stream(device=dev)
-        self._side2.wait_stream(main)
-        ops.user_encoder_bwd(*ub, phase=ops.BWD_PARAMS, stream=self._side2)
+        if side2 is not main:
+            side2.wait_stream(main)
+        ops.user_encoder_bwd(*ub, phase=ops.BWD_PARAMS, stream=side2)
         M = n_titles * T
         nb = (news_shape, b["ids"], table, news_flat, b["d_news_vec"], news_saved, news_scratch,
               self.flat_grad[:self.n_enc], b["d_rows"], p, seed, gm)
@@ -471,14 +477,16 @@ class FusedTrainer:
         if self.world > 1 and not sharded:
             # dense exchange: all-reduce of the whole table gradient underneath the weight-gradient GEMMs, then
             # the replicated Adam
-            main.wait_stream(self._side)
+            if side is not main:
+                main.wait_stream(side)
             ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad)
             pending = self.exchange.allreduce([self.table_grad], async_op=True)
         else:
-            tstream = self._comm if sharded else self._side      # (the plan was computed on self._side)
-            tstream.wait_stream(main)
-            if sharded:
-                tstream.wait_stream(self._side)
+            tstream = (self._comm if self.overlap else main) if sharded else side   # (the plan was computed on `side`)
+            if tstream is not main:
+                tstream.wait_stream(main)
+            if sharded and side is not tstream:
+                tstream.wait_stream(side)
             ops.embedding_grad_dense(plan, b["d_rows"], M, V, D, self.table_grad, stream=tstream)
             if sharded:
                 with torch.cuda.stream(tstream):      # (torch.distributed takes the current stream)
@@ -490,7 +498,8 @@ class FusedTrainer:
                 ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
                               b1, b2, self.eps, stream=tstream)
         ops.news_encoder_bwd(*nb, phase=ops.BWD_PARAMS)
-        main.wait_stream(self._side2)             # the user encoder's half of flat_grad
+        if side2 is not main:
+            main.wait_stream(side2)               # the user encoder's half of flat_grad
         pending += (self.exchange_flat if sharded else self.exchange).allreduce([self.flat_grad], async_op=True)
         for h_ in pending:
             h_.wait()
@@ -500,8 +509,8 @@ class FusedTrainer:
         if self.world > 1 and not sharded:
             ops.adam_step(table, self.table_grad, self.table_m, self.table_v, self.step_count, self.lr,
                           b1, b2, self.eps)
-        else:
-            main.wait_stream(self._comm if sharded else self._side)   # the updated table is what the next forward reads
+        elif tstream is not main:
+            main.wait_stream(tstream)             # the updated table is what the next forward reads
         self.model._nrms_weights_version = getattr(self.model, "_nrms_weights_version", 0) + 1
         if "slot_free" in b:                      # this step's input slot may be overwritten from here on
             ev = b["slot_free"][b["slot"]]

@@ -10,13 +10,14 @@ import json
 import sys
 
 LABELS = [   # (substring of the ncu function name, bench.py label)
-    ("attn_mma_bwd", "attn_bwd"), ("attn_bwd_kernel", "attn_bwd"), ("attn_hpn_bwd", "attn_bwd"),
+    ("attn_mma_bwd", "attn_bwd"), ("attn_bwd_kernel", "attn_bwd"), ("attn_hpn_bwd", "attn_bwd"), ("attn_hpl_bwd", "attn_bwd"),
     ("attn_mma_fwd", "attn_fwd"), ("attn_fwd_kernel", "attn_fwd"), ("attn_hp_fwd", "attn_fwd"), ("attn_hpn_fwd", "attn_fwd"),
-    ("ig_gemm_kernel<0, 0, 240, 0>", "gemm_fwd_qkv"), ("ig_gemm_kernel<0, 0, 256, 6>", "gemm_fwd_qkv"),
-    ("ig_gemm_kernel<0, 0, 208, 1>", "gemm_fwd_additive"),
-    ("ig_gemm_kernel<0, 1, 320, 5>", "gemm_dgrad_additive"), ("ig_gemm_kernel<0, 1, 64, 5>", "gemm_dgrad_additive"),
-    ("ig_gemm_kernel<0, 1, 320, 3>", "gemm_dgrad_qkv"), ("ig_gemm_kernel<0, 1, 64, 3>", "gemm_dgrad_qkv"),
-    ("ig_gemm_kernel<1, 1, 320, 4>", "gemm_wgrad"), ("gather_rows_img", "gather"), ("pool_fwd", "pool_fwd"),
+    ("attn_hpl_fwd", "attn_fwd"),
+    ("ig_gemm_kernel<0, 0, 240, 0", "gemm_fwd_qkv"), ("ig_gemm_kernel<0, 0, 256, 6", "gemm_fwd_qkv"),
+    ("ig_gemm_kernel<0, 0, 208, 1", "gemm_fwd_additive"),
+    ("ig_gemm_kernel<0, 1, 320, 5", "gemm_dgrad_additive"), ("ig_gemm_kernel<0, 1, 64, 5", "gemm_dgrad_additive"),
+    ("ig_gemm_kernel<0, 1, 320, 3", "gemm_dgrad_qkv"), ("ig_gemm_kernel<0, 1, 64, 3", "gemm_dgrad_qkv"),
+    ("ig_gemm_kernel<1, 1, 320, 4", "gemm_wgrad"), ("gather_rows_img", "gather"), ("pool_fwd", "pool_fwd"),
     ("pool_bwd", "pool_bwd"), ("adam_kernel", "adam"), ("embgrad_reduce", "embgrad_reduce"), ("reduce_wgrad", "reduce_wgrad"),
     ("reduce_rows", "reduce_rows"), ("img_pack", "img_pack"), ("score_kernel", "score_1"), ("zero_kernel", "zero"), ("plan_", "plan"),
 ]
