@@ -580,15 +580,20 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
             constexpr int MY_OV = OV_BLK / 2, MY_REST = (N_BLK - OV_BLK) / 2;
             static_assert(DOUBLE_ACC || MY_REST >= 1, "the release point sits before the first non-overlap block");
             const int n_mine = DOUBLE_ACC ? (half == 0 ? H0 : N_BLK - H0) : MY_OV + MY_REST;
+            auto block_of = [&](int bi) {
+                if (DOUBLE_ACC) return half == 0 ? bi : H0 + bi;
+                const int ov0 = buf == 0 ? N_BLK - OV_BLK : 0;      // first overlap block (local numbering)
+                const int rest0 = buf == 0 ? 0 : OV_BLK;            // first block outside the overlap
+                return bi < MY_OV ? ov0 + half * MY_OV + bi : rest0 + half * MY_REST + (bi - MY_OV);
+            };
+            // The TMEM read of block bi + 1 is in flight while block bi is processed (tcgen05.ld is asynchronous;
+            // the epilogue has one or two warps per scheduler, so an exposed load latency is dead time).
+            uint32_t vnext[32];
+            if (n_mine > 0) tc::tmem_ld32_issue(t_row + 32u * (uint32_t)block_of(0), vnext);
 #pragma unroll 1
             for (int bi = 0; bi < n_mine; ++bi) {
-                int blk;
-                if (DOUBLE_ACC) {
-                    blk = half == 0 ? bi : H0 + bi;
-                } else {
-                    const int ov0 = buf == 0 ? N_BLK - OV_BLK : 0;      // first overlap block (local numbering)
-                    const int rest0 = buf == 0 ? 0 : OV_BLK;            // first block outside the overlap
-                    blk = bi < MY_OV ? ov0 + half * MY_OV + bi : rest0 + half * MY_REST + (bi - MY_OV);
+                const int blk = block_of(bi);
+                if (!DOUBLE_ACC) {
                     if (bi == MY_OV) {
                         // the overlap columns are in registers / stored: the next tile's main loop may start
                         tc::tc_fence_before();
@@ -603,7 +608,10 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                 if ((EPI == EPI_MASK || EPI == EPI_POOLADD) && a.mask_bits && row_ok && ((n0 + cb) >> 5) < a.mask_words)
                     mword = __ldg(a.mask_bits + (long long)m * a.mask_words + ((n0 + cb) >> 5));
                 float v[32];
-                tc::tmem_ld32(t_row + (uint32_t)cb, v);
+                tc::tmem_ld32_arrive(vnext);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vnext[i]);
+                if (bi + 1 < n_mine) tc::tmem_ld32_issue(t_row + 32u * (uint32_t)block_of(bi + 1), vnext);
                 if (EPI == EPI_BIAS_SPLIT) {
                     // TMEM gives a lane one output row; 32 columns = one head of the head-padded order, i.e.
                     // one 64-byte row of a head block per plane.  The rows go through the warp's staging
