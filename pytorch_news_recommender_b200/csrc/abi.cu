@@ -637,8 +637,8 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     }
                 } else if (L > 32) {
                     using C = HpN<64>;
-                    const size_t smem = (size_t)C::ITEMS_BWD * C::ITEM_BWD;
-                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), 2 * kNumSMs);
+                    const size_t smem = (size_t)C::ITEMS_BWD * C::item_bwd(terms);
+                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), (terms == 3 ? 2 : 3) * kNumSMs);
                     const int threads = C::ITEMS_BWD * C::NW * 32;
                     if (terms == 3) {
                         if ((rc = set_smem(attn_hpn_bwd_kernel<3, 64>, smem))) return rc;

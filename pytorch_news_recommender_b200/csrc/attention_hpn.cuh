@@ -35,6 +35,10 @@ struct HpN {
     static constexpr int PPLANE = LT * PROWB;
     static constexpr bool SEP = LT > 32;               // P / dS in their own buffers
     static constexpr int ITEM_BWD = 4 * PAIR + (SEP ? 4 * PPLANE : 0);
+    // plain-bf16 products (TERMS == 1) never touch the lo planes of P / dS: half the separate planes, which
+    // lets a third 64-row item fit an SM (59 KB instead of 77 KB per item)
+    static constexpr int ITEM_BWD_HI = 4 * PAIR + (SEP ? 2 * PPLANE : 0);
+    __host__ __device__ static constexpr int item_bwd(int terms) { return terms == 3 ? ITEM_BWD : ITEM_BWD_HI; }
     static constexpr int ITEM_FWD = 2 * PAIR + LT * 8;
     static constexpr int ITEMS_BWD = LT == 32 ? 4 : 1; // items per CTA (4 x 2 warps = 256 threads: 128 registers each, no spills; 5 measured 7 % slower)
     static constexpr int ITEMS_FWD = LT == 32 ? 5 : 2;
@@ -326,13 +330,13 @@ __global__ void __launch_bounds__(HpN<LT>::ITEMS_BWD* HpN<LT>::NW * 32, 2) attn_
     const int g = lane >> 2, t = lane & 3;
     const int L = a.L, D = a.D, dk = a.dk, DP = 32 * a.n_heads;
     const long long stride = (long long)gridDim.x * C::ITEMS_BWD;
-    uint8_t* Qb = sm + (size_t)slot * C::ITEM_BWD;
+    uint8_t* Qb = sm + (size_t)slot * C::item_bwd(TERMS);
     const uint32_t Qs = (uint32_t)__cvta_generic_to_shared(Qb);   // Q  -> dK staging
     const uint32_t Ks = Qs + C::PAIR;                             // K  -> dQ staging
     const uint32_t Vs = Ks + C::PAIR;                             // V  (-> P when LT = 32) -> dV staging
     const uint32_t Gs = Vs + C::PAIR;                             // dO fp32 tile -> dO planes (-> dS when LT = 32)
     const uint32_t Ps = C::SEP ? Gs + C::PAIR : Vs;               // P[row][key] planes
-    const uint32_t Ss = C::SEP ? Ps + 2 * C::PPLANE : Gs;         // dS[row][key] planes
+    const uint32_t Ss = C::SEP ? Ps + (TERMS == 3 ? 2 : 1) * C::PPLANE : Gs;   // dS[row][key] planes
     float* const stageQ = reinterpret_cast<float*>(Qb);
     float* const stageK = reinterpret_cast<float*>(Qb + C::PAIR);
     float* const stageV = reinterpret_cast<float*>(Qb + 2 * C::PAIR);
