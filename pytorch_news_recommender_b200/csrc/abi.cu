@@ -4,8 +4,6 @@
 #include "../../include/nrms_b200.h"
 
 #include <algorithm>
-#include <map>
-#include <tuple>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -333,25 +331,6 @@ AttnCfg attn_bwd_cfg(int L, int n_heads, int n_seq) {
     return c;
 }
 
-// grid of a persistent kernel (CTAs loop over items with stride gridDim): exactly the CTAs that are resident
-// at once — a grid larger than that runs in waves and its last wave is partly empty
-template <typename K>
-unsigned resident_grid(K kernel, int threads, size_t smem, long long items) {
-    // (asked once per (kernel, block size, shared memory): the answer does not change)
-    static thread_local std::map<std::tuple<const void*, int, size_t>, int> cache;
-    const auto key = std::make_tuple(reinterpret_cast<const void*>(kernel), threads, smem);
-    auto it = cache.find(key);
-    if (it == cache.end()) {
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
-            (void)cudaGetLastError();
-            per_sm = 1;
-        }
-        it = cache.emplace(key, per_sm).first;
-    }
-    return (unsigned)std::min<long long>(items, (long long)it->second * kNumSMs);
-}
-
 template <typename K>
 int set_smem(K kernel, size_t smem) {
     NRMS_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -454,14 +433,13 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 // one CTA per (sequence, head), a warp per 16 rows, keys in tiles of 64 with an online softmax
                 // (attention_hpl.cuh)
                 const size_t smem = attn_hpl_fwd_smem_bytes(L);
+                const unsigned grid = (unsigned)std::min<long long>(items, 8ll * kNumSMs);
                 const int threads = hpl_warps(L) * 32;
                 if (terms == 3) {
                     if ((rc = set_smem(attn_hpl_fwd_kernel<3>, smem))) return rc;
-                    const unsigned grid = resident_grid(attn_hpl_fwd_kernel<3>, threads, smem, items);
                     NRMS_LAUNCH("attn_fwd", s, (attn_hpl_fwd_kernel<3><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
                 } else {
                     if ((rc = set_smem(attn_hpl_fwd_kernel<1>, smem))) return rc;
-                    const unsigned grid = resident_grid(attn_hpl_fwd_kernel<1>, threads, smem, items);
                     NRMS_LAUNCH("attn_fwd", s, (attn_hpl_fwd_kernel<1><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
                 }
             } else if (L > 32) {
@@ -479,14 +457,12 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 }
             } else {
             const size_t smem = attn_hp_fwd_smem_bytes();
-            const long long ctas = ceil_div64(items, kHpFwdWarps);   // persistent warps: grid = resident CTAs
+            const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpFwdWarps), 2 * kNumSMs);   // persistent warps
             if (terms == 3) {
                 if ((rc = set_smem(attn_hp_fwd_kernel<3>, smem))) return rc;
-                const unsigned grid = resident_grid(attn_hp_fwd_kernel<3>, kHpFwdWarps * 32, smem, ctas);
                 NRMS_LAUNCH("attn_fwd", s, (attn_hp_fwd_kernel<3><<<grid, kHpFwdWarps * 32, smem, s>>>(a, items)));
             } else {
                 if ((rc = set_smem(attn_hp_fwd_kernel<1>, smem))) return rc;
-                const unsigned grid = resident_grid(attn_hp_fwd_kernel<1>, kHpFwdWarps * 32, smem, ctas);
                 NRMS_LAUNCH("attn_fwd", s, (attn_hp_fwd_kernel<1><<<grid, kHpFwdWarps * 32, smem, s>>>(a, items)));
             }
             }
@@ -650,42 +626,37 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 if (L >= hpl_min(false)) {
                     a.ctx_img = sv.ctx_img;     // delta = dO . O comes from the saved context image
                     const size_t smem = attn_hpl_bwd_smem_bytes(L);
+                    const unsigned grid = (unsigned)std::min<long long>(items, 8ll * kNumSMs);
                     const int threads = hpl_warps(L) * 32;
                     if (terms == 3) {
                         if ((rc = set_smem(attn_hpl_bwd_kernel<3>, smem))) return rc;
-                        const unsigned grid = resident_grid(attn_hpl_bwd_kernel<3>, threads, smem, items);
                         NRMS_LAUNCH("attn_bwd", s, (attn_hpl_bwd_kernel<3><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
                     } else {
                         if ((rc = set_smem(attn_hpl_bwd_kernel<1>, smem))) return rc;
-                        const unsigned grid = resident_grid(attn_hpl_bwd_kernel<1>, threads, smem, items);
                         NRMS_LAUNCH("attn_bwd", s, (attn_hpl_bwd_kernel<1><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
                     }
                 } else if (L > 32) {
                     using C = HpN<64>;
                     const size_t smem = (size_t)C::ITEMS_BWD * C::item_bwd(terms);
-                    const long long ctas = ceil_div64(items, C::ITEMS_BWD);
+                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), (terms == 3 ? 2 : 3) * kNumSMs);
                     const int threads = C::ITEMS_BWD * C::NW * 32;
                     if (terms == 3) {
                         if ((rc = set_smem(attn_hpn_bwd_kernel<3, 64>, smem))) return rc;
-                        const unsigned grid = resident_grid(attn_hpn_bwd_kernel<3, 64>, threads, smem, ctas);
                         NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<3, 64><<<grid, threads, smem, s>>>(a, items)));
                     } else {
                         if ((rc = set_smem(attn_hpn_bwd_kernel<1, 64>, smem))) return rc;
-                        const unsigned grid = resident_grid(attn_hpn_bwd_kernel<1, 64>, threads, smem, ctas);
                         NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<1, 64><<<grid, threads, smem, s>>>(a, items)));
                     }
                 } else {
                     using C = HpN<32>;
                     const size_t smem = (size_t)C::ITEMS_BWD * C::ITEM_BWD;
-                    const long long ctas = ceil_div64(items, C::ITEMS_BWD);
+                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), 2 * kNumSMs);
                     const int threads = C::ITEMS_BWD * C::NW * 32;
                     if (terms == 3) {
                         if ((rc = set_smem(attn_hpn_bwd_kernel<3, 32>, smem))) return rc;
-                        const unsigned grid = resident_grid(attn_hpn_bwd_kernel<3, 32>, threads, smem, ctas);
                         NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<3, 32><<<grid, threads, smem, s>>>(a, items)));
                     } else {
                         if ((rc = set_smem(attn_hpn_bwd_kernel<1, 32>, smem))) return rc;
-                        const unsigned grid = resident_grid(attn_hpn_bwd_kernel<1, 32>, threads, smem, ctas);
                         NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<1, 32><<<grid, threads, smem, s>>>(a, items)));
                     }
                 }
