@@ -11,9 +11,9 @@ On-disk inputs (the files the reference reads; synthetic writers in `synthetic.w
 Building `idx_*.pkl` from the raw MIND dumps (`News_Processor`, nltk tokenisation) is the
 reference's preprocessing, out of scope here: `load_dataset` reads the cached list only.
 
-`MyDataset.__getitem__` follows data_handler.py:185-250 line for line (zero-initialised int64
-arrays, front-aligned fill, `[:sample_size]` truncation of the candidates, uint8 masks) and is the
-host-side mirror that `torch.utils.data.DataLoader` can drive exactly like the reference's.
+`MyDataset` produces per sample what data_handler.py:185-250 produces (zero int64 arrays, front-aligned
+fill, `[:sample_size]` truncation of the candidates, uint8 masks) from dense token tables built once, and
+is the host-side mirror that `torch.utils.data.DataLoader` can drive exactly like the reference's.
 
 `DeviceBatcher` replaces DataLoader + MyDataset for the hot path: the ragged sample lists are packed
 ONCE into padded id matrices, the title dict becomes a resident `[n_news, T]` int64 table in HBM,
@@ -82,14 +82,50 @@ def get_Demo_Words_Infos(config):
     return _words_infos(config, 'demo_')
 
 
+def _front_aligned(values, slots: int) -> np.ndarray:
+    """`values` at the front of a zero int64 vector of `slots` entries (a longer list is a ValueError, the
+    broadcast error the reference's slice assignment raises)."""
+    out = np.zeros(slots, dtype=np.int64)
+    out[:len(values)] = np.asarray(values, dtype=np.int64)
+    return out
+
+
+class _TokenTable:
+    """A news-row -> token-list dict as one dense matrix (row r = dict[r]) plus a presence mask, so that a
+    sample's titles are ONE fancy-indexing gather instead of a Python list per news."""
+
+    def __init__(self, mapping: Dict[int, Sequence[int]], width: int):
+        n = (max(mapping) + 1) if mapping else 0
+        self.rows = np.zeros((n, width), dtype=np.int64)
+        self.present = np.zeros(n, dtype=bool)
+        for r, toks in mapping.items():
+            self.rows[r, :] = np.asarray(toks, dtype=np.int64)
+            self.present[r] = True
+
+    def lookup(self, news_ids, slots: int) -> np.ndarray:
+        """[slots, width]: row k = tokens of news id news_ids[k] (id = row + 1), zero rows behind."""
+        out = np.zeros((slots, self.rows.shape[1]), dtype=np.int64)
+        r = np.asarray(news_ids, dtype=np.int64) - 1
+        if r.size:
+            bad = (r < 0) | (r >= self.present.size)
+            if bad.any() or not self.present[r].all():
+                raise KeyError(int(r[bad][0]) if bad.any() else int(r[~self.present[r]][0]))   # the reference: dict KeyError
+            out[:r.size] = self.rows[r]
+        return out
+
+
 class MyDataset(Dataset):
-    """data_handler.py:161-250.  `datas` is the list `load_dataset` returns."""
+    """Host-side loader with the reference's interface and per-sample output (data_handler.py:161-250:
+    same keys, dtypes and shapes, front-aligned zero padding, `[:sample_size]` truncation of the
+    candidates, uint8 masks), so that `torch.utils.data.DataLoader` drives it exactly like the
+    reference's.  It exists for the drop-in scripts and as the checker of `DeviceBatcher`; the hot path
+    assembles batches on the GPU.  `datas` is the list `load_dataset` returns."""
 
     def __init__(self, config, datas, type=0, words_infos=None):
         super().__init__()
         self.config = config
         self.data_type = type
-        self.bacthes = datas
+        self.bacthes = datas          # (sic) the reference's attribute name
         if words_infos is not None:
             self.id2title_dict, self.id2abst_dict = words_infos
         elif getattr(config, 'mode', None) == 'demo':
@@ -97,62 +133,27 @@ class MyDataset(Dataset):
         else:
             self.id2title_dict, self.id2abst_dict = get_Words_Infos(config)
         self.sample_size = self.config.sample_size + 1 if type < 1 else self.config.max_candidate_size
+        self._titles = _TokenTable(self.id2title_dict, config.n_words_title)
+        n_abst = getattr(config, 'n_words_abst', 0)
+        self._absts = _TokenTable(self.id2abst_dict, n_abst) if (n_abst and self.id2abst_dict) else None
 
     def __len__(self):
         return len(self.bacthes)
 
     def __getitem__(self, index):
-        cfg, S = self.config, self.sample_size
-        data = self.bacthes[index]
-        H, T = cfg.history_len, cfg.n_words_title
-        A = getattr(cfg, 'n_words_abst', 0)
-        browsed_ids = np.zeros((H), dtype=np.int64)
-        candidate_ids = np.zeros((S), dtype=np.int64)
-        browsed_titles = np.zeros((H, T), dtype=np.int64)
-        browsed_categ_ids = np.zeros((H), dtype=np.int64)
-        browsed_subcateg_ids = np.zeros((H), dtype=np.int64)
-        candidate_titles = np.zeros((S, T), dtype=np.int64)
-        candidate_categ_ids = np.zeros((S), dtype=np.int64)
-        candidate_subcateg_ids = np.zeros((S), dtype=np.int64)
-
-        x = len(data[0])
-        browsed_ids[:x] = np.array(data[0])
-        browsed_mask = torch.ByteTensor([1 for _ in range(x)] + [0 for _ in range(H - x)])
-        if x:
-            browsed_titles[:x, :] = np.array([self.id2title_dict[i - 1] for i in data[0]])
-        browsed_categ_ids[:x] = np.array(data[1])
-        browsed_subcateg_ids[:x] = np.array(data[2])
-
-        cand = data[3][:S]
-        y = len(cand)
-        candidate_ids[:y] = np.array(cand)
-        if y:
-            candidate_titles[:y, :] = np.array([self.id2title_dict[i - 1] for i in cand])
-        ss = len(data[4])
-        candidate_categ_ids[:ss] = np.array(data[4])
-        candidate_subcateg_ids[:ss] = np.array(data[5])
-        candidate_mask = torch.ByteTensor([1 for _ in range(y)] + [0 for _ in range(S - y)])
-
-        out = {'browsed_lens': x,
-               'browsed_ids': browsed_ids,
-               'browsed_titles': browsed_titles,
-               'browsed_categ_ids': browsed_categ_ids,
-               'browsed_subcateg_ids': browsed_subcateg_ids,
-               'browsed_mask': browsed_mask,
-               'candidate_ids': candidate_ids,
-               'candidate_titles': candidate_titles,
-               'candidate_categ_ids': candidate_categ_ids,
-               'candidate_subcateg_ids': candidate_subcateg_ids,
-               'candidate_mask': candidate_mask}
-        if A and self.id2abst_dict:
-            browsed_absts = np.zeros((H, A), dtype=np.int64)
-            candidate_absts = np.zeros((S, A), dtype=np.int64)
-            if x:
-                browsed_absts[:x, :] = np.array([self.id2abst_dict[i - 1] for i in data[0]])
-            if y:
-                candidate_absts[:y, :] = np.array([self.id2abst_dict[i - 1] for i in cand])
-            out['browsed_absts'] = browsed_absts
-            out['candidate_absts'] = candidate_absts
+        H, S = self.config.history_len, self.sample_size
+        hist, hist_categ, hist_subcateg, cand, cand_categ, cand_subcateg = self.bacthes[index][:6]
+        cand = cand[:S]
+        out = {'browsed_lens': len(hist)}
+        for side, ids, slots, categ, subcateg in (('browsed', hist, H, hist_categ, hist_subcateg),
+                                                  ('candidate', cand, S, cand_categ, cand_subcateg)):
+            out[side + '_ids'] = _front_aligned(ids, slots)
+            out[side + '_titles'] = self._titles.lookup(ids, slots)
+            out[side + '_categ_ids'] = _front_aligned(categ, slots)
+            out[side + '_subcateg_ids'] = _front_aligned(subcateg, slots)
+            out[side + '_mask'] = torch.from_numpy((np.arange(slots) < len(ids)).astype(np.uint8))
+            if self._absts is not None:
+                out[side + '_absts'] = self._absts.lookup(ids, slots)
         return out
 
 

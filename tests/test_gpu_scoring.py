@@ -123,3 +123,57 @@ def test_train_demo_call_sequence(fused, built_lib):
         out = model(train_iter[0])
     final = torch.nn.functional.cross_entropy(out, torch.zeros(16, dtype=torch.long, device=out.device)).item()
     assert final < float(np.log(cfg.sample_size + 1))
+
+
+def test_train_loop_evaluates_logs_and_checkpoints(tmp_path, built_lib):
+    """train_eval.train (reference train_eval.py:34-153): warm-up iterations with the rising learning rate,
+    an evaluation every `eval_step` batches and after each epoch, one `log_res` line per evaluation, a
+    checkpoint whenever the dev AUC beats AUC_best — and the reference's quirk that the model stays in eval
+    mode after the first evaluation."""
+    from pytorch_news_recommender_b200 import synthetic as S, train_eval
+    cfg, pool, model = _setup(gemm_mode=1, dropout=0.2)
+    cfg.num_epochs, cfg.learning_rate, cfg.eval_step = 1, 2e-3, 2
+    cfg.warm_up, cfg.warm_up_steps = True, 4
+    cfg.save_flag, cfg.save_path, cfg.log_path = True, str(tmp_path / "save") + "/", str(tmp_path / "logs")
+    train_iter = [S.make_train_batch(pool, 16, cfg.history_len, cfg.sample_size, seed=i) for i in range(5)]
+    imp = S.make_eval_impressions(pool, 40, cfg.history_len, cfg.max_candidate_size, seed=2, mean_candidates=8.0)
+    tt = torch.from_numpy(pool.title_table())
+    dev_iter = [{"browsed_titles": tt[imp["browsed_ids"][i:i + 16]], "candidate_titles": tt[imp["candidate_ids"][i:i + 16]],
+                 "candidate_mask": imp["candidate_mask"][i:i + 16]} for i in range(0, 40, 16)]
+    lines = []
+    w0 = model.state_dict()["user_encoder.additive_attention.linear.weight"].clone()
+    res = train_eval.train(cfg, model, train_iter, dev_iter, y_true=imp["y_true"], log=lambda *a: lines.append(" ".join(map(str, a))))
+    assert res["total_batch"] == 5 and len(res["loss_records"]) == 5
+    assert sum(l.startswith("AUC:") for l in lines) == 3            # batches 2 and 4, then the end of the epoch
+    assert any("warm-up training" in l for l in lines) and any("Warm-up Steps" in l for l in lines)
+    log = open(cfg.log_path + "/res.txt").read().splitlines()
+    assert len(log) == 3 and "_2_:auc_" in log[0] and "_4_:auc_" in log[1]
+    assert log[-1].split("_:auc_")[0].endswith("epoch_0")
+    assert not model.training                                       # (sic) left in eval mode, as the reference
+    assert not torch.equal(w0, model.state_dict()["user_encoder.additive_attention.linear.weight"])
+    ckpts = os.listdir(cfg.save_path) if os.path.isdir(cfg.save_path) else []
+    if res["auc_best"] > 0.56:                                      # a checkpoint exists exactly when the AUC beat 0.56
+        assert ckpts and all(c.endswith(".ckpt") and cfg.model_name in c for c in ckpts)
+        assert train_eval.best_checkpoint(cfg) in ckpts
+    else:
+        assert not ckpts
+
+
+def test_cached_scorer_rebuilds_after_a_weight_update(built_lib):
+    """the news-vector cache must not outlive the weights it was built from."""
+    from pytorch_news_recommender_b200 import synthetic as S
+    from pytorch_news_recommender_b200.engine import FusedTrainer
+    from pytorch_news_recommender_b200.scoring import CachedScorer
+    cfg, pool, model = _setup(gemm_mode=1, dropout=0.0)
+    batch = S.make_train_batch(pool, 9, cfg.history_len, cfg.sample_size, seed=3)
+    scorer = CachedScorer(model, torch.from_numpy(pool.title_table()))
+    before = scorer.score(batch["browsed_ids"], batch["candidate_ids"], batch["candidate_mask"]).clone()
+    model.train()
+    FusedTrainer(model, lr=1e-2).step(batch)
+    model.eval()
+    after = scorer.score(batch["browsed_ids"], batch["candidate_ids"], batch["candidate_mask"])
+    with torch.no_grad():
+        full = model(batch)
+    real = batch["candidate_mask"].bool().cuda()
+    assert not torch.allclose(before[real], after[real])
+    assert ((after - full).abs()[real] / full.abs()[real].clamp_min(1e-3)).max().item() < 1e-4
