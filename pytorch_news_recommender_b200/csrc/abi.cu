@@ -981,16 +981,27 @@ int nrms_embedding_plan(const int64_t* ids, int64_t n_rows, int32_t vocab, void*
                     (long long)plan_bytes(n_rows, vocab));
     cudaStream_t s = (cudaStream_t)stream;
     PlanView v = plan_view(plan, n_rows, vocab);
+    // 1. counts -> offsets, n_valid
     NRMS_CHECK_CUDA(cudaMemsetAsync(v.counts, 0, sizeof(int32_t) * vocab, s));
     NRMS_LAUNCH("plan_hist", s, plan_hist_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.counts));
     const int scan_blocks = ceil_div(vocab, kScanBlock);
     NRMS_LAUNCH("plan_scan", s, plan_block_totals_kernel<<<scan_blocks, kScanBlock, 0, s>>>(v.counts, v.block_tot, vocab));
-    NRMS_LAUNCH("plan_scan", s, plan_scan_kernel<<<scan_blocks, kScanBlock, 0, s>>>(v.counts, v.block_tot, v.offsets, v.cursor,
-                                                                              v.n_valid, vocab));
-    NRMS_LAUNCH("plan_fill", s, plan_fill_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, v.offsets, v.cursor,
-                                                          v.perm, v.sorted_id));
-    NRMS_LAUNCH("plan_sort_segments", s, plan_sort_segments_kernel<<<grid_for((long long)vocab * 32, 256), 256, 0, s>>>(v.offsets, v.perm,
-                                                                                  vocab));
+    NRMS_LAUNCH("plan_scan", s, plan_scan_kernel<<<scan_blocks, kScanBlock, 0, s>>>(v.counts, v.block_tot, v.offsets, v.n_valid, vocab));
+    // 2. stable LSD radix sort of (id, row): keys run up to `vocab` (the key of a padding id)
+    int bits = 1;
+    while ((1ll << bits) <= (long long)vocab) ++bits;
+    const int rb = bits <= 18 ? 9 : 8, passes = ceil_div(bits, rb), bins = 1 << rb;
+    const int nblk = (int)ceil_div64(n_rows, kRsBlock);
+    int32_t *ka = v.sorted_id, *va = v.perm, *kb = v.tmp_key, *vb = v.tmp_val;
+    if (passes % 2) { std::swap(ka, kb); std::swap(va, vb); }   // an odd number of passes must end in (sorted_id, perm)
+    NRMS_LAUNCH("plan_sort", s, rsort_init_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, ka, va));
+    for (int p = 0; p < passes; ++p) {
+        NRMS_LAUNCH("plan_sort", s, rsort_hist_kernel<<<nblk, 256, 0, s>>>(ka, n_rows, p * rb, bins, v.rhist, nblk));
+        NRMS_LAUNCH("plan_sort", s, rsort_scan_kernel<<<1, 1024, 0, s>>>(v.rhist, (long long)bins * nblk));
+        NRMS_LAUNCH("plan_sort", s, rsort_scatter_kernel<<<nblk, 256, 0, s>>>(ka, va, n_rows, p * rb, bins, v.rhist, nblk, kb, vb));
+        std::swap(ka, kb);
+        std::swap(va, vb);
+    }
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
@@ -1006,8 +1017,10 @@ int nrms_embedding_grad_dense(const void* plan, int64_t plan_bytes_, const float
     PlanView v = plan_view(const_cast<void*>(plan), n_rows, vocab);
     const long long n4 = (long long)vocab * D / 4;
     NRMS_LAUNCH("zero", s, zero_kernel<<<grid_for(n4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(d_table), n4));
-    NRMS_LAUNCH("embgrad_reduce", s, embgrad_reduce_kernel<<<grid_for(n_rows, 256, 16), 256, 0, s>>>(v.perm, v.sorted_id, v.offsets,
-                                                                   v.n_valid, d_rows, D, d_table));
+    NRMS_LAUNCH("embgrad_reduce", s, embgrad_reduce_kernel<<<grid_for(n_rows, 256, 16), 256, 0, s>>>(
+        v.perm, v.sorted_id, v.offsets, v.n_valid, d_rows, D, d_table, v.part, v.n_chunks));
+    NRMS_LAUNCH("embgrad_reduce", s, embgrad_fixup_kernel<<<grid_for((long long)vocab * 32, 256, 8), 256, 0, s>>>(
+        v.offsets, vocab, D, v.part, v.n_chunks, d_table));
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }

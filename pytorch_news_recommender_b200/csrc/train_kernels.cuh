@@ -157,34 +157,61 @@ __global__ void __launch_bounds__(256) score_cached_kernel(const ScoreCachedArgs
 }
 
 // ---------------------------------------------------------------------------------------
-// Embedding gradient: counting sort of token rows by vocab id, then a load-balanced
-// segmented reduction (one warp per 32 sorted rows) into the dense table gradient.
+// Embedding gradient: stable sort of the token rows by vocab id, then a load-balanced segmented
+// reduction (one warp per 32 sorted rows) into the dense table gradient.
 // Replaces 55 x (zero-fill [V,D] + scatter + accumulate) of the reference.
-// plan blob: int32 counts[V] | int32 offsets[V+1] | int32 cursor[V] | int32 perm[n_rows]
-//            | int32 sorted_id[n_rows] | int32 n_valid | int32 block_tot[ceil(V/1024)]
+//
+// Everything here is DETERMINISTIC, also for words that occur thousands of times in a step (Zipf / real
+// text): the rows of a word are summed in ascending row order, in fixed 32-row pieces, and pieces are
+// combined in piece order — no floating-point atomics and no order handed out by an atomic cursor.
+//   1. counts / offsets: histogram (integer atomics: exact) + two-level exclusive scan;
+//   2. (id, row) pairs sorted by id with a stable LSD radix sort (rows of one id stay in row order);
+//   3. one warp per 32 sorted rows sums runs of equal id; a run that lies inside its chunk is stored, a
+//      run that crosses a chunk edge leaves its piece in a partial slot of that chunk;
+//   4. one warp per multi-chunk word adds that word's pieces in chunk order and stores the row.
+// plan blob: int32 counts[V] | offsets[V+1] | perm[n] | sorted_id[n] | n_valid | block_tot[ceil(V/1024)]
+//            | tmp_key[n] | tmp_val[n] | radix hist[512 * ceil(n/2048)] | float part[2][ceil(n/32)][kPartLd]
 // ---------------------------------------------------------------------------------------
+constexpr int kPartLd = 384;          // floats per partial slot (the kernels support D <= 384)
+constexpr int kRsBlock = 2048;        // keys per CTA of the radix passes (8 warps x 8 x 32)
+constexpr int kRsMaxBins = 512;
+
 struct PlanView {
     int32_t* counts;
     int32_t* offsets;
-    int32_t* cursor;
     int32_t* perm;
     int32_t* sorted_id;
     int32_t* n_valid;
     int32_t* block_tot;
+    int32_t* tmp_key;
+    int32_t* tmp_val;
+    int32_t* rhist;
+    float* part;          // [2][n_chunks][kPartLd]: slot 0 = piece of a run that began in an EARLIER chunk,
+                          //                           slot 1 = piece of a run that continues into the NEXT chunk
+    long long n_chunks;
 };
+inline int64_t plan_ints(int64_t n_rows, int32_t vocab) {
+    return 2ll * vocab + 1 + 2 * n_rows + 4 + (vocab + 1023) / 1024 + 2 * n_rows + (int64_t)kRsMaxBins * ceil_div64(n_rows, kRsBlock);
+}
 inline int64_t plan_bytes(int64_t n_rows, int32_t vocab) {
-    return align_up((int64_t)sizeof(int32_t) * (3ll * vocab + 1 + 2 * n_rows + 4 + (vocab + 1023) / 1024), 256);
+    return align_up((int64_t)sizeof(int32_t) * plan_ints(n_rows, vocab), 256) +
+           (int64_t)sizeof(float) * 2 * ceil_div64(n_rows, 32) * kPartLd;
 }
 inline PlanView plan_view(void* blob, int64_t n_rows, int32_t vocab) {
     PlanView v;
     int32_t* p = reinterpret_cast<int32_t*>(blob);
     v.counts = p;
     v.offsets = v.counts + vocab;
-    v.cursor = v.offsets + vocab + 1;
-    v.perm = v.cursor + vocab;
+    v.perm = v.offsets + vocab + 1;
     v.sorted_id = v.perm + n_rows;
     v.n_valid = v.sorted_id + n_rows;
-    v.block_tot = v.n_valid + 1;
+    v.block_tot = v.n_valid + 4;
+    v.tmp_key = v.block_tot + (vocab + 1023) / 1024;
+    v.tmp_val = v.tmp_key + n_rows;
+    v.rhist = v.tmp_val + n_rows;
+    v.part = reinterpret_cast<float*>(reinterpret_cast<char*>(blob) +
+                                      align_up((int64_t)sizeof(int32_t) * plan_ints(n_rows, vocab), 256));
+    v.n_chunks = ceil_div64(n_rows, 32);
     return v;
 }
 
@@ -199,7 +226,7 @@ __global__ void plan_hist_kernel(const int64_t* __restrict__ ids, long long n, i
 
 // Exclusive scan of counts[V] -> offsets[V+1] in two small launches of ceil(V/1024) CTAs:
 // (1) per-CTA totals, (2) every CTA sums the totals of the CTAs before it (at most a few hundred
-// values) and scans its own 1024 counts.  cursor = 0; n_valid = total.
+// values) and scans its own 1024 counts.  n_valid = total.
 constexpr int kScanBlock = 1024;
 
 __device__ __forceinline__ int32_t block_inclusive_scan(int32_t x, int32_t* warp_tot /*[32]*/, int32_t* total) {
@@ -239,7 +266,6 @@ __global__ void __launch_bounds__(kScanBlock) plan_block_totals_kernel(const int
 __global__ void __launch_bounds__(kScanBlock) plan_scan_kernel(const int32_t* __restrict__ counts,
                                                               const int32_t* __restrict__ block_tot,
                                                               int32_t* __restrict__ offsets,
-                                                              int32_t* __restrict__ cursor,
                                                               int32_t* __restrict__ n_valid, int vocab) {
     __shared__ int32_t warp_tot[32];
     __shared__ int32_t total;
@@ -255,54 +281,100 @@ __global__ void __launch_bounds__(kScanBlock) plan_scan_kernel(const int32_t* __
     const int i = blockIdx.x * kScanBlock + threadIdx.x;
     const int32_t c = i < vocab ? counts[i] : 0;
     const int32_t inc = block_inclusive_scan(c, warp_tot, &total);
-    if (i < vocab) {
-        offsets[i] = base + inc - c;
-        cursor[i] = 0;
-    }
+    if (i < vocab) offsets[i] = base + inc - c;
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         offsets[vocab] = base + total;
         *n_valid = base + total;
     }
 }
 
-__global__ void plan_fill_kernel(const int64_t* __restrict__ ids, long long n, int vocab,
-                                 const int32_t* __restrict__ offsets,
-                                 int32_t* __restrict__ cursor, int32_t* __restrict__ perm,
-                                 int32_t* __restrict__ sorted_id) {
+// ---- stable LSD radix sort of (key = vocab id, value = token row) --------------------------------
+// key of a padding / out-of-range id = vocab (sorts behind every real id); values start as 0..n-1, so after
+// the stable passes the rows of one id are in ascending row order.
+__global__ void rsort_init_kernel(const int64_t* __restrict__ ids, long long n, int vocab,
+                                  int32_t* __restrict__ key, int32_t* __restrict__ val) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const long long id = ids[i];
-        if (id > 0 && id < vocab) {
-            const int32_t pos = offsets[id] + atomicAdd(cursor + id, 1);
-            perm[pos] = (int32_t)i;
-            sorted_id[pos] = (int32_t)id;
-        }
+        key[i] = (id > 0 && id < vocab) ? (int32_t)id : vocab;
+        val[i] = (int32_t)i;
     }
 }
-
-// Rows of one id land in arbitrary order inside their segment (atomic cursor); sorting each
-// short segment restores a deterministic summation order.  One warp per vocab row, segments
-// up to 32 entries are bitonic-sorted in registers; longer ones are left as they are.
-__global__ void plan_sort_segments_kernel(const int32_t* __restrict__ offsets,
-                                          int32_t* __restrict__ perm, int vocab) {
-    const int lane = threadIdx.x & 31;
-    const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long v = warp_g; v < vocab; v += nwarps) {
-        const int beg = offsets[v], len = offsets[v + 1] - beg;
-        if (len < 2 || len > 32) continue;
-        int32_t x = lane < len ? perm[beg + lane] : 0x7fffffff;
+// digit histogram of each 2048-key block: hist[digit * nblk + block]
+__global__ void __launch_bounds__(256) rsort_hist_kernel(const int32_t* __restrict__ key, long long n, int shift,
+                                                        int bins, int32_t* __restrict__ hist, int nblk) {
+    __shared__ int32_t h[kRsMaxBins];
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const long long base = (long long)blockIdx.x * kRsBlock;
+    for (int i = threadIdx.x; i < kRsBlock; i += blockDim.x)
+        if (base + i < n) atomicAdd(&h[(key[base + i] >> shift) & (bins - 1)], 1);
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[(long long)i * nblk + blockIdx.x] = h[i];
+}
+// exclusive scan of hist[bins * nblk] in place (digit-major: all blocks of digit 0, then digit 1, ...): one CTA
+__global__ void __launch_bounds__(1024) rsort_scan_kernel(int32_t* __restrict__ hist, long long total) {
+    __shared__ int32_t warp_tot[32];
+    __shared__ int32_t tot;
+    const long long per = ceil_div64(total, 1024);
+    const long long lo = threadIdx.x * per, hi = lo + per < total ? lo + per : total;
+    int32_t sum = 0;
+    for (long long i = lo; i < hi; ++i) sum += hist[i];
+    const int32_t inc = block_inclusive_scan(sum, warp_tot, &tot);
+    int32_t run = inc - sum;
+    for (long long i = lo; i < hi; ++i) {
+        const int32_t c = hist[i];
+        hist[i] = run;
+        run += c;
+    }
+}
+// stable scatter: warp w of a block owns keys [256 w, 256 w + 256) of the block and walks them in order, 32
+// at a time; the rank of a key among the block's earlier keys of the same digit = (count in earlier warps) +
+// (count in this warp's earlier groups) + (earlier lanes of its group with the same digit)
+__global__ void __launch_bounds__(256) rsort_scatter_kernel(const int32_t* __restrict__ key, const int32_t* __restrict__ val,
+                                                           long long n, int shift, int bins,
+                                                           const int32_t* __restrict__ base, int nblk,
+                                                           int32_t* __restrict__ key_out, int32_t* __restrict__ val_out) {
+    __shared__ int32_t wh[8][kRsMaxBins];      // per-warp digit counts, then exclusive prefix over the warps
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 8 * kRsMaxBins; i += blockDim.x) (&wh[0][0])[i] = 0;
+    __syncthreads();
+    const long long b0 = (long long)blockIdx.x * kRsBlock + warp * 256;
+    int32_t k[8], v[8], rank[8];
 #pragma unroll
-        for (int k = 2; k <= 32; k <<= 1) {
+    for (int j = 0; j < 8; ++j) {
+        const long long i = b0 + j * 32 + lane;
+        const bool ok = i < n;
+        k[j] = ok ? key[i] : 0;
+        v[j] = ok ? val[i] : 0;
+        const int d = ok ? (k[j] >> shift) & (bins - 1) : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int before = __popc(peers & ((1u << lane) - 1u));
+        rank[j] = ok ? wh[warp][d] + before : 0;
+        __syncwarp();
+        if (ok && before == 0) wh[warp][d] += __popc(peers);      // the group's first lane of this digit
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < bins; d += blockDim.x) {         // exclusive prefix over the 8 warps, per digit
+        int32_t run = 0;
 #pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                const int32_t y = __shfl_xor_sync(0xffffffffu, x, j);
-                const bool up = ((lane & k) == 0);
-                const bool lower = ((lane & j) == 0);
-                x = (lower == up) ? min(x, y) : max(x, y);
-            }
+        for (int w = 0; w < 8; ++w) {
+            const int32_t c = wh[w][d];
+            wh[w][d] = run;
+            run += c;
         }
-        if (lane < len) perm[beg + lane] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const long long i = b0 + j * 32 + lane;
+        if (i < n) {
+            const int d = (k[j] >> shift) & (bins - 1);
+            const int32_t pos = base[(long long)d * nblk + blockIdx.x] + wh[warp][d] + rank[j];
+            key_out[pos] = k[j];
+            val_out[pos] = v[j];
+        }
     }
 }
 
@@ -313,14 +385,15 @@ __global__ void zero_kernel(float4* __restrict__ p, long long n4) {
         p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// One warp per chunk of 32 sorted rows.  Runs of equal id are summed in registers; a run
-// that lies strictly inside the chunk AND covers its whole segment is stored, any run that
-// touches a chunk edge may continue in the neighbour chunk and is added atomically
-// (red.global.add.v4.f32).  D % 4 == 0, D <= 384 (3 float4 per lane).
+// One warp per chunk of 32 sorted rows.  Runs of equal id are summed in registers (ascending row order).
+// A run that lies inside the chunk AND is its word's whole segment is stored into the table gradient; a run
+// that crosses a chunk edge leaves its piece in the chunk's partial slot (0: the run began in an earlier
+// chunk; 1: it continues into the next one) for embgrad_fixup_kernel.  D % 4 == 0, D <= 384.
 __global__ void __launch_bounds__(256) embgrad_reduce_kernel(
     const int32_t* __restrict__ perm, const int32_t* __restrict__ sorted_id,
     const int32_t* __restrict__ offsets, const int32_t* __restrict__ n_valid_p,
-    const float* __restrict__ d_rows, int D, float* __restrict__ d_table) {
+    const float* __restrict__ d_rows, int D, float* __restrict__ d_table, float* __restrict__ part,
+    long long n_chunks) {
     const int lane = threadIdx.x & 31;
     const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -339,22 +412,13 @@ __global__ void __launch_bounds__(256) embgrad_reduce_kernel(
             if (id != cur) {
                 // flush run [.., r) of id `cur`
                 const int seg_beg = offsets[cur], seg_end = offsets[cur + 1];
-                const bool whole = seg_beg >= base && seg_end <= base + cnt;
-                float* dst = d_table + (long long)cur * D;
+                float* dst;
+                if (seg_beg >= base && seg_end <= base + cnt) dst = d_table + (long long)cur * D;     // whole segment
+                else dst = part + ((seg_beg < base ? 0ll : n_chunks) + chunk) * kPartLd;              // a piece
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     const int col4 = lane + 32 * c;
-                    if (col4 < d4) {
-                        if (whole) {
-                            reinterpret_cast<float4*>(dst)[col4] = acc[c];
-                        } else {
-                            float* a4 = dst + 4 * col4;
-                            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(a4),
-                                         "f"(acc[c].x), "f"(acc[c].y), "f"(acc[c].z),
-                                         "f"(acc[c].w)
-                                         : "memory");
-                        }
-                    }
+                    if (col4 < d4) reinterpret_cast<float4*>(dst)[col4] = acc[c];
                     acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 cur = id;
@@ -371,6 +435,55 @@ __global__ void __launch_bounds__(256) embgrad_reduce_kernel(
                     }
                 }
             }
+        }
+    }
+}
+// One warp per word whose segment spans several chunks: its pieces — the head piece in slot 1 of the first
+// chunk, then slot 0 of every following chunk — are added in chunk order (four loads in flight, adds in order).
+__global__ void __launch_bounds__(256) embgrad_fixup_kernel(const int32_t* __restrict__ offsets, int vocab, int D,
+                                                           const float* __restrict__ part, long long n_chunks,
+                                                           float* __restrict__ d_table) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int d4 = D >> 2;
+    for (long long v = warp_g; v < vocab; v += nwarps) {
+        const int beg = offsets[v], end = offsets[v + 1];
+        if (end <= beg) continue;
+        const int c0 = beg >> 5, c1 = (end - 1) >> 5;
+        if (c0 == c1) continue;                           // stored by the reduction kernel
+        float4 acc[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int col4 = lane + 32 * c;
+            acc[c] = col4 < d4 ? __ldg(reinterpret_cast<const float4*>(part + (n_chunks + c0) * kPartLd) + col4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int ch = c0 + 1; ch <= c1; ch += 4) {
+            float4 t[4][3];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const int col4 = lane + 32 * c;
+                    t[u][c] = (ch + u <= c1 && col4 < d4)
+                                  ? __ldg(reinterpret_cast<const float4*>(part + (long long)(ch + u) * kPartLd) + col4)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ch + u <= c1) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        acc[c].x += t[u][c].x; acc[c].y += t[u][c].y; acc[c].z += t[u][c].z; acc[c].w += t[u][c].w;
+                    }
+                }
+        }
+        float* dst = d_table + v * D;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int col4 = lane + 32 * c;
+            if (col4 < d4) reinterpret_cast<float4*>(dst)[col4] = acc[c];
         }
     }
 }

@@ -18,7 +18,7 @@ LABELS = [   # (substring of the ncu function name, bench.py label)
     ("ig_gemm_kernel<0, 1, 320, 5", "gemm_dgrad_additive"), ("ig_gemm_kernel<0, 1, 64, 5", "gemm_dgrad_additive"),
     ("ig_gemm_kernel<0, 1, 320, 3", "gemm_dgrad_qkv"), ("ig_gemm_kernel<0, 1, 64, 3", "gemm_dgrad_qkv"),
     ("ig_gemm_kernel<1, 1, 320, 4", "gemm_wgrad"), ("gather_rows_img", "gather"), ("pool_fwd", "pool_fwd"),
-    ("pool_bwd", "pool_bwd"), ("adam_kernel", "adam"), ("embgrad_reduce", "embgrad_reduce"), ("reduce_wgrad", "reduce_wgrad"),
+    ("pool_bwd", "pool_bwd"), ("adam_kernel", "adam"), ("embgrad_reduce", "embgrad_reduce"), ("embgrad_fixup", "embgrad_reduce"), ("rsort_", "plan"), ("reduce_wgrad", "reduce_wgrad"),
     ("reduce_rows", "reduce_rows"), ("img_pack", "img_pack"), ("score_kernel", "score_1"), ("zero_kernel", "zero"), ("plan_", "plan"),
 ]
 

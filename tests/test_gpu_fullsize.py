@@ -133,33 +133,26 @@ def test_cfg4_shaped_cached_scoring_and_metrics_match_oracle(built_lib):
     assert res["n_defined"] == 1024
 
 
-def test_zipf_step_run_to_run(built_lib):
-    """What is and is not bitwise repeatable with heavy-tailed tokens.  The forward, the loss and every
-    dense-parameter gradient are reduced in a fixed order: identical bits run to run.  The table gradient
-    sums the rows of one word in 32-row chunks; a word that occurs more than 32 times in a step (every
-    frequent word under Zipf) spans several chunks whose partial sums meet through `red.global.add` in an
-    order the hardware picks, and its rows sit in their segment in the order an atomic cursor handed out
-    (`plan_sort_segments_kernel` only sorts segments of at most 32 rows) — so those rows of the table
-    gradient agree to fp32 rounding (checked: 1e-6 of the row norm), not bit for bit; rows of words with at
-    most 32 occurrences are bitwise repeatable."""
+def test_zipf_step_is_bitwise_repeatable(built_lib):
+    """Heavy-tailed tokens: the most frequent words occur thousands of times in one step, so their rows of
+    the table gradient are sums over hundreds of 32-row pieces.  The (word, row) pairs are sorted by a stable
+    radix sort and the pieces are combined in piece order (no floating-point atomics, no order handed out by
+    an atomic cursor), so the WHOLE step — loss, every dense gradient, every row of the table gradient —
+    is bit-identical run to run (round 1 was only repeatable for words with <= 32 occurrences)."""
     from pytorch_news_recommender_b200 import synthetic as S
     from pytorch_news_recommender_b200.engine import FusedTrainer
-    from pytorch_news_recommender_b200.model import NRMS_V0
     pool = S.make_news_pool(65000, 30, 70000, seed=0, zipf=True)
     batch = S.make_train_batch(pool, 32, 50, 4, seed=1)
     counts = torch.bincount(torch.cat([batch["browsed_titles"].reshape(-1), batch["candidate_titles"].reshape(-1)]),
                             minlength=70000)
+    assert int(counts[1:].max()) > 1000 and int((counts[1:] > 32).sum()) > 50
     runs = []
-    for _ in range(3):
+    for _ in range(4):
         cfg, model, _ = _build()
         model.train()
         tr = FusedTrainer(model)
-        loss = tr.step(batch).item()
-        runs.append((loss, tr.flat_grad.clone(), tr.table_grad.clone()))
-    light = (counts <= 32).cuda()
-    light[0] = True
-    for loss, fg, tg in runs[1:]:
-        assert loss == runs[0][0] and torch.equal(fg, runs[0][1])
-        assert torch.equal(tg[light], runs[0][2][light])
-        d = (tg - runs[0][2]).norm(dim=1)
-        assert float((d / runs[0][2].norm(dim=1).clamp_min(1e-20)).max()) < 1e-5
+        losses = [tr.step(batch).item() for _ in range(2)]
+        runs.append((losses, tr.flat_grad.clone(), tr.table_grad.clone(), model.state_dict()[O.TABLE_KEY].clone()))
+    for losses, fg, tg, tab in runs[1:]:
+        assert losses == runs[0][0] and torch.equal(fg, runs[0][1])
+        assert torch.equal(tg, runs[0][2]) and torch.equal(tab, runs[0][3])
