@@ -145,7 +145,7 @@ def test_zipf_step_is_bitwise_repeatable(built_lib):
     batch = S.make_train_batch(pool, 32, 50, 4, seed=1)
     counts = torch.bincount(torch.cat([batch["browsed_titles"].reshape(-1), batch["candidate_titles"].reshape(-1)]),
                             minlength=70000)
-    assert int(counts[1:].max()) > 1000 and int((counts[1:] > 32).sum()) > 50
+    assert int(counts[1:].max()) > 1000 and int((counts[1:] > 32).sum()) > 20
     runs = []
     for _ in range(4):
         cfg, model, _ = _build()
