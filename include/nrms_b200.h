@@ -161,9 +161,13 @@ int nrms_score_ce_fwd_bwd(int32_t B, int32_t C, int32_t D, int32_t B_global, con
                           float* loss_mean, uint32_t* ticket, nrms_stream_t stream);
 
 /* Deduplicated sparse scatter-add of the embedding-row gradients (the replacement of the 55
- * dense embedding_dense_backward calls).  plan = counting sort of the n_rows
- * ids by vocab row (id 0 = padding_idx, dropped: nrms_v0.py:136).
- *   plan blob layout is private; size it with nrms_embedding_plan_bytes. */
+ * dense embedding_dense_backward calls).  plan = STABLE radix sort of the
+ * (id, row) pairs by vocab row (id 0 = padding_idx, dropped: nrms_v0.py:136), so the rows of
+ * one id are summed in row order on every run; runs that cross a 32-row chunk edge go through
+ * per-chunk partial slots inside the plan blob and are combined in chunk order (no
+ * floating-point atomics: d_table is bitwise repeatable for any id distribution).
+ *   plan blob layout is private; size it with nrms_embedding_plan_bytes (~ 120 bytes per row:
+ *   sort buffers + 2 partial slots of 384 floats per 32 rows). */
 int64_t nrms_embedding_plan_bytes(int64_t n_rows, int32_t vocab);
 int nrms_embedding_plan(const int64_t* ids, int64_t n_rows, int32_t vocab, void* plan,
                         int64_t plan_bytes, nrms_stream_t stream);
