@@ -19,6 +19,13 @@ def make_embedding_table(vocab: int, dim: int = 300, seed: int = 0) -> np.ndarra
     return t
 
 
+def make_news_vector_table(n_news: int, dim: int = 512, seed: int = 0, scale: float = 0.5) -> np.ndarray:
+    """[n_news + 1, dim] stand-in for the pre-computed BERT news vectors of the `nrms` variant
+    (model/nrms.py:222-224, `news_embeds_512.npz`).  Row 0 — the id history padding uses — is an ordinary
+    row: the reference builds this table without padding_idx."""
+    return (np.random.default_rng(seed + 7).standard_normal((n_news + 1, dim)) * scale).astype(np.float32)
+
+
 def save_embedding_npz(path: str, table: np.ndarray) -> None:
     """The npz the model constructor reads: key "embeddings" (nrms_v0.py:134-135)."""
     np.savez(path, embeddings=table)

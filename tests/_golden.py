@@ -70,3 +70,46 @@ def check_summary(case, prefix, tensors, rtol, atol_frac=1e-4, what="", abs_floo
         tol = rtol * np.abs(samples) + atol_frac * rms + abs_floor
         bad = np.abs(got - samples) > tol
         assert not bad.any(), f"{what}{prefix}/{k}: samples differ: {got[bad][:4]} vs {samples[bad][:4]}"
+
+
+class BertCase:
+    """Fixtures of the `nrms` variant (tests/golden/make_golden_bert.py)."""
+
+    def __init__(self, name):
+        from oracle import nrms_bert_oracle as OB
+        self.name = name
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        B, H, C, E, heads, Q, n_news = [int(v) for v in self.z["meta/dims"]]
+        self.B, self.H, self.C, self.E, self.heads, self.Q, self.n_news = B, H, C, E, heads, Q, n_news
+        self.seed = int(self.z["meta/seed"])
+        self.cfg = OB.BertOracleConfig(H, C - 1, E, E, heads, Q, float(self.z["meta/dropout"]), float(self.z["meta/lr"]))
+        self.batch = {
+            "browsed_ids": torch.from_numpy(self.z["in/browsed_ids"].astype(np.int64)),
+            "candidate_ids": torch.from_numpy(self.z["in/candidate_ids"].astype(np.int64)),
+            "browsed_mask": torch.from_numpy(self.z["in/browsed_mask"]),
+            "candidate_mask": torch.from_numpy(self.z["in/candidate_mask"]),
+        }
+        self.table = S.make_news_vector_table(n_news, E, seed=self.seed)
+        self.keys = OB.state_dict_keys()
+        self._OB = OB
+
+    def state_dict(self):
+        if f"sd0/{self.keys[0]}" in self.z:
+            return {k: torch.from_numpy(self.z[f"sd0/{k}"].copy()) for k in self.keys}
+        return self._OB.init_state_dict(self.cfg, self.table, seed=42)
+
+    def mults(self, step):
+        """The dropout multipliers make_golden_bert.py injected at train step `step`."""
+        rng = np.random.default_rng(2000 + self.seed)
+        p = self.cfg.dropout
+        out = None
+        for _ in range(step + 1):
+            out = {}
+            for k, shape in (("cand", (self.B, self.C, self.E)), ("hist", (self.B, self.H, self.E)),
+                             ("attn", (self.B, self.heads, self.H, self.H))):
+                out[k] = torch.from_numpy((rng.random(shape) >= p).astype(np.float32) / np.float32(1.0 - p))
+        return out
+
+    def summary(self, prefix, key):
+        return (float(self.z[f"{prefix}/{key}/norm"]), float(self.z[f"{prefix}/{key}/sum"]),
+                self.z[f"{prefix}/{key}/samples"])

@@ -103,3 +103,38 @@ def test_metric_kats():
         if n10 is not None:
             assert abs(got[3] - n10) < 1e-12
     assert np.isnan(O.impression_metrics([0, 0, 0], [.1, .2, .3])).all()
+
+
+# ---- the `nrms` sibling variant: oracle/nrms_bert_oracle.py vs reference model/nrms.py ----
+from oracle import nrms_bert_oracle as OB  # noqa: E402
+from _golden import BertCase  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["bert_tiny", "bert_mind"])
+def test_bert_init_and_eval_forward(name):
+    c = BertCase(name)
+    check_summary(c, "sd0sum", OB.init_state_dict(c.cfg, c.table, seed=42), rtol=0.0, atol_frac=0.0, abs_floor=0.0)
+    sd = c.state_dict()
+    with torch.no_grad():
+        logits, parts = OB.model_forward(sd, c.batch, c.cfg, return_parts=True)
+    np.testing.assert_allclose(logits.numpy(), c.z["eval/logits"], rtol=2e-5, atol=1e-5)
+    np.testing.assert_allclose(parts["user_vec"].numpy(), c.z["eval/user_vec"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(parts["cand_vec"].numpy(), c.z["eval/cand_vec"], rtol=2e-5, atol=2e-6)
+    assert (logits.numpy()[c.batch["candidate_mask"].numpy() == 0] == -1e9).all()
+
+
+@pytest.mark.parametrize("name", ["bert_tiny", "bert_mind"])
+def test_bert_grads_eval_and_train_masks(name):
+    c = BertCase(name)
+    sd = c.state_dict()
+    loss, _, grads = OB.loss_and_grads(sd, c.batch, c.cfg)
+    assert abs(float(loss) - float(c.z["evalgrad/loss"])) < 1e-5
+    check_summary(c, "evalgrad", grads, rtol=2e-4)
+    # no padding_idx in this variant (nrms.py:222-224), but every use of the pad id is masked: padded
+    # history slots get probability exp(-1e9 - max) == 0.0f as keys and as pooled slots, padded candidates
+    # are overwritten by -1e9 — so row 0's gradient is exactly zero anyway
+    assert float(grads[OB.TABLE_KEY][0].abs().max()) == 0.0
+    loss, logits, grads = OB.loss_and_grads(sd, c.batch, c.cfg, c.mults(0))
+    assert abs(float(loss) - float(c.z["train/step0/loss"])) < 2e-5
+    np.testing.assert_allclose(logits.numpy(), c.z["train/step0/logits"], rtol=1e-4, atol=2e-5)
+    check_summary(c, "train/step0/grad", grads, rtol=5e-4)
