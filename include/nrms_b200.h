@@ -258,6 +258,51 @@ int nrms_gemm_selftest(int32_t variant, const float* A, const float* B, float* C
 int nrms_validate_ids(const int64_t* ids, int64_t n, int64_t vocab, int32_t* d_flag,
                       nrms_stream_t stream);
 
+/* ---- the `nrms` sibling variant (reference model/nrms.py) ---------------------
+ * Its sub-modules as separate entry points (the host side composes them: pytorch_news_recommender_b200/
+ * model/nrms.py), all fp32 in / fp32 out, row-major, caller-owned work blobs.
+ *
+ * nn.Linear (nrms.py:65-66 the Q/K/V and output projections, :91 the additive projection, :226-230
+ * news_dense): y[M,N] = x[M,K] W[N,K]^T + bias[N] on the tcgen05 image GEMMs (fp32-grade bf16x3);
+ * backward: dx[M,K] = dy W (dx may be NULL), dW[N,K] = dy^T x, dbias[N] = column sums of dy (may be NULL).
+ * N % 4 == 0, K % 4 == 0; work >= nrms_linear_work_bytes(M, N, K) serves both directions. */
+int64_t nrms_linear_work_bytes(int32_t M, int32_t N, int32_t K);
+int nrms_linear_fwd(const float* x, const float* W, const float* bias, float* y, int32_t M, int32_t N,
+                    int32_t K, void* work, int64_t work_bytes, nrms_stream_t stream);
+int nrms_linear_bwd(const float* x, const float* W, const float* dy, float* dx, float* dW, float* dbias,
+                    int32_t M, int32_t N, int32_t K, void* work, int64_t work_bytes, nrms_stream_t stream);
+
+/* nn.Dropout on a [n_rows, n_cols] activation (nrms.py:254): y = x * m with m the multiplier
+ * nrms_dropout_mask() reports for (seed, stream_id, p); the backward is the same call on dy.
+ * stream_id 3 = candidate vectors, 4 = history vectors (5 = attention probabilities, applied inside
+ * nrms_masked_attention_*). */
+int nrms_dropout_apply(uint64_t seed, uint32_t stream_id, float p, int64_t n_rows, int32_t n_cols,
+                       const float* x, float* y, nrms_stream_t stream);
+
+/* Attention.forward (nrms.py:26-49) for all heads: qkv [B, L, 3*heads*dk] (Q | K | V side by side),
+ * mask [B, L] uint8 (1 = real slot; NULL = no mask): score(i, j) = -1e9 unless slots i AND j are real
+ * (:38-41); probs [B, heads, L, L] = softmax BEFORE dropout (saved for the backward); dropout of rate
+ * p_drop on the probabilities (:45-47; multiplier of element (b, h, i, j) = nrms_dropout_mask(seed, 5, p)
+ * at row (b*heads + h)*L + i, column j); ctx [B, L, heads*dk].  L <= 128.
+ * Backward: d_qkv [B, L, 3*heads*dk] from d_ctx; masked scores pass no gradient. */
+int nrms_masked_attention_fwd(const float* qkv, const uint8_t* mask, int32_t B, int32_t L, int32_t heads,
+                              int32_t dk, float p_drop, uint64_t seed, float* probs, float* ctx,
+                              nrms_stream_t stream);
+int nrms_masked_attention_bwd(const float* qkv, const uint8_t* mask, const float* probs, const float* d_ctx,
+                              int32_t B, int32_t L, int32_t heads, int32_t dk, float p_drop, uint64_t seed,
+                              float* d_qkv, nrms_stream_t stream);
+
+/* AdditiveAttention.forward (nrms.py:98-117) after its Linear: t [B, L, Q] = x W^T + b (pre-tanh),
+ * qv [Q], x [B, L, E], mask [B, L] or NULL (padded slots scored -1e9, :112-113) ->
+ * alpha [B, L] softmax weights, out [B, E] = sum_i alpha_i x_i.
+ * Backward: d_t [B, L, Q], d_x [B, L, E] (the pooling's own share alpha_i * d_out; the Linear's share
+ * comes from nrms_linear_bwd), d_qv [Q]; work: B*Q floats. */
+int nrms_masked_pool_fwd(const float* t, const float* qv, const float* x, const uint8_t* mask, int32_t B,
+                         int32_t L, int32_t Q, int32_t E, float* alpha, float* out, nrms_stream_t stream);
+int nrms_masked_pool_bwd(const float* t, const float* qv, const float* x, const uint8_t* mask,
+                         const float* alpha, const float* d_out, int32_t B, int32_t L, int32_t Q, int32_t E,
+                         float* d_t, float* d_x, float* d_qv, float* work, nrms_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

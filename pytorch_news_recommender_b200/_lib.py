@@ -77,6 +77,15 @@ SIGNATURES = {
     "nrms_gemm_selftest_bytes": (_I64, [_I32, _I32, _I32, _I32]),
     "nrms_gemm_selftest": (C.c_int, [_I32, _P, _P, _P, _I32, _I32, _I32, _P, _I64, _P]),
     "nrms_validate_ids": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    # the `nrms` sibling variant (model/nrms.py)
+    "nrms_linear_work_bytes": (_I64, [_I32, _I32, _I32]),
+    "nrms_linear_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _I64, _P]),
+    "nrms_linear_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _I64, _P]),
+    "nrms_dropout_apply": (C.c_int, [C.c_uint64, C.c_uint32, _F, _I64, _I32, _P, _P, _P]),
+    "nrms_masked_attention_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _F, C.c_uint64, _P, _P, _P]),
+    "nrms_masked_attention_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, C.c_uint64, _P, _P]),
+    "nrms_masked_pool_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "nrms_masked_pool_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -29,7 +29,9 @@ _PATH_KNOBS = dict(
     word_embedding_pretrained='all_word_embedding_v3.npz',
 )
 
-# knobs of the surrounding scripts / other model variants (inert for this path) ---------------
+# knobs of the surrounding scripts / other model variants (inert for the nrms_v0 path; the `nrms` sibling
+# plugin reads bert_embedding_pretrained here and bert_embed_size, news_feature_size, user_heads_num,
+# query_vector_dim_large from __nrms__) --------------------------------------------------------
 _INERT_KNOBS = dict(
     bert_embedding_pretrained='news_embeds_512.npz',
     entity_embedding_pretrained='entitiy_embeds.npz',

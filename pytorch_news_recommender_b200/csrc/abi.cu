@@ -18,6 +18,7 @@
 #include "gemm_simt.cuh"
 #include "gather.cuh"
 #include "gemm_img.cuh"
+#include "masked_user.cuh"
 #include "metrics.cuh"
 #include "pooling.cuh"
 #include "profiler.cuh"
@@ -1272,5 +1273,7 @@ int nrms_validate_ids(const int64_t* ids, int64_t n, int64_t vocab, int32_t* d_f
     NRMS_CHECK_CUDA(cudaGetLastError());
     return NRMS_OK;
 }
+
+#include "abi_masked.inc"
 
 }  // extern "C"

@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from .nrms_v0 import Model as NRMS_V0  # noqa: F401
+from .nrms import Model as NRMS  # noqa: F401  (the BERT-vector sibling: reference model/__init__.py:1)
 
 
 class Model(nn.Module):

@@ -357,3 +357,114 @@ def validate_ids(ids, vocab: int) -> bool:
     check(_lib.load().nrms_validate_ids(ptr(ids), ids.numel(), vocab, ptr(flag), _stream()),
           "nrms_validate_ids")
     return int(flag.item()) == 0
+
+
+# ---- the `nrms` sibling variant (model/nrms.py; include/nrms_b200.h, last section) ------------------------
+DROP_CAND_VEC = 3
+DROP_HIST_VEC = 4
+DROP_ATTN_PROB = 5
+
+_linear_work: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
+
+
+def _linear_blob(M: int, N: int, K: int, device) -> torch.Tensor:
+    """Work blob of a Linear shape, kept per device: forward and backward of a layer run on one stream, one
+    after the other, and every call re-packs what it reads."""
+    key = (M, N, K, device.index if device.index is not None else torch.cuda.current_device())
+    blob = _linear_work.get(key)
+    if blob is None:
+        n = int(_lib.load().nrms_linear_work_bytes(M, N, K))
+        if n < 0:
+            raise NrmsError(f"nrms_linear_work_bytes: bad shape M={M} N={N} K={K} (N, K multiples of 4)")
+        blob = torch.empty(n, dtype=torch.uint8, device=device)
+        _linear_work[key] = blob
+    return blob
+
+
+def linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """y[M, N] = x[M, K] W[N, K]^T + bias on the tcgen05 image GEMMs (fp32-grade)."""
+    _require_cuda(x, W, bias)
+    x, W = _cf32(x), _cf32(W)
+    (M, K), N = x.shape, W.shape[0]
+    work = _linear_blob(M, N, K, x.device)
+    y = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(_lib.load().nrms_linear_fwd(ptr(x), ptr(W), ptr(bias), ptr(y), M, N, K, ptr(work), work.numel(),
+                                      _stream()), "nrms_linear_fwd")
+    return y
+
+
+def linear_bwd(x, W, dy, need_dx: bool = True, need_dbias: bool = True):
+    _require_cuda(x, W, dy)
+    x, W, dy = _cf32(x), _cf32(W), _cf32(dy)
+    (M, K), N = x.shape, W.shape[0]
+    work = _linear_blob(M, N, K, x.device)
+    dx = torch.empty_like(x) if need_dx else None
+    dW = torch.empty_like(W)
+    db = torch.empty(N, dtype=torch.float32, device=x.device) if need_dbias else None
+    check(_lib.load().nrms_linear_bwd(ptr(x), ptr(W), ptr(dy), ptr(dx), ptr(dW), ptr(db), M, N, K, ptr(work),
+                                      work.numel(), _stream()), "nrms_linear_bwd")
+    return dx, dW, db
+
+
+def dropout_apply(x: torch.Tensor, seed: int, stream_id: int, p: float) -> torch.Tensor:
+    """x * multiplier of (seed, stream_id, p) over x viewed as [rows, last dim]; also its own backward."""
+    _require_cuda(x)
+    x = _cf32(x)
+    y = torch.empty_like(x)
+    n_cols = x.shape[-1]
+    check(_lib.load().nrms_dropout_apply(int(seed) & (2**64 - 1), stream_id, float(p), x.numel() // n_cols,
+                                         n_cols, ptr(x), ptr(y), _stream()), "nrms_dropout_apply")
+    return y
+
+
+def masked_attention_fwd(qkv, mask, heads: int, p_drop: float, seed: int):
+    """qkv [B, L, 3E], mask [B, L] uint8 or None -> (ctx [B, L, E], probs [B, heads, L, L])."""
+    _require_cuda(qkv, mask)
+    qkv = _cf32(qkv)
+    B, L, E3 = qkv.shape
+    E = E3 // 3
+    probs = torch.empty((B, heads, L, L), dtype=torch.float32, device=qkv.device)
+    ctx = torch.empty((B, L, E), dtype=torch.float32, device=qkv.device)
+    check(_lib.load().nrms_masked_attention_fwd(ptr(qkv), ptr(mask), B, L, heads, E // heads, float(p_drop),
+                                                int(seed) & (2**64 - 1), ptr(probs), ptr(ctx), _stream()),
+          "nrms_masked_attention_fwd")
+    return ctx, probs
+
+
+def masked_attention_bwd(qkv, mask, probs, d_ctx, heads: int, p_drop: float, seed: int):
+    _require_cuda(qkv, mask, probs, d_ctx)
+    d_ctx = _cf32(d_ctx)
+    B, L, E3 = qkv.shape
+    d_qkv = torch.empty_like(qkv)
+    check(_lib.load().nrms_masked_attention_bwd(ptr(qkv), ptr(mask), ptr(probs), ptr(d_ctx), B, L, heads,
+                                                E3 // 3 // heads, float(p_drop), int(seed) & (2**64 - 1),
+                                                ptr(d_qkv), _stream()), "nrms_masked_attention_bwd")
+    return d_qkv
+
+
+def masked_pool_fwd(t, qv, x, mask):
+    """t [B, L, Q] pre-tanh, qv [Q], x [B, L, E], mask [B, L] uint8 or None -> (out [B, E], alpha [B, L])."""
+    _require_cuda(t, qv, x, mask)
+    t, qv, x = _cf32(t), _cf32(qv), _cf32(x)
+    B, L, Q = t.shape
+    E = x.shape[-1]
+    alpha = torch.empty((B, L), dtype=torch.float32, device=x.device)
+    out = torch.empty((B, E), dtype=torch.float32, device=x.device)
+    check(_lib.load().nrms_masked_pool_fwd(ptr(t), ptr(qv), ptr(x), ptr(mask), B, L, Q, E, ptr(alpha), ptr(out),
+                                           _stream()), "nrms_masked_pool_fwd")
+    return out, alpha
+
+
+def masked_pool_bwd(t, qv, x, mask, alpha, d_out):
+    _require_cuda(t, qv, x, mask, alpha, d_out)
+    d_out = _cf32(d_out)
+    B, L, Q = t.shape
+    E = x.shape[-1]
+    d_t = torch.empty_like(t)
+    d_x = torch.empty_like(x)
+    d_qv = torch.empty_like(qv)
+    work = torch.empty((B, Q), dtype=torch.float32, device=x.device)
+    check(_lib.load().nrms_masked_pool_bwd(ptr(t), ptr(qv), ptr(x), ptr(mask), ptr(alpha), ptr(d_out), B, L, Q,
+                                           E, ptr(d_t), ptr(d_x), ptr(d_qv), ptr(work), _stream()),
+          "nrms_masked_pool_bwd")
+    return d_t, d_x, d_qv
