@@ -58,6 +58,35 @@ def load(cpu_proxy: bool):
     return ref
 
 
+def load_variant():
+    """The staged, unmodified `model/nrms.py` (the BERT-vector sibling).  It imports `torchsnooper` (absent
+    here; every `@snoop()` in the file is commented out) and `tools.log_exec_time` (tools.py pulls in
+    matplotlib): both are answered with empty stand-ins for the duration of the import."""
+    import sys
+    manifest = json.load(open(os.path.join(REF_DIR, "MANIFEST.json")))
+    path = os.path.join(REF_DIR, "nrms.py")
+    if "nrms.py" not in manifest or not os.path.exists(path):
+        raise FileNotFoundError("oracle/_ref/nrms.py is not staged (python oracle/stage_ref.py in the build container)")
+    if hashlib.sha256(open(path, "rb").read()).hexdigest() != manifest["nrms.py"]["sha256"]:
+        raise RuntimeError("oracle/_ref/nrms.py does not match its manifest: not the unmodified reference file")
+    snoop, tools = types.ModuleType("torchsnooper"), types.ModuleType("tools")
+    snoop.snoop = lambda *a, **k: (lambda f: f)
+    tools.log_exec_time = lambda f: f
+    saved = {k: sys.modules.get(k) for k in ("torchsnooper", "tools")}
+    sys.modules["torchsnooper"], sys.modules["tools"] = snoop, tools
+    try:
+        spec = importlib.util.spec_from_file_location("ref_nrms_variant_staged", path)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return ref
+
+
 class RefConfig:
     """The attributes nrms_v0.Model reads (config.py:30-57 + __nrms__ :65-88)."""
 

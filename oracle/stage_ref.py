@@ -22,7 +22,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = "/root/reference/MIND_2020"
 DST = os.path.join(HERE, "_ref")
-FILES = {"nrms_v0.py": "model/nrms_v0.py", "evaluation.py": "evaluation.py"}
+FILES = {"nrms_v0.py": "model/nrms_v0.py", "evaluation.py": "evaluation.py",
+         "nrms.py": "model/nrms.py"}          # the sibling variant's module (scripts/variant_bench.py)
 
 
 def sha256(path: str) -> str:

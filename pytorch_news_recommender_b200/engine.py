@@ -202,6 +202,40 @@ class ScoreFn(torch.autograd.Function):
         return d_cand, d_user, None
 
 
+class DeviceAdam:
+    """torch.optim.Adam with its defaults (train_eval.py:167) as ONE `nrms_adam_step` launch per parameter
+    tensor — the optimizer of the autograd-driven plugins (the `nrms` sibling), whose step is not fused into a
+    `FusedTrainer`.  Same surface as far as the reference's loop uses it: `param_groups[i]['lr']`,
+    `zero_grad()`, `step()`."""
+
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.params = [p for p in params if p.requires_grad]
+        self.param_groups = [{"params": self.params, "lr": float(lr)}]
+        self.betas, self.eps = betas, eps
+        self.state: Dict[torch.nn.Parameter, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self.step_count = 0
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        self.step_count += 1
+        lr = float(self.param_groups[0]["lr"])
+        for p in self.params:
+            if p.grad is None:
+                continue
+            if not p.is_cuda:
+                raise NrmsError("DeviceAdam runs on CUDA parameters only (no CPU fallback)")
+            st = self.state.get(p)
+            if st is None:
+                st = self.state[p] = (torch.zeros_like(p), torch.zeros_like(p))
+            ops.adam_step(p.data, p.grad.contiguous(), st[0], st[1], self.step_count, lr, self.betas[0],
+                          self.betas[1], self.eps)
+            torch.autograd.graph.increment_version(p)     # the kernel wrote through a raw pointer
+
+
 # ------------------------------------------------------------------------------------------
 # fused training step
 # ------------------------------------------------------------------------------------------

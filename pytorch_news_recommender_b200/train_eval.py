@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 
 from . import evaluation
-from .engine import FusedTrainer
+from .engine import DeviceAdam, FusedTrainer
 
 _y_true: Optional[List[List[int]]] = None     # the reference keeps the dev labels in a module global
 last_metrics = {}                             # AUC / MRR / nDCG@5 / nDCG@10 of the last evaluate()
@@ -65,6 +65,20 @@ def warmup_lr(base_lr: float, i: int, warm_up_steps: int) -> float:
     return base_lr if e > warm_up_steps else base_lr * float(e) / warm_up_steps
 
 
+def _pick_step(config, model, fused: bool):
+    """fused=True asks for the device-side training step: `FusedTrainer` (forward + loss + backward + Adam
+    without an autograd tape) exists for the nrms_v0 plugin; every other plugin (the `nrms` sibling) runs the
+    reference's statements over its autograd nodes with `DeviceAdam`.  fused=False is the literal reference
+    loop with `torch.optim.Adam`.  Returns (use FusedTrainer, optimizer or None)."""
+    from .model import nrms_v0
+    inner = getattr(model, 'model', model)
+    if fused and isinstance(inner, nrms_v0.Model):
+        return True, None
+    if fused:
+        return False, DeviceAdam(model.parameters(), lr=config.learning_rate)
+    return False, torch.optim.Adam(model.parameters(), lr=config.learning_rate)
+
+
 def train(config, model, train_iter, dev_iter, y_true: Optional[Sequence[Sequence[int]]] = None,
           fused: bool = True, restore_train_mode: bool = False, log=print):
     """The reference's main loop (train_eval.py:34-153, entered from run_v0.py): optional warm-up
@@ -84,8 +98,8 @@ def train(config, model, train_iter, dev_iter, y_true: Optional[Sequence[Sequenc
         set_y_true(load_y_true(config.data_path + 'dev_behaviors.csv'))
     start_time = time.time()
     model.train()
+    fused, optimizer = _pick_step(config, model, fused)
     trainer = FusedTrainer(model, lr=config.learning_rate) if fused else None
-    optimizer = None if fused else torch.optim.Adam(model.parameters(), lr=config.learning_rate)
     criterion = nn.CrossEntropyLoss()
     total_batch, AUC_best, loss_list, STEP_SIZE, improve = 0, 0.56, [], 100, '*'
     loss_records: List[float] = []
@@ -159,8 +173,8 @@ def train_demo(config, model, train_iter, dev_iter, y_true: Optional[Sequence[Se
     log('result_length::::', len(_y_true))
     start_time = time.time()
     model.train()
+    fused, optimizer = _pick_step(config, model, fused)
     trainer = FusedTrainer(model, lr=config.learning_rate) if fused else None
-    optimizer = None if fused else torch.optim.Adam(model.parameters(), lr=config.learning_rate)
     criterion = nn.CrossEntropyLoss()
     total_batch, AUC_best, loss_list, STEP_SIZE, improve = 0, 0, [], 100, '*'
     auc = float('nan')
