@@ -264,7 +264,8 @@ int nrms_validate_ids(const int64_t* ids, int64_t n, int64_t vocab, int32_t* d_f
  *
  * nn.Linear (nrms.py:65-66 the Q/K/V and output projections, :91 the additive projection, :226-230
  * news_dense): y[M,N] = x[M,K] W[N,K]^T + bias[N] on the tcgen05 image GEMMs (fp32-grade bf16x3);
- * backward: dx[M,K] = dy W (dx may be NULL), dW[N,K] = dy^T x, dbias[N] = column sums of dy (may be NULL).
+ * backward: dx[M,K] = dy W (dx may be NULL), dW[N,K] = dy^T x, dbias[N] = column sums of dy (may be NULL;
+ * it comes out of the weight-gradient GEMM through a ones column appended to x).
  * N % 4 == 0, K % 4 == 0; work >= nrms_linear_work_bytes(M, N, K) serves both directions. */
 int64_t nrms_linear_work_bytes(int32_t M, int32_t N, int32_t K);
 int nrms_linear_fwd(const float* x, const float* W, const float* bias, float* y, int32_t M, int32_t N,

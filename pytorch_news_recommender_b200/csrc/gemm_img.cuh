@@ -134,8 +134,10 @@ __global__ void img_pack_kernel(const float* __restrict__ src, int R, int C, int
 }
 // two weight matrices of an encoder in ONE launch (the packs are launch-latency-sized kernels): the
 // second matrix's units follow the first's in the flattened index space
+// ones_col1 >= 0: column ones_col1 of the SECOND image is 1.0 in every real row (the weight-gradient GEMM then
+// yields the bias gradient in that output column: reduce_wgrad_kernel)
 __global__ void img_pack2_kernel(const float* __restrict__ src0, int R0, int C0, int ld0, Img im0, int hp_D, int hp_dk,
-                                 const float* __restrict__ src1, int R1, int C1, int ld1, Img im1) {
+                                 const float* __restrict__ src1, int R1, int C1, int ld1, Img im1, int ones_col1) {
     const long long t0 = (long long)im0.rows_pad * im0.chunks * 8, t1 = (long long)im1.rows_pad * im1.chunks * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t0 + t1;
          i += (long long)gridDim.x * blockDim.x) {
@@ -152,16 +154,17 @@ __global__ void img_pack2_kernel(const float* __restrict__ src0, int R0, int C0,
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = g * 8 + j;
-            x[j] = (sr >= 0 && c < C) ? __ldg(src + sr * ld + c) : 0.f;
+            x[j] = (sr >= 0 && c < C) ? __ldg(src + sr * ld + c) : ((!first && sr >= 0 && c == ones_col1) ? 1.f : 0.f);
         }
         img_store8(im, r, g, x);
     }
 }
 inline cudaError_t img_pack2(const float* src0, int R0, int C0, int ld0, const Img& im0, int hp_D, int hp_dk,
-                             const float* src1, int R1, int C1, int ld1, const Img& im1, cudaStream_t s) {
+                             const float* src1, int R1, int C1, int ld1, const Img& im1, cudaStream_t s,
+                             int ones_col1 = -1) {
     const long long total = (long long)im0.rows_pad * im0.chunks * 8 + (long long)im1.rows_pad * im1.chunks * 8;
     NRMS_LAUNCH("img_pack", s, img_pack2_kernel<<<(unsigned)ceil_div64(total, 256), 256, 0, s>>>(
-        src0, R0, C0, ld0, im0, hp_D, hp_dk, src1, R1, C1, ld1, im1));
+        src0, R0, C0, ld0, im0, hp_D, hp_dk, src1, R1, C1, ld1, im1, ones_col1));
     return cudaGetLastError();
 }
 inline cudaError_t img_pack(const float* src, int R, int C, int ld, const Img& im, cudaStream_t s, int hp_D = 0,

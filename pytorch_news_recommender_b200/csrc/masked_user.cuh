@@ -35,28 +35,6 @@ __global__ void dropout_apply_kernel(Dropout dr, uint32_t sid, long long n_rows,
     }
 }
 
-// ---- column sums (bias gradients): out[n] = sum_m x[m, n], rows added in ascending order per warp slice,
-// the 8 slices in slice order
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long M, int N, int ld,
-                                                    float* __restrict__ out) {
-    __shared__ float part[8][32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + lane;
-    const long long per = ceil_div64(M, 8);
-    const long long m0 = warp * per, m1 = m0 + per < M ? m0 + per : M;
-    float s = 0.f;
-    if (n < N)
-        for (long long m = m0; m < m1; ++m) s += x[m * ld + n];
-    part[warp][lane] = s;
-    __syncthreads();
-    if (warp == 0 && n < N) {
-        float t = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) t += part[w][lane];
-        out[n] = t;
-    }
-}
-
 // ---- masked multi-head attention (nrms.py:26-49) ---------------------------------------------------------
 // qkv [B, L, 3E] fp32 (Q | K | V of every head side by side, the fused projection's output), mask [B, L]
 // (1 = real slot) or NULL, probs [B, h, L, L] = softmax BEFORE dropout (saved for the backward),
