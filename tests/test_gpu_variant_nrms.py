@@ -214,7 +214,9 @@ def test_plugin_train_mode_matches_oracle_with_the_kernels_masks(name, built_lib
         for k, prm in model.named_parameters():
             w = want_grads[k].double()
             e = (prm.grad.double().cpu() - w).norm().item()
-            assert e <= 2e-3 * max(w.norm().item(), 1e-12) + 1e-9, (step, k, e, w.norm().item())
+            # the key projection's bias gradient is mathematically zero (softmax is invariant to a per-query
+            # constant): only rounding noise is left on either side, hence the absolute floor
+            assert e <= 2e-3 * w.norm().item() + 1e-7 * math.sqrt(w.numel()), (step, k, e, w.norm().item())
 
 
 def test_plugin_trains_with_the_reference_loop_and_reloads(built_lib):
