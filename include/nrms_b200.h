@@ -284,7 +284,9 @@ int nrms_dropout_apply(uint64_t seed, uint32_t stream_id, float p, int64_t n_row
  * mask [B, L] uint8 (1 = real slot; NULL = no mask): score(i, j) = -1e9 unless slots i AND j are real
  * (:38-41); probs [B, heads, L, L] = softmax BEFORE dropout (saved for the backward); dropout of rate
  * p_drop on the probabilities (:45-47; multiplier of element (b, h, i, j) = nrms_dropout_mask(seed, 5, p)
- * at row (b*heads + h)*L + i, column j); ctx [B, L, heads*dk].  L <= 128.
+ * at row (b*heads + h)*L + i, column j); ctx [B, L, heads*dk].  L <= 128, dk <= 128 and the item's
+ * tiles must fit shared memory (4 L ld + 2 L ceil8(L) + 64 L floats <= 227 KB, ld ~ dk + 4: the
+ * reference's 50-slot history with 64-wide heads takes 90 KB).
  * Backward: d_qkv [B, L, 3*heads*dk] from d_ctx; masked scores pass no gradient. */
 int nrms_masked_attention_fwd(const float* qkv, const uint8_t* mask, int32_t B, int32_t L, int32_t heads,
                               int32_t dk, float p_drop, uint64_t seed, float* probs, float* ctx,

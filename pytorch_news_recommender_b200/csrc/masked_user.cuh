@@ -38,9 +38,15 @@ __global__ void dropout_apply_kernel(Dropout dr, uint32_t sid, long long n_rows,
 // ---- masked multi-head attention (nrms.py:26-49) ---------------------------------------------------------
 // qkv [B, L, 3E] fp32 (Q | K | V of every head side by side, the fused projection's output), mask [B, L]
 // (1 = real slot) or NULL, probs [B, h, L, L] = softmax BEFORE dropout (saved for the backward),
-// ctx [B, L, E].  One CTA per (sequence, head); K, V and Q of the item in shared memory ([L][dk + 1] fp32),
-// a warp per query row: lane j owns keys j, j + 32, ...; the row's probabilities go through a per-warp
-// shared row for the P.V product (lane d owns columns d, d + 32, ...).
+// ctx [B, L, E].  One CTA per (sequence, head), 8 warps, every operand of the item in shared memory as a
+// row-major fp32 tile whose row length ld is a multiple of 4 with ld/4 odd (16-byte loads of 8 different
+// rows hit 8 different bank groups).  Register tiling: a warp owns EIGHT query rows at a time —
+//   rows x keys  (S = Q K^T, dPd = dO V^T): lane = key (j = lane + 32 t), k = head columns, 4 at a time:
+//                 8 broadcast 16-byte loads of the rows + T 16-byte loads of the lane's keys per 32 T FMAs;
+//   rows x cols  (O = P V, dQ = dS K, and with keys for rows dK = dS^T Q, dV = Pd^T dO): lane = head column,
+//                 k = keys; the 8 weights of a key are two broadcast 16-byte loads (the warp stages its P /
+//                 dS rows transposed, [key][8]; dK / dV read 8 adjacent columns of the row-major dS / Pd).
+// That is ~4 FMAs per shared-memory wavefront (the first version, one row per warp, had 0.5).
 struct MaskedAttnArgs {
     const float* qkv;
     const uint8_t* mask;
@@ -53,81 +59,187 @@ struct MaskedAttnArgs {
     Dropout drop;
 };
 constexpr int kMaWarps = 8;
+constexpr int kMaRows = 8;                // rows per warp step
 constexpr int kMaMaxKeysPerLane = 4;      // L <= 128
+constexpr int kMaMaxColsPerLane = 4;      // head dim <= 128
+
+__host__ __device__ inline int ma_ld(int dk) {
+    int ld = (dk + 3) / 4 * 4;
+    if (((ld / 4) & 1) == 0) ld += 4;
+    return ld;
+}
+__host__ __device__ inline int ma_lp(int L) { return (L + 7) / 8 * 8; }
 
 inline size_t masked_attn_fwd_smem(int L, int dk) {
-    return sizeof(float) * ((size_t)3 * L * (dk + 1) + (size_t)kMaWarps * L);
+    return sizeof(float) * ((size_t)3 * L * ma_ld(dk) + (size_t)kMaWarps * L * kMaRows);
 }
 inline size_t masked_attn_bwd_smem(int L, int dk) {
-    return sizeof(float) * ((size_t)4 * L * (dk + 1) + (size_t)2 * L * (L + 1));
+    return sizeof(float) * ((size_t)4 * L * ma_ld(dk) + (size_t)2 * L * ma_lp(L) + (size_t)kMaWarps * L * kMaRows);
 }
 
+// rows [.., L) x columns [0, dk) of a [.., stride] global matrix -> tile [L][ld], padding columns zero
+__device__ __forceinline__ void ma_load_tile(float* dst, const float* __restrict__ src, long long stride, int L, int dk, int ld) {
+    for (int i = threadIdx.x; i < L * ld; i += blockDim.x) {
+        const int r = i / ld, d = i - r * ld;
+        dst[i] = d < dk ? src[(long long)r * stride + d] : 0.f;
+    }
+}
+// acc[r][t] = sum_d A[i0 + r][d] * Bm[lane + 32 t][d]   (rows / keys beyond L read row L - 1: discarded by the caller)
+__device__ __forceinline__ void ma_rows_dot(float (&acc)[kMaRows][kMaMaxKeysPerLane], const float* A, const float* Bm, int i0, int L,
+                                            int ld, int T, int lane) {
+    const float* brow[kMaMaxKeysPerLane];
+#pragma unroll
+    for (int t = 0; t < kMaMaxKeysPerLane; ++t) brow[t] = Bm + min(lane + 32 * t, L - 1) * ld;
+#pragma unroll
+    for (int r = 0; r < kMaRows; ++r)
+#pragma unroll
+        for (int t = 0; t < kMaMaxKeysPerLane; ++t) acc[r][t] = 0.f;
+    for (int d = 0; d < ld; d += 4) {
+        float4 bv[kMaMaxKeysPerLane];
+#pragma unroll
+        for (int t = 0; t < kMaMaxKeysPerLane; ++t)
+            if (t < T) bv[t] = *reinterpret_cast<const float4*>(brow[t] + d);
+#pragma unroll
+        for (int r = 0; r < kMaRows; ++r) {
+            const float4 av = *reinterpret_cast<const float4*>(A + min(i0 + r, L - 1) * ld + d);
+#pragma unroll
+            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
+                if (t < T) {
+                    acc[r][t] = fmaf(av.x, bv[t].x, acc[r][t]);
+                    acc[r][t] = fmaf(av.y, bv[t].y, acc[r][t]);
+                    acc[r][t] = fmaf(av.z, bv[t].z, acc[r][t]);
+                    acc[r][t] = fmaf(av.w, bv[t].w, acc[r][t]);
+                }
+        }
+    }
+}
+// acc[r][u] = sum_{k < n} W[k * wstride + r] * Bm[k][lane + 32 u]   (W + k * wstride 32-byte aligned)
+__device__ __forceinline__ void ma_cols_acc(float (&acc)[kMaRows][kMaMaxColsPerLane], const float* W, int wstride, const float* Bm,
+                                            int n, int ld, int U, int lane) {
+#pragma unroll
+    for (int r = 0; r < kMaRows; ++r)
+#pragma unroll
+        for (int u = 0; u < kMaMaxColsPerLane; ++u) acc[r][u] = 0.f;
+    for (int k = 0; k < n; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(W + k * wstride);
+        const float4 w1 = *reinterpret_cast<const float4*>(W + k * wstride + 4);
+        const float w[kMaRows] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int u = 0; u < kMaMaxColsPerLane; ++u)
+            if (u < U) {
+                const int d = lane + 32 * u;
+                const float bv = d < ld ? Bm[k * ld + d] : 0.f;
+#pragma unroll
+                for (int r = 0; r < kMaRows; ++r) acc[r][u] = fmaf(w[r], bv, acc[r][u]);
+            }
+    }
+}
+// Dropout keep bits of 8 rows x ceil(L/8) groups: one Philox call per (row, group) spread over the lanes
+// (round k, lane l holds pair 32 k + l = row * G + group) instead of one call per element.
+struct MaKeep {
+    uint32_t kp[4];
+    int G;
+    __device__ __forceinline__ void fill(const Dropout& dr, uint64_t row0, int L, int lane) {
+        G = (L + 7) >> 3;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int pair = 32 * k + lane;
+            kp[k] = 0xffu;
+            if (dr.enabled() && 32 * k < kMaRows * G && pair < kMaRows * G)
+                kp[k] = dr.keep8(kDropAttnProb, row0 + (uint64_t)(pair / G), (uint32_t)(pair % G));
+        }
+    }
+    // keep bit of (row r of the step, key j); every lane of the warp must call it
+    __device__ __forceinline__ bool keep(int r, int j) const {
+        const int pair = r * G + (j >> 3);
+        uint32_t v = 0xffu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t x = __shfl_sync(0xffffffffu, kp[k], pair & 31);
+            if ((pair >> 5) == k) v = x;
+        }
+        return (v >> (j & 7)) & 1u;
+    }
+};
+
 __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAttnArgs a) {
-    extern __shared__ float sm[];
-    const int L = a.L, dk = a.dk, ld = dk + 1, E = a.heads * dk;
+    extern __shared__ __align__(16) float sm[];
+    const int L = a.L, dk = a.dk, ld = ma_ld(dk), E = a.heads * dk;
     float* Qs = sm;
     float* Ks = Qs + L * ld;
     float* Vs = Ks + L * ld;
-    float* Ps = Vs + L * ld;                     // [warps][L]
+    float* Pt = Vs + L * ld;                     // [warps][L][8]
     const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* src = a.qkv + (long long)b * L * 3 * E + h * dk;
-    for (int i = threadIdx.x; i < L * dk; i += blockDim.x) {
-        const int r = i / dk, d = i - r * dk;
-        const float* p = src + (long long)r * 3 * E + d;
-        Qs[r * ld + d] = p[0];
-        Ks[r * ld + d] = p[E];
-        Vs[r * ld + d] = p[2 * E];
-    }
+    ma_load_tile(Qs, src, 3 * E, L, dk, ld);
+    ma_load_tile(Ks, src + E, 3 * E, L, dk, ld);
+    ma_load_tile(Vs, src + 2 * E, 3 * E, L, dk, ld);
     __syncthreads();
     const uint8_t* mrow = a.mask ? a.mask + (long long)b * L : nullptr;
-    float* prow = Ps + warp * L;
-    for (int i = warp; i < L; i += kMaWarps) {
-        const bool qi_real = !mrow || mrow[i] != 0;
-        float s[kMaMaxKeysPerLane];
-        float mx = -INFINITY;
+    const int T = (L + 31) >> 5, U = (dk + 31) >> 5;
+    float* pt = Pt + warp * L * kMaRows;
+    bool key_real[kMaMaxKeysPerLane];
 #pragma unroll
-        for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
-            const int j = lane + 32 * t;
-            float acc = 0.f;
-            if (j < L) {
-                for (int d = 0; d < dk; ++d) acc = fmaf(Qs[i * ld + d], Ks[j * ld + d], acc);
-                acc *= a.scale;
-                if (!(qi_real && (!mrow || mrow[j] != 0))) acc = -1e9f;      // masked_fill (nrms.py:38-41)
-                mx = fmaxf(mx, acc);
-            }
-            s[t] = acc;
-        }
-        mx = warp_max(mx);
-        float sum = 0.f;
+    for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
+        const int j = lane + 32 * t;
+        key_real[t] = j < L && (!mrow || mrow[j] != 0);
+    }
+    for (int i0 = warp * kMaRows; i0 < L; i0 += kMaWarps * kMaRows) {
+        float acc[kMaRows][kMaMaxKeysPerLane];
+        ma_rows_dot(acc, Qs, Ks, i0, L, ld, T, lane);
+        const long long prow0 = ((long long)b * a.heads + h) * L + i0;
+        MaKeep mk;
+        mk.fill(a.drop, (uint64_t)prow0, L, lane);
 #pragma unroll
-        for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
-            const int j = lane + 32 * t;
-            s[t] = j < L ? expf(s[t] - mx) : 0.f;
-            sum += s[t];
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.f / sum;
-        const long long prow_g = (((long long)b * a.heads + h) * L + i);
+        for (int r = 0; r < kMaRows; ++r) {
+            const int i = i0 + r;
+            const bool row_ok = i < L;
+            const bool qi_real = !mrow || mrow[min(i, L - 1)] != 0;
+            float mx = -INFINITY;
 #pragma unroll
-        for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
-            const int j = lane + 32 * t;
-            if (j < L) {
-                float p = s[t] * inv;
-                a.probs[prow_g * L + j] = p;
-                if (a.drop.enabled()) {
-                    const uint32_t keep = a.drop.keep8(kDropAttnProb, (uint64_t)prow_g, (uint32_t)(j >> 3));
-                    p = ((keep >> (j & 7)) & 1u) ? p * a.drop.scale : 0.f;
+            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
+                if (t < T) {
+                    float v = acc[r][t] * a.scale;
+                    if (!(qi_real && key_real[t])) v = -1e9f;      // masked_fill (nrms.py:38-41)
+                    acc[r][t] = v;
+                    if (lane + 32 * t < L) mx = fmaxf(mx, v);
                 }
-                prow[j] = p;
-            }
+            mx = warp_max(mx);
+            float sum = 0.f;
+#pragma unroll
+            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
+                if (t < T) {
+                    acc[r][t] = lane + 32 * t < L ? expf(acc[r][t] - mx) : 0.f;
+                    sum += acc[r][t];
+                }
+            sum = warp_sum(sum);
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
+                if (t < T) {
+                    const int j = lane + 32 * t;
+                    float p = acc[r][t] * inv;
+                    const bool kept = mk.keep(r, min(j, L - 1));
+                    if (j < L) {
+                        if (row_ok) a.probs[(prow0 + r) * L + j] = p;
+                        if (a.drop.enabled()) p = kept ? p * a.drop.scale : 0.f;
+                        pt[j * kMaRows + r] = p;
+                    }
+                }
         }
         __syncwarp();
-        for (int d = lane; d < dk; d += 32) {
-            float acc = 0.f;
-            for (int j = 0; j < L; ++j) acc = fmaf(prow[j], Vs[j * ld + d], acc);
-            a.ctx[((long long)b * L + i) * E + h * dk + d] = acc;
-        }
+        float o[kMaRows][kMaMaxColsPerLane];
+        ma_cols_acc(o, pt, kMaRows, Vs, L, ld, U, lane);
+#pragma unroll
+        for (int r = 0; r < kMaRows; ++r)
+            if (i0 + r < L) {
+#pragma unroll
+                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                    const int d = lane + 32 * u;
+                    if (u < U && d < dk) a.ctx[((long long)b * L + i0 + r) * E + h * dk + d] = o[r][u];
+                }
+            }
         __syncwarp();
     }
 }
@@ -135,77 +247,116 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAt
 // backward of the above: dV = Pd^T dO, dPd = dO V^T, dP = dPd * keep/(1-p), dS = P (dP - rowsum(P dP)) / sqrt(dk)
 // with dS = 0 wherever the score was overwritten by the mask (masked_fill passes no gradient), dQ = dS K, dK = dS^T Q.
 __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_bwd_kernel(MaskedAttnArgs a) {
-    extern __shared__ float sm[];
-    const int L = a.L, dk = a.dk, ld = dk + 1, E = a.heads * dk, lp = L + 1;
+    extern __shared__ __align__(16) float sm[];
+    const int L = a.L, dk = a.dk, ld = ma_ld(dk), E = a.heads * dk, lp = ma_lp(L);
     float* Qs = sm;
     float* Ks = Qs + L * ld;
     float* Vs = Ks + L * ld;
     float* Os = Vs + L * ld;                     // dO
-    float* dS = Os + L * ld;                     // [L][L + 1]
-    float* Pd = dS + L * lp;                     // [L][L + 1] dropped probabilities
+    float* dS = Os + L * ld;                     // [L][lp]
+    float* Pd = dS + L * lp;                     // [L][lp] dropped probabilities
+    float* St = Pd + L * lp;                     // [warps][L][8]: a warp's dS rows, transposed
     const int b = blockIdx.x / a.heads, h = blockIdx.x % a.heads;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* src = a.qkv + (long long)b * L * 3 * E + h * dk;
-    const float* dsrc = a.d_ctx + (long long)b * L * E + h * dk;
-    for (int i = threadIdx.x; i < L * dk; i += blockDim.x) {
-        const int r = i / dk, d = i - r * dk;
-        const float* p = src + (long long)r * 3 * E + d;
-        Qs[r * ld + d] = p[0];
-        Ks[r * ld + d] = p[E];
-        Vs[r * ld + d] = p[2 * E];
-        Os[r * ld + d] = dsrc[(long long)r * E + d];
+    ma_load_tile(Qs, src, 3 * E, L, dk, ld);
+    ma_load_tile(Ks, src + E, 3 * E, L, dk, ld);
+    ma_load_tile(Vs, src + 2 * E, 3 * E, L, dk, ld);
+    ma_load_tile(Os, a.d_ctx + (long long)b * L * E + h * dk, E, L, dk, ld);
+    for (int i = threadIdx.x; i < L * (lp - L); i += blockDim.x) {      // padding columns: read (and discarded) by dK / dV
+        const int r = i / (lp - L), c = L + i % (lp - L);
+        dS[r * lp + c] = 0.f;
+        Pd[r * lp + c] = 0.f;
     }
     __syncthreads();
     const uint8_t* mrow = a.mask ? a.mask + (long long)b * L : nullptr;
-    for (int i = warp; i < L; i += kMaWarps) {
-        const bool qi_real = !mrow || mrow[i] != 0;
-        const long long prow_g = (((long long)b * a.heads + h) * L + i);
-        float p[kMaMaxKeysPerLane], dp[kMaMaxKeysPerLane];
-        float delta = 0.f;
+    const int T = (L + 31) >> 5, U = (dk + 31) >> 5;
+    float* st = St + warp * L * kMaRows;
+    float* dst = a.d_qkv + (long long)b * L * 3 * E + h * dk;
+    bool key_real[kMaMaxKeysPerLane];
 #pragma unroll
-        for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
-            const int j = lane + 32 * t;
-            p[t] = 0.f;
-            dp[t] = 0.f;
-            if (j < L) {
-                float acc = 0.f;
-                for (int d = 0; d < dk; ++d) acc = fmaf(Os[i * ld + d], Vs[j * ld + d], acc);
-                p[t] = a.probs[prow_g * L + j];
-                float mult = 1.f;
-                if (a.drop.enabled()) {
-                    const uint32_t keep = a.drop.keep8(kDropAttnProb, (uint64_t)prow_g, (uint32_t)(j >> 3));
-                    mult = ((keep >> (j & 7)) & 1u) ? a.drop.scale : 0.f;
+    for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
+        const int j = lane + 32 * t;
+        key_real[t] = j < L && (!mrow || mrow[j] != 0);
+    }
+    for (int i0 = warp * kMaRows; i0 < L; i0 += kMaWarps * kMaRows) {
+        float acc[kMaRows][kMaMaxKeysPerLane];
+        ma_rows_dot(acc, Os, Vs, i0, L, ld, T, lane);                   // dPd
+        const long long prow0 = ((long long)b * a.heads + h) * L + i0;
+        MaKeep mk;
+        mk.fill(a.drop, (uint64_t)prow0, L, lane);
+#pragma unroll
+        for (int r = 0; r < kMaRows; ++r) {
+            const int i = min(i0 + r, L - 1);
+            const bool row_ok = i0 + r < L;
+            const bool qi_real = !mrow || mrow[i] != 0;
+            float p[kMaMaxKeysPerLane];
+            float delta = 0.f;
+#pragma unroll
+            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
+                if (t < T) {
+                    const int j = lane + 32 * t;
+                    const bool kept = mk.keep(r, min(j, L - 1));
+                    p[t] = 0.f;
+                    float dp = 0.f;
+                    if (j < L) {
+                        p[t] = a.probs[(prow0 - i0 + i) * L + j];
+                        const float mult = a.drop.enabled() ? (kept ? a.drop.scale : 0.f) : 1.f;
+                        if (row_ok) Pd[i * lp + j] = p[t] * mult;
+                        dp = acc[r][t] * mult;
+                    }
+                    acc[r][t] = dp;
+                    delta = fmaf(p[t], dp, delta);
                 }
-                Pd[i * lp + j] = p[t] * mult;
-                dp[t] = acc * mult;
-                delta = fmaf(p[t], dp[t], delta);
-            }
-        }
-        delta = warp_sum(delta);
+            delta = warp_sum(delta);
 #pragma unroll
-        for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
-            const int j = lane + 32 * t;
-            if (j < L) {
-                const bool live = qi_real && (!mrow || mrow[j] != 0);
-                dS[i * lp + j] = live ? p[t] * (dp[t] - delta) * a.scale : 0.f;
-            }
+            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
+                if (t < T) {
+                    const int j = lane + 32 * t;
+                    if (j < L) {
+                        const float v = (qi_real && key_real[t]) ? p[t] * (acc[r][t] - delta) * a.scale : 0.f;
+                        if (row_ok) dS[i * lp + j] = v;
+                        st[j * kMaRows + r] = v;
+                    }
+                }
         }
+        __syncwarp();
+        float o[kMaRows][kMaMaxColsPerLane];
+        ma_cols_acc(o, st, kMaRows, Ks, L, ld, U, lane);                // dQ rows [i0, i0 + 8)
+#pragma unroll
+        for (int r = 0; r < kMaRows; ++r)
+            if (i0 + r < L) {
+#pragma unroll
+                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                    const int d = lane + 32 * u;
+                    if (u < U && d < dk) dst[(long long)(i0 + r) * 3 * E + d] = o[r][u];
+                }
+            }
+        __syncwarp();
     }
     __syncthreads();
-    float* dst = a.d_qkv + (long long)b * L * 3 * E + h * dk;
-    for (int r = warp; r < L; r += kMaWarps) {
-        for (int d = lane; d < dk; d += 32) {
-            float dq = 0.f, dkk = 0.f, dv = 0.f;
-            for (int j = 0; j < L; ++j) {
-                dq = fmaf(dS[r * lp + j], Ks[j * ld + d], dq);          // row r as a query
-                dkk = fmaf(dS[j * lp + r], Qs[j * ld + d], dkk);        // row r as a key
-                dv = fmaf(Pd[j * lp + r], Os[j * ld + d], dv);
+    for (int j0 = warp * kMaRows; j0 < L; j0 += kMaWarps * kMaRows) {
+        float o[kMaRows][kMaMaxColsPerLane];
+        ma_cols_acc(o, dS + j0, lp, Qs, L, ld, U, lane);                // dK rows [j0, j0 + 8): sum over query rows
+#pragma unroll
+        for (int r = 0; r < kMaRows; ++r)
+            if (j0 + r < L) {
+#pragma unroll
+                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                    const int d = lane + 32 * u;
+                    if (u < U && d < dk) dst[(long long)(j0 + r) * 3 * E + E + d] = o[r][u];
+                }
             }
-            float* o = dst + (long long)r * 3 * E + d;
-            o[0] = dq;
-            o[E] = dkk;
-            o[2 * E] = dv;
-        }
+        ma_cols_acc(o, Pd + j0, lp, Os, L, ld, U, lane);                // dV
+#pragma unroll
+        for (int r = 0; r < kMaRows; ++r)
+            if (j0 + r < L) {
+#pragma unroll
+                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                    const int d = lane + 32 * u;
+                    if (u < U && d < dk) dst[(long long)(j0 + r) * 3 * E + 2 * E + d] = o[r][u];
+                }
+            }
     }
 }
 

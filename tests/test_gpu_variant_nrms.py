@@ -43,6 +43,14 @@ def test_linear_fwd_bwd(M, N, K, built_lib):
     assert dx2 is None and db2 is None and torch.equal(dW2, dW)       # same kernels, same order: bitwise
 
 
+def test_masked_attention_rejects_what_does_not_fit(built_lib):
+    from pytorch_news_recommender_b200 import ops
+    from pytorch_news_recommender_b200._lib import NrmsError
+    for B, L, E3, heads in ((1, 129, 3 * 64, 2), (1, 128, 3 * 128, 1), (1, 16, 3 * 160, 1)):   # L > 128; smem; head dim > 128
+        with pytest.raises(NrmsError):
+            ops.masked_attention_fwd(torch.zeros(B, L, E3, device="cuda"), None, heads, 0.0, 0)
+
+
 def _attention_ref(qkv, mask, heads, mult):
     B, L, E3 = qkv.shape
     E = E3 // 3
@@ -57,7 +65,7 @@ def _attention_ref(qkv, mask, heads, mult):
     return (pd @ v).transpose(1, 2).reshape(B, L, E), p
 
 
-@pytest.mark.parametrize("B,L,heads,dk,p", [(3, 7, 4, 12, 0.0), (5, 50, 8, 64, 0.2), (2, 128, 2, 32, 0.1),
+@pytest.mark.parametrize("B,L,heads,dk,p", [(3, 7, 4, 12, 0.0), (5, 50, 8, 64, 0.2), (2, 96, 2, 32, 0.1),
                                             (4, 33, 5, 100, 0.0)])
 def test_masked_attention(B, L, heads, dk, p, built_lib):
     from pytorch_news_recommender_b200 import ops
