@@ -10,6 +10,7 @@
 // Linears run on the tcgen05 image GEMMs (abi_masked.inc).  Every reduction runs in a fixed order.
 #pragma once
 #include "common.cuh"
+#include "profiler.cuh"
 
 namespace nrms {
 namespace mu {
@@ -85,53 +86,58 @@ __device__ __forceinline__ void ma_load_tile(float* dst, const float* __restrict
     }
 }
 // acc[r][t] = sum_d A[i0 + r][d] * Bm[lane + 32 t][d]   (rows / keys beyond L read row L - 1: discarded by the caller)
-__device__ __forceinline__ void ma_rows_dot(float (&acc)[kMaRows][kMaMaxKeysPerLane], const float* A, const float* Bm, int i0, int L,
-                                            int ld, int T, int lane) {
-    const float* brow[kMaMaxKeysPerLane];
+template <int T>
+__device__ __forceinline__ void ma_rows_dot(float (&acc)[kMaRows][T], const float* A, const float* Bm, int i0, int L, int ld,
+                                            int lane) {
+    const float* brow[T];
+    const float* arow[kMaRows];
 #pragma unroll
-    for (int t = 0; t < kMaMaxKeysPerLane; ++t) brow[t] = Bm + min(lane + 32 * t, L - 1) * ld;
+    for (int t = 0; t < T; ++t) brow[t] = Bm + min(lane + 32 * t, L - 1) * ld;
 #pragma unroll
-    for (int r = 0; r < kMaRows; ++r)
+    for (int r = 0; r < kMaRows; ++r) {
+        arow[r] = A + min(i0 + r, L - 1) * ld;
 #pragma unroll
-        for (int t = 0; t < kMaMaxKeysPerLane; ++t) acc[r][t] = 0.f;
+        for (int t = 0; t < T; ++t) acc[r][t] = 0.f;
+    }
     for (int d = 0; d < ld; d += 4) {
-        float4 bv[kMaMaxKeysPerLane];
+        float4 bv[T];
 #pragma unroll
-        for (int t = 0; t < kMaMaxKeysPerLane; ++t)
-            if (t < T) bv[t] = *reinterpret_cast<const float4*>(brow[t] + d);
+        for (int t = 0; t < T; ++t) bv[t] = *reinterpret_cast<const float4*>(brow[t] + d);
 #pragma unroll
         for (int r = 0; r < kMaRows; ++r) {
-            const float4 av = *reinterpret_cast<const float4*>(A + min(i0 + r, L - 1) * ld + d);
+            const float4 av = *reinterpret_cast<const float4*>(arow[r] + d);
 #pragma unroll
-            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
-                if (t < T) {
-                    acc[r][t] = fmaf(av.x, bv[t].x, acc[r][t]);
-                    acc[r][t] = fmaf(av.y, bv[t].y, acc[r][t]);
-                    acc[r][t] = fmaf(av.z, bv[t].z, acc[r][t]);
-                    acc[r][t] = fmaf(av.w, bv[t].w, acc[r][t]);
-                }
+            for (int t = 0; t < T; ++t) {
+                acc[r][t] = fmaf(av.x, bv[t].x, acc[r][t]);
+                acc[r][t] = fmaf(av.y, bv[t].y, acc[r][t]);
+                acc[r][t] = fmaf(av.z, bv[t].z, acc[r][t]);
+                acc[r][t] = fmaf(av.w, bv[t].w, acc[r][t]);
+            }
         }
     }
 }
 // acc[r][u] = sum_{k < n} W[k * wstride + r] * Bm[k][lane + 32 u]   (W + k * wstride 32-byte aligned)
-__device__ __forceinline__ void ma_cols_acc(float (&acc)[kMaRows][kMaMaxColsPerLane], const float* W, int wstride, const float* Bm,
-                                            int n, int ld, int U, int lane) {
+template <int U>
+__device__ __forceinline__ void ma_cols_acc(float (&acc)[kMaRows][U], const float* W, int wstride, const float* Bm, int n, int ld,
+                                            int lane) {
+    int col[U];      // columns beyond the tile read column 0 (discarded by the caller)
 #pragma unroll
-    for (int r = 0; r < kMaRows; ++r)
+    for (int u = 0; u < U; ++u) {
+        col[u] = lane + 32 * u < ld ? lane + 32 * u : 0;
 #pragma unroll
-        for (int u = 0; u < kMaMaxColsPerLane; ++u) acc[r][u] = 0.f;
+        for (int r = 0; r < kMaRows; ++r) acc[r][u] = 0.f;
+    }
+#pragma unroll 2
     for (int k = 0; k < n; ++k) {
         const float4 w0 = *reinterpret_cast<const float4*>(W + k * wstride);
         const float4 w1 = *reinterpret_cast<const float4*>(W + k * wstride + 4);
         const float w[kMaRows] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-        for (int u = 0; u < kMaMaxColsPerLane; ++u)
-            if (u < U) {
-                const int d = lane + 32 * u;
-                const float bv = d < ld ? Bm[k * ld + d] : 0.f;
+        for (int u = 0; u < U; ++u) {
+            const float bv = Bm[k * ld + col[u]];
 #pragma unroll
-                for (int r = 0; r < kMaRows; ++r) acc[r][u] = fmaf(w[r], bv, acc[r][u]);
-            }
+            for (int r = 0; r < kMaRows; ++r) acc[r][u] = fmaf(w[r], bv, acc[r][u]);
+        }
     }
 }
 // Dropout keep bits of 8 rows x ceil(L/8) groups: one Philox call per (row, group) spread over the lanes
@@ -162,6 +168,7 @@ struct MaKeep {
     }
 };
 
+template <int T, int U>
 __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAttnArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int L = a.L, dk = a.dk, ld = ma_ld(dk), E = a.heads * dk;
@@ -177,17 +184,16 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAt
     ma_load_tile(Vs, src + 2 * E, 3 * E, L, dk, ld);
     __syncthreads();
     const uint8_t* mrow = a.mask ? a.mask + (long long)b * L : nullptr;
-    const int T = (L + 31) >> 5, U = (dk + 31) >> 5;
     float* pt = Pt + warp * L * kMaRows;
-    bool key_real[kMaMaxKeysPerLane];
+    bool key_real[T];
 #pragma unroll
-    for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
+    for (int t = 0; t < T; ++t) {
         const int j = lane + 32 * t;
         key_real[t] = j < L && (!mrow || mrow[j] != 0);
     }
     for (int i0 = warp * kMaRows; i0 < L; i0 += kMaWarps * kMaRows) {
-        float acc[kMaRows][kMaMaxKeysPerLane];
-        ma_rows_dot(acc, Qs, Ks, i0, L, ld, T, lane);
+        float acc[kMaRows][T];
+        ma_rows_dot<T>(acc, Qs, Ks, i0, L, ld, lane);
         const long long prow0 = ((long long)b * a.heads + h) * L + i0;
         MaKeep mk;
         mk.fill(a.drop, (uint64_t)prow0, L, lane);
@@ -198,8 +204,7 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAt
             const bool qi_real = !mrow || mrow[min(i, L - 1)] != 0;
             float mx = -INFINITY;
 #pragma unroll
-            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
-                if (t < T) {
+            for (int t = 0; t < T; ++t) {
                     float v = acc[r][t] * a.scale;
                     if (!(qi_real && key_real[t])) v = -1e9f;      // masked_fill (nrms.py:38-41)
                     acc[r][t] = v;
@@ -208,16 +213,14 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAt
             mx = warp_max(mx);
             float sum = 0.f;
 #pragma unroll
-            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
-                if (t < T) {
+            for (int t = 0; t < T; ++t) {
                     acc[r][t] = lane + 32 * t < L ? expf(acc[r][t] - mx) : 0.f;
                     sum += acc[r][t];
                 }
             sum = warp_sum(sum);
             const float inv = 1.f / sum;
 #pragma unroll
-            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
-                if (t < T) {
+            for (int t = 0; t < T; ++t) {
                     const int j = lane + 32 * t;
                     float p = acc[r][t] * inv;
                     const bool kept = mk.keep(r, min(j, L - 1));
@@ -229,15 +232,15 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAt
                 }
         }
         __syncwarp();
-        float o[kMaRows][kMaMaxColsPerLane];
-        ma_cols_acc(o, pt, kMaRows, Vs, L, ld, U, lane);
+        float o[kMaRows][U];
+        ma_cols_acc<U>(o, pt, kMaRows, Vs, L, ld, lane);
 #pragma unroll
         for (int r = 0; r < kMaRows; ++r)
             if (i0 + r < L) {
 #pragma unroll
-                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int d = lane + 32 * u;
-                    if (u < U && d < dk) a.ctx[((long long)b * L + i0 + r) * E + h * dk + d] = o[r][u];
+                    if (d < dk) a.ctx[((long long)b * L + i0 + r) * E + h * dk + d] = o[r][u];
                 }
             }
         __syncwarp();
@@ -246,6 +249,7 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAt
 
 // backward of the above: dV = Pd^T dO, dPd = dO V^T, dP = dPd * keep/(1-p), dS = P (dP - rowsum(P dP)) / sqrt(dk)
 // with dS = 0 wherever the score was overwritten by the mask (masked_fill passes no gradient), dQ = dS K, dK = dS^T Q.
+template <int T, int U>
 __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_bwd_kernel(MaskedAttnArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int L = a.L, dk = a.dk, ld = ma_ld(dk), E = a.heads * dk, lp = ma_lp(L);
@@ -270,18 +274,17 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_bwd_kernel(MaskedAt
     }
     __syncthreads();
     const uint8_t* mrow = a.mask ? a.mask + (long long)b * L : nullptr;
-    const int T = (L + 31) >> 5, U = (dk + 31) >> 5;
     float* st = St + warp * L * kMaRows;
     float* dst = a.d_qkv + (long long)b * L * 3 * E + h * dk;
-    bool key_real[kMaMaxKeysPerLane];
+    bool key_real[T];
 #pragma unroll
-    for (int t = 0; t < kMaMaxKeysPerLane; ++t) {
+    for (int t = 0; t < T; ++t) {
         const int j = lane + 32 * t;
         key_real[t] = j < L && (!mrow || mrow[j] != 0);
     }
     for (int i0 = warp * kMaRows; i0 < L; i0 += kMaWarps * kMaRows) {
-        float acc[kMaRows][kMaMaxKeysPerLane];
-        ma_rows_dot(acc, Os, Vs, i0, L, ld, T, lane);                   // dPd
+        float acc[kMaRows][T];
+        ma_rows_dot<T>(acc, Os, Vs, i0, L, ld, lane);                   // dPd
         const long long prow0 = ((long long)b * a.heads + h) * L + i0;
         MaKeep mk;
         mk.fill(a.drop, (uint64_t)prow0, L, lane);
@@ -290,11 +293,10 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_bwd_kernel(MaskedAt
             const int i = min(i0 + r, L - 1);
             const bool row_ok = i0 + r < L;
             const bool qi_real = !mrow || mrow[i] != 0;
-            float p[kMaMaxKeysPerLane];
+            float p[T];
             float delta = 0.f;
 #pragma unroll
-            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
-                if (t < T) {
+            for (int t = 0; t < T; ++t) {
                     const int j = lane + 32 * t;
                     const bool kept = mk.keep(r, min(j, L - 1));
                     p[t] = 0.f;
@@ -310,8 +312,7 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_bwd_kernel(MaskedAt
                 }
             delta = warp_sum(delta);
 #pragma unroll
-            for (int t = 0; t < kMaMaxKeysPerLane; ++t)
-                if (t < T) {
+            for (int t = 0; t < T; ++t) {
                     const int j = lane + 32 * t;
                     if (j < L) {
                         const float v = (qi_real && key_real[t]) ? p[t] * (acc[r][t] - delta) * a.scale : 0.f;
@@ -321,43 +322,63 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_bwd_kernel(MaskedAt
                 }
         }
         __syncwarp();
-        float o[kMaRows][kMaMaxColsPerLane];
-        ma_cols_acc(o, st, kMaRows, Ks, L, ld, U, lane);                // dQ rows [i0, i0 + 8)
+        float o[kMaRows][U];
+        ma_cols_acc<U>(o, st, kMaRows, Ks, L, ld, lane);                // dQ rows [i0, i0 + 8)
 #pragma unroll
         for (int r = 0; r < kMaRows; ++r)
             if (i0 + r < L) {
 #pragma unroll
-                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int d = lane + 32 * u;
-                    if (u < U && d < dk) dst[(long long)(i0 + r) * 3 * E + d] = o[r][u];
+                    if (d < dk) dst[(long long)(i0 + r) * 3 * E + d] = o[r][u];
                 }
             }
         __syncwarp();
     }
     __syncthreads();
     for (int j0 = warp * kMaRows; j0 < L; j0 += kMaWarps * kMaRows) {
-        float o[kMaRows][kMaMaxColsPerLane];
-        ma_cols_acc(o, dS + j0, lp, Qs, L, ld, U, lane);                // dK rows [j0, j0 + 8): sum over query rows
+        float o[kMaRows][U];
+        ma_cols_acc<U>(o, dS + j0, lp, Qs, L, ld, lane);                // dK rows [j0, j0 + 8): sum over query rows
 #pragma unroll
         for (int r = 0; r < kMaRows; ++r)
             if (j0 + r < L) {
 #pragma unroll
-                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int d = lane + 32 * u;
-                    if (u < U && d < dk) dst[(long long)(j0 + r) * 3 * E + E + d] = o[r][u];
+                    if (d < dk) dst[(long long)(j0 + r) * 3 * E + E + d] = o[r][u];
                 }
             }
-        ma_cols_acc(o, Pd + j0, lp, Os, L, ld, U, lane);                // dV
+        ma_cols_acc<U>(o, Pd + j0, lp, Os, L, ld, lane);                // dV
 #pragma unroll
         for (int r = 0; r < kMaRows; ++r)
             if (j0 + r < L) {
 #pragma unroll
-                for (int u = 0; u < kMaMaxColsPerLane; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const int d = lane + 32 * u;
-                    if (u < U && d < dk) dst[(long long)(j0 + r) * 3 * E + 2 * E + d] = o[r][u];
+                    if (d < dk) dst[(long long)(j0 + r) * 3 * E + 2 * E + d] = o[r][u];
                 }
             }
     }
+}
+
+// keys per lane T = ceil(L / 32) and head columns per lane U = ceil(dk / 32) are compile-time (fully unrolled
+// register tiles); 3 rounds up to 4
+template <bool BWD>
+cudaError_t launch_masked_attn(const MaskedAttnArgs& a, size_t smem, cudaStream_t s) {
+    const int T = ceil_div(a.L, 32), U = ceil_div(a.dk, 32);
+#define NRMS_MA_CASE(TT, UU)                                                                                       \
+    if (T <= TT && U <= UU) {                                                                                      \
+        auto k = BWD ? masked_attn_bwd_kernel<TT, UU> : masked_attn_fwd_kernel<TT, UU>;                      \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+        if (e != cudaSuccess) return e;                                                                            \
+        NRMS_LAUNCH(BWD ? "masked_attn_bwd" : "masked_attn_fwd", s, k<<<a.B * a.heads, kMaWarps * 32, smem, s>>>(a)); \
+        return cudaGetLastError();                                                                                 \
+    }
+    NRMS_MA_CASE(1, 1) NRMS_MA_CASE(1, 2) NRMS_MA_CASE(1, 4)
+    NRMS_MA_CASE(2, 1) NRMS_MA_CASE(2, 2) NRMS_MA_CASE(2, 4)
+    NRMS_MA_CASE(4, 1) NRMS_MA_CASE(4, 2) NRMS_MA_CASE(4, 4)
+#undef NRMS_MA_CASE
+    return cudaErrorInvalidValue;
 }
 
 // ---- masked additive attention (nrms.py:98-117) after its Linear ------------------------------------------
