@@ -78,13 +78,31 @@ inline size_t masked_attn_bwd_smem(int L, int dk) {
     return sizeof(float) * ((size_t)4 * L * ma_ld(dk) + (size_t)2 * L * ma_lp(L) + (size_t)kMaWarps * L * kMaRows);
 }
 
-// rows [.., L) x columns [0, dk) of a [.., stride] global matrix -> tile [L][ld], padding columns zero
+// rows [0, L) x columns [0, dk) of a [.., stride] global matrix -> tile [L][ld], padding columns zero.
+// 16-byte cp.async where the source allows it (every load of the CTA in flight at once: the tiles are the
+// only global reads of the kernel and with 2 CTAs per SM their latency is exposed); the caller waits with
+// ma_tiles_wait() before its __syncthreads().
 __device__ __forceinline__ void ma_load_tile(float* dst, const float* __restrict__ src, long long stride, int L, int dk, int ld) {
-    for (int i = threadIdx.x; i < L * ld; i += blockDim.x) {
-        const int r = i / ld, d = i - r * ld;
-        dst[i] = d < dk ? src[(long long)r * stride + d] : 0.f;
+    const bool vec = (dk & 3) == 0 && (stride & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+    if (vec) {
+        const int c4 = dk >> 2;
+        for (int i = threadIdx.x; i < L * c4; i += blockDim.x) {
+            const int r = i / c4, c = i - r * c4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + r * ld + 4 * c)),
+                         "l"(src + (long long)r * stride + 4 * c) : "memory");
+        }
+        for (int i = threadIdx.x; i < L * (ld - dk); i += blockDim.x) {
+            const int r = i / (ld - dk), d = dk + i % (ld - dk);
+            dst[r * ld + d] = 0.f;
+        }
+    } else {
+        for (int i = threadIdx.x; i < L * ld; i += blockDim.x) {
+            const int r = i / ld, d = i - r * ld;
+            dst[i] = d < dk ? src[(long long)r * stride + d] : 0.f;
+        }
     }
 }
+__device__ __forceinline__ void ma_tiles_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 // acc[r][t] = sum_d A[i0 + r][d] * Bm[lane + 32 t][d]   (rows / keys beyond L read row L - 1: discarded by the caller)
 template <int T>
 __device__ __forceinline__ void ma_rows_dot(float (&acc)[kMaRows][T], const float* A, const float* Bm, int i0, int L, int ld,
@@ -182,6 +200,7 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_fwd_kernel(MaskedAt
     ma_load_tile(Qs, src, 3 * E, L, dk, ld);
     ma_load_tile(Ks, src + E, 3 * E, L, dk, ld);
     ma_load_tile(Vs, src + 2 * E, 3 * E, L, dk, ld);
+    ma_tiles_wait();
     __syncthreads();
     const uint8_t* mrow = a.mask ? a.mask + (long long)b * L : nullptr;
     float* pt = Pt + warp * L * kMaRows;
@@ -272,6 +291,7 @@ __global__ void __launch_bounds__(kMaWarps * 32) masked_attn_bwd_kernel(MaskedAt
         dS[r * lp + c] = 0.f;
         Pd[r * lp + c] = 0.f;
     }
+    ma_tiles_wait();
     __syncthreads();
     const uint8_t* mrow = a.mask ? a.mask + (long long)b * L : nullptr;
     float* st = St + warp * L * kMaRows;
