@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """The collectives of the data-parallel step, timed alone and inside the step.
 
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/nccl_probe.py [steps=40]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 scripts/nccl_probe.py [steps=40] [caps=16,8,4]
 
 One process per GPU.  Prints one JSON line on rank 0:
   alone     CUDA-event time (max over ranks, mean of 20 calls after 5 warm-ups, nothing else on the GPU) of
@@ -32,6 +32,7 @@ from pytorch_news_recommender_b200.model import NRMS_V0  # noqa: E402
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    caps = [int(c) for c in (sys.argv[2] if len(sys.argv) > 2 else "16,8,4").split(",") if c]
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -81,7 +82,7 @@ def main():
     lib = _lib.load()
     host_batches = bench.make_batches(4, rank)
     in_step = {}
-    for label, cap in (("default", None), ("max_ctas_16", 16), ("max_ctas_8", 8), ("max_ctas_4", 4)):
+    for label, cap in [("default", None)] + [("max_ctas_%d" % c, c) for c in caps]:
         group = None
         if cap is not None:
             try:
