@@ -128,6 +128,12 @@ inline int hpl_min(bool fwd) {
     return fwd ? f : b;
 }
 
+// 48-row backward tiles for sequences of 33..48 tokens (experiment knob NRMS_HPN48=0: 64-row tiles as before)
+inline bool hpn48() {
+    static const bool on = !(getenv("NRMS_HPN48") && atoi(getenv("NRMS_HPN48")) == 0);
+    return on;
+}
+
 struct Saved {
     float* qkv;      // [M, 3D] fp32; HP: bf16 planes hi [M, NP] then lo [M, NP]
     float* lse;      // [M, h]
@@ -635,6 +641,20 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     } else {
                         if ((rc = set_smem(attn_hpl_bwd_kernel<1>, smem))) return rc;
                         NRMS_LAUNCH("attn_bwd", s, (attn_hpl_bwd_kernel<1><<<grid, threads, smem, s>>>(a, items, hp_rows(d))));
+                    }
+                } else if (L > 32 && L <= 48 && hpn48()) {
+                    // 48-row tiles, three warps per item, four items per SM (52 KB each): a 48-token title on
+                    // 64-row tiles wastes a quarter of the rows and 44 % of the S / P work
+                    using C = HpN<48>;
+                    const size_t smem = (size_t)C::ITEMS_BWD * C::item_bwd(terms);
+                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), 4 * kNumSMs);
+                    const int threads = C::ITEMS_BWD * C::NW * 32;
+                    if (terms == 3) {
+                        if ((rc = set_smem(attn_hpn_bwd_kernel<3, 48>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<3, 48><<<grid, threads, smem, s>>>(a, items)));
+                    } else {
+                        if ((rc = set_smem(attn_hpn_bwd_kernel<1, 48>, smem))) return rc;
+                        NRMS_LAUNCH("attn_bwd", s, (attn_hpn_bwd_kernel<1, 48><<<grid, threads, smem, s>>>(a, items)));
                     }
                 } else if (L > 32) {
                     using C = HpN<64>;

@@ -1,6 +1,7 @@
 // attention_hpn.cuh — head-padded attention with SEVERAL warps per (sequence, head), for
-// sequences of up to 32 tokens (LT = 32: two warps per item) and up to 64 tokens (LT = 64: four
-// warps; the user encoder's 50-click history, 48-token titles).  Same math, inputs and outputs as
+// sequences of up to 32 tokens (LT = 32: two warps per item), up to 48 tokens (LT = 48: three warps,
+// backward only; cfg5's 48-token titles) and up to 64 tokens (LT = 64: four warps; the user encoder's
+// 50-click history).  Same math, inputs and outputs as
 // attention_hp.cuh (reference nrms_v0.py:13-23, 46-76, 171-173).
 //
 // Why several warps: shared memory fixes how many items an SM holds (LT = 32 backward: four operand
@@ -25,7 +26,10 @@ namespace nrms {
 
 template <int LT>
 struct HpN {
-    static_assert(LT == 32 || LT == 64, "tiles of 32 or 64 rows");
+    static_assert(LT == 32 || LT == 48 || LT == 64, "tiles of 32, 48 or 64 rows");
+    // rows of a head block in HBM: the 48-row tile (backward only; cfg5's 48-token titles) reads the first 48
+    // rows of the 64-row blocks that the projection writes for sequences of 33..64 tokens
+    static constexpr int BR = LT == 48 ? 64 : LT;
     static constexpr int NW = LT / 16;                 // warps per item
     static constexpr int KSL = LT / 16;                // 16-wide k-steps over query rows / keys
     static constexpr int NTL = LT / 8;                 // 8-wide n-tiles over keys
@@ -128,6 +132,17 @@ __device__ __forceinline__ void hpn_mma_kn(float (&c)[4][4], const uint32_t (&ah
             for (int j = 0; j < 2; ++j)
                 hpn_mma3<TERMS>(c[nt], ah[2 * kh + j], al[2 * kh + j], bh[2 * j], bh[2 * j + 1], bl[2 * j], bl[2 * j + 1]);
         }
+    if (KS & 1) {
+        // odd number of 16-wide k-steps (48-row tiles): the last one is a 16-row ldmatrix.x2
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const uint32_t addr = pair + (16 * (KS - 1) + (lane & 15)) * kHpRowB + nt * 16;
+            uint32_t bh[2], bl[2] = {0u, 0u};
+            ldsm_x2_t(bh, addr);
+            if (TERMS == 3) ldsm_x2_t(bl, addr + lo_off);
+            hpn_mma3<TERMS>(c[nt], ah[KS - 1], al[KS - 1], bh[0], bh[1], bl[0], bl[1]);
+        }
+    }
 }
 template <int N>
 __device__ __forceinline__ void hpn_zero(float (&c)[N][4]) {
@@ -203,10 +218,10 @@ __device__ __forceinline__ void hpn_request_do(uint32_t tile, const float* d_ctx
     }
 }
 template <bool LO>
-__device__ __forceinline__ void hpn_prefetch_blocks(const AttnArgs& a, long long seq, int h, int rows, int lane) {
+__device__ __forceinline__ void hpn_prefetch_blocks(const AttnArgs& a, long long seq, int h, int rows, int lane, int blk_rows = 0) {
     if (lane < (LO ? 6 : 3)) {
         const int plane = lane / 3, which = lane - plane * 3;
-        const uint16_t* p = (plane ? a.qkv_lo : a.qkv_hi) + hp_block_off(seq, which, h, a.n_heads, rows);
+        const uint16_t* p = (plane ? a.qkv_lo : a.qkv_hi) + hp_block_off(seq, which, h, a.n_heads, blk_rows ? blk_rows : rows);
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(rows * 64) : "memory");
     }
 }
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(HpN<LT>::ITEMS_FWD* HpN<LT>::NW * 32, 2) attn_
 //   dV = P^T dO ; dK = dS^T Q ; dQ = dS K        -> d_qkv image, head-padded column order
 // ------------------------------------------------------------------------------------------------
 template <int TERMS, int LT>
-__global__ void __launch_bounds__(HpN<LT>::ITEMS_BWD* HpN<LT>::NW * 32, (LT == 64 && TERMS == 1) ? 3 : 2)
+__global__ void __launch_bounds__(HpN<LT>::ITEMS_BWD* HpN<LT>::NW * 32, LT == 48 ? 4 : (LT == 64 && TERMS == 1) ? 3 : 2)
 attn_hpn_bwd_kernel(const AttnArgs a, long long n_items) {
     using C = HpN<LT>;
     extern __shared__ __align__(16) float smem[];
@@ -362,9 +377,9 @@ attn_hpn_bwd_kernel(const AttnArgs a, long long n_items) {
         const bool has_next = item + stride < n_items;
         const long long nseq = (item + stride) / a.n_heads;
         const int nh = (int)(item + stride - nseq * a.n_heads);
-        hpn_load_rows<TERMS == 3>(Qs, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 0, h, a.n_heads, LT), m0, L, lane);
-        hpn_load_rows<TERMS == 3>(Ks, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads, LT), m0, L, lane);
-        hpn_load_rows<TERMS == 3>(Vs, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads, LT), m0, L, lane);
+        hpn_load_rows<TERMS == 3>(Qs, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 0, h, a.n_heads, C::BR), m0, L, lane);
+        hpn_load_rows<TERMS == 3>(Ks, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads, C::BR), m0, L, lane);
+        hpn_load_rows<TERMS == 3>(Vs, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads, C::BR), m0, L, lane);
         float lse[2];
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -400,7 +415,7 @@ attn_hpn_bwd_kernel(const AttnArgs a, long long n_items) {
         }
         hpn_store_a<TERMS, 2>(Gs, kHpRowB, C::PLANE, gh, gl, m0, g, t);
         if (has_next && w == 0) {
-            hpn_prefetch_blocks<TERMS == 3>(a, nseq, nh, LT, lane);
+            hpn_prefetch_blocks<TERMS == 3>(a, nseq, nh, LT, lane, C::BR);
             if (lane < L) prefetch_l2(a.lse + (nseq * L + lane) * a.n_heads + nh);
         }
         float p[C::NTL][4], ds[C::NTL][4];
