@@ -134,6 +134,11 @@ inline bool hpn48() {
     return on;
 }
 
+inline bool hpn48_fwd() {
+    static const bool on = getenv("NRMS_HPN48_FWD") && atoi(getenv("NRMS_HPN48_FWD")) == 1;
+    return on && hpn48();
+}
+
 struct Saved {
     float* qkv;      // [M, 3D] fp32; HP: bf16 planes hi [M, NP] then lo [M, NP]
     float* lse;      // [M, h]
@@ -436,7 +441,20 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             a.qkv_hi = reinterpret_cast<const uint16_t*>(sv.qkv);
             a.qkv_lo = a.qkv_hi + (long long)d.n_seq * hp_rows(d) * NP;
             const long long items = (long long)d.n_seq * h;
-            if (L >= hpl_min(true)) {
+            if (L > 32 && L <= 48 && hpn48_fwd()) {
+                // three warps per (sequence, head) over the first 48 rows of the 64-row blocks (attention_hpn.cuh)
+                using C = HpN<48>;
+                const size_t smem = (size_t)C::ITEMS_FWD * C::ITEM_FWD;
+                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_FWD), 3 * kNumSMs);
+                const int threads = C::ITEMS_FWD * C::NW * 32;
+                if (terms == 3) {
+                    if ((rc = set_smem(attn_hpn_fwd_kernel<3, 48>, smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<3, 48><<<grid, threads, smem, s>>>(a, items)));
+                } else {
+                    if ((rc = set_smem(attn_hpn_fwd_kernel<1, 48>, smem))) return rc;
+                    NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<1, 48><<<grid, threads, smem, s>>>(a, items)));
+                }
+            } else if (L >= hpl_min(true)) {
                 // one CTA per (sequence, head), a warp per 16 rows, keys in tiles of 64 with an online softmax
                 // (attention_hpl.cuh)
                 const size_t smem = attn_hpl_fwd_smem_bytes(L);

@@ -1,6 +1,6 @@
 // attention_hpn.cuh — head-padded attention with SEVERAL warps per (sequence, head), for
-// sequences of up to 32 tokens (LT = 32: two warps per item), up to 48 tokens (LT = 48: three warps,
-// backward only; cfg5's 48-token titles) and up to 64 tokens (LT = 64: four warps; the user encoder's
+// sequences of up to 32 tokens (LT = 32: two warps per item), up to 48 tokens (LT = 48: three warps;
+// cfg5's 48-token titles) and up to 64 tokens (LT = 64: four warps; the user encoder's
 // 50-click history).  Same math, inputs and outputs as
 // attention_hp.cuh (reference nrms_v0.py:13-23, 46-76, 171-173).
 //
@@ -27,7 +27,7 @@ namespace nrms {
 template <int LT>
 struct HpN {
     static_assert(LT == 32 || LT == 48 || LT == 64, "tiles of 32, 48 or 64 rows");
-    // rows of a head block in HBM: the 48-row tile (backward only; cfg5's 48-token titles) reads the first 48
+    // rows of a head block in HBM: the 48-row tile (cfg5's 48-token titles) reads the first 48
     // rows of the 64-row blocks that the projection writes for sequences of 33..64 tokens
     static constexpr int BR = LT == 48 ? 64 : LT;
     static constexpr int NW = LT / 16;                 // warps per item
@@ -230,7 +230,7 @@ __device__ __forceinline__ void hpn_prefetch_blocks(const AttnArgs& a, long long
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int TERMS, int LT>
-__global__ void __launch_bounds__(HpN<LT>::ITEMS_FWD* HpN<LT>::NW * 32, 2) attn_hpn_fwd_kernel(const AttnArgs a, long long n_items) {
+__global__ void __launch_bounds__(HpN<LT>::ITEMS_FWD* HpN<LT>::NW * 32, LT == 48 ? 3 : 2) attn_hpn_fwd_kernel(const AttnArgs a, long long n_items) {
     using C = HpN<LT>;
     extern __shared__ __align__(16) float smem[];
     uint8_t* sm = reinterpret_cast<uint8_t*>(smem);
@@ -249,11 +249,11 @@ __global__ void __launch_bounds__(HpN<LT>::ITEMS_FWD* HpN<LT>::NW * 32, 2) attn_
         const int h = (int)(item - seq * a.n_heads);
         const long long row0 = seq * L;
         const int col = h * dk, g0 = col >> 3;
-        hpn_load_rows<TERMS == 3>(Ks, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads, LT), m0, L, lane);
-        hpn_load_rows<TERMS == 3>(Vs, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads, LT), m0, L, lane);
+        hpn_load_rows<TERMS == 3>(Ks, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads, C::BR), m0, L, lane);
+        hpn_load_rows<TERMS == 3>(Vs, C::PLANE, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads, C::BR), m0, L, lane);
         // Q is only ever an A operand: the own rows' fragments come straight from the global planes
         uint32_t qh[2][4], ql[2][4];
-        const long long qblk = hp_block_off(seq, 0, h, a.n_heads, LT);
+        const long long qblk = hp_block_off(seq, 0, h, a.n_heads, C::BR);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(HpN<LT>::ITEMS_FWD* HpN<LT>::NW * 32, 2) attn_
         item_bar(bar, C::NW * 32);                          // K and V complete
         if (w == 0 && item + stride < n_items) {
             const long long nseq = (item + stride) / a.n_heads;
-            hpn_prefetch_blocks<TERMS == 3>(a, nseq, (int)(item + stride - nseq * a.n_heads), LT, lane);
+            hpn_prefetch_blocks<TERMS == 3>(a, nseq, (int)(item + stride - nseq * a.n_heads), LT, lane, C::BR);
         }
         float s[C::NTL][4];
         hpn_zero(s);
