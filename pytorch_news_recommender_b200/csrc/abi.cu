@@ -413,7 +413,8 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         if (use_pairs())
             NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT, true>(g, s, "gemm_fwd_qkv")));
         else
-            NRMS_CHECK_CUDA((ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT>(g, s, "gemm_fwd_qkv")));
+            NRMS_CHECK_CUDA((terms == 3 ? ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT>(g, s, "gemm_fwd_qkv")
+                                        : ig::ig_launch<false, false, 256, ig::EPI_BIAS_SPLIT_HI>(g, s, "gemm_fwd_qkv")));
     } else if (tcm) {
         NRMS_CHECK_CUDA(ig::img_pack2(pv.Wqkv, 3 * D, D, D, sv.wqkv_img, 0, 0, pv.Wa, Q, D, D, sv.wa_img, s));
         ig::IgArgs g = ig_args(sv.x_img, sv.wqkv_img, sv.qkv, 3 * D, M, 3 * D);

@@ -177,7 +177,8 @@ inline cudaError_t img_pack(const float* src, int R, int C, int ld, const Img& i
 
 // ---- the GEMM ----------------------------------------------------------------------------------
 enum Epi { EPI_BIAS = 0, EPI_TANH_DOT = 1, EPI_ACCUM = 2, EPI_MASK = 3, EPI_PARTIAL = 4, EPI_POOLADD = 5,
-           EPI_BIAS_SPLIT = 6 };   // bias (head-padded order) + split-bf16 row-major planes out
+           EPI_BIAS_SPLIT = 6,     // bias (head-padded order) + split-bf16 row-major planes out
+           EPI_BIAS_SPLIT_HI = 7 };// the same with the hi plane only (plain-bf16 products: nobody reads lo)
 
 struct IgArgs {
     Img A, B;
@@ -514,7 +515,9 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
         const int q = warp & 3;                       // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;             // which of the quadrant's two warps
         const int et = (warp - 2) * 32 + lane;        // 0..255 within the epilogue group
-        static_assert(!(EPI == EPI_BIAS || EPI == EPI_TANH_DOT || EPI == EPI_BIAS_SPLIT) || N_T <= 256,
+        constexpr bool SPLIT = EPI == EPI_BIAS_SPLIT || EPI == EPI_BIAS_SPLIT_HI;
+        constexpr bool SPLIT_LO = EPI == EPI_BIAS_SPLIT;
+        static_assert(!(EPI == EPI_BIAS || EPI == EPI_TANH_DOT || SPLIT) || N_T <= 256,
                       "epilogue staging holds 256 columns");
         static_assert(EPI != EPI_TANH_DOT || N_T <= 224, "query-vector / row-dot staging exists for N_T <= 224 only");
         float* s_bias = s_epi;                        // [NPAD]
@@ -533,11 +536,11 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
             const int m_tile = PAIR ? 2 * mt_w + (int)rank : mt_w;      // (may be one past the last tile: rows >= M)
             const int n0 = n_tile * N_T;
             const int buf = (int)(tile_it & 1u);
-            if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT || EPI == EPI_BIAS_SPLIT) {
+            if (EPI == EPI_BIAS || EPI == EPI_TANH_DOT || SPLIT) {
                 asm volatile("bar.sync 1, 256;" ::: "memory");     // previous tile's readers are done
                 for (int i = et; i < N_T; i += 256) {
                     const int n = n0 + i;
-                    if (EPI == EPI_BIAS_SPLIT) {
+                    if (SPLIT) {
                         const int ns = n < a.N ? hp_unpad(n, a.hp_D, a.hp_dk) : -1;
                         s_bias[i] = ns >= 0 ? __ldg(a.bias + ns) : 0.f;
                         continue;
@@ -560,7 +563,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
             // EPI_BIAS_SPLIT: element offset of the four block rows this lane stores (row 8i + lane%8 of the
             // warp's 32), without the head part: ((seq * 3 * heads) * rows_per_block + l) * 32; -1 past M
             long long split_row_off[4] = {-1, -1, -1, -1};
-            if (EPI == EPI_BIAS_SPLIT) {
+            if (SPLIT) {
                 const int nh = a.hp_D / a.hp_dk;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -615,7 +618,7 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(vnext[i]);
                 if (bi + 1 < n_mine) tc::tmem_ld32_issue(t_row + 32u * (uint32_t)block_of(bi + 1), vnext);
-                if (EPI == EPI_BIAS_SPLIT) {
+                if (SPLIT) {
                     // TMEM gives a lane one output row; 32 columns = one head of the head-padded order, i.e.
                     // one 64-byte row of a head block per plane.  The rows go through the warp's staging
                     // buffer (row = 128 bytes: 4 hi units, 4 lo units, unit index XOR row%8) so that a store
@@ -626,15 +629,21 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b4 = tc::lds128f(s_bias_a + 4u * (uint32_t)(cb + 4 * j));
-                            split2(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, hi[2 * j], lo[2 * j]);
-                            split2(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w, hi[2 * j + 1], lo[2 * j + 1]);
+                            if (SPLIT_LO) {
+                                split2(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, hi[2 * j], lo[2 * j]);
+                                split2(v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w, hi[2 * j + 1], lo[2 * j + 1]);
+                            } else {
+                                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi[2 * j]) : "f"(v[4 * j + 1] + b4.y), "f"(v[4 * j] + b4.x));
+                                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi[2 * j + 1]) : "f"(v[4 * j + 3] + b4.w), "f"(v[4 * j + 2] + b4.z));
+                            }
                         }
                         const int l7 = lane & 7;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             tc::sts128(s_xb + lane * 128 + ((j ^ l7) << 4), hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                            tc::sts128(s_xb + lane * 128 + (((4 + j) ^ l7) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2],
-                                       lo[4 * j + 3]);
+                            if (SPLIT_LO)
+                                tc::sts128(s_xb + lane * 128 + (((4 + j) ^ l7) << 4), lo[4 * j], lo[4 * j + 1], lo[4 * j + 2],
+                                           lo[4 * j + 3]);
                         }
                         __syncwarp();
                         // lane -> (row 8i + lane%8, unit lane/8): the 8 lanes of a shared-memory phase read 8
@@ -646,9 +655,11 @@ __global__ void __launch_bounds__(ig_threads(N_T), 1) ig_gemm_kernel(const IgArg
                             if (split_row_off[i] >= 0) {
                                 const int rr = 8 * i + l7;      // rr % 8 == l7
                                 const uint4 h4 = tc::lds128(s_xb + rr * 128 + ((u ^ l7) << 4));
-                                const uint4 l4 = tc::lds128(s_xb + rr * 128 + (((4 + u) ^ l7) << 4));
                                 *reinterpret_cast<uint4*>(a.Chi + split_row_off[i] + jpart) = h4;
-                                if (a.Clo) *reinterpret_cast<uint4*>(a.Clo + split_row_off[i] + jpart) = l4;
+                                if (SPLIT_LO) {
+                                    const uint4 l4 = tc::lds128(s_xb + rr * 128 + (((4 + u) ^ l7) << 4));
+                                    if (a.Clo) *reinterpret_cast<uint4*>(a.Clo + split_row_off[i] + jpart) = l4;
+                                }
                             }
                         }
                         __syncwarp();
