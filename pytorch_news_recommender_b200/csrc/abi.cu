@@ -1039,8 +1039,10 @@ int nrms_embedding_plan(const int64_t* ids, int64_t n_rows, int32_t vocab, void*
     NRMS_LAUNCH("plan_sort", s, rsort_init_kernel<<<grid_for(n_rows, 256), 256, 0, s>>>(ids, n_rows, vocab, ka, va));
     for (int p = 0; p < passes; ++p) {
         NRMS_LAUNCH("plan_sort", s, rsort_hist_kernel<<<nblk, 256, 0, s>>>(ka, n_rows, p * rb, bins, v.rhist, nblk));
-        NRMS_LAUNCH("plan_sort", s, rsort_scan_kernel<<<1, 1024, 0, s>>>(v.rhist, (long long)bins * nblk));
-        NRMS_LAUNCH("plan_sort", s, rsort_scatter_kernel<<<nblk, 256, 0, s>>>(ka, va, n_rows, p * rb, bins, v.rhist, nblk, kb, vb));
+        const int nh = bins * nblk, hblocks = ceil_div(nh, kScanBlock);
+        NRMS_LAUNCH("plan_sort", s, plan_block_totals_kernel<<<hblocks, kScanBlock, 0, s>>>(v.rhist, v.rblock_tot, nh));
+        NRMS_LAUNCH("plan_sort", s, plan_scan_kernel<<<hblocks, kScanBlock, 0, s>>>(v.rhist, v.rblock_tot, v.rscan, nullptr, nh));
+        NRMS_LAUNCH("plan_sort", s, rsort_scatter_kernel<<<nblk, 256, 0, s>>>(ka, va, n_rows, p * rb, bins, v.rscan, nblk, kb, vb));
         std::swap(ka, kb);
         std::swap(va, vb);
     }

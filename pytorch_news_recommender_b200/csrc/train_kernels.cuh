@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(256) score_cached_kernel(const ScoreCachedArgs
 //      run that crosses a chunk edge leaves its piece in a partial slot of that chunk;
 //   4. one warp per multi-chunk word adds that word's pieces in chunk order and stores the row.
 // plan blob: int32 counts[V] | offsets[V+1] | perm[n] | sorted_id[n] | n_valid | block_tot[ceil(V/1024)]
-//            | tmp_key[n] | tmp_val[n] | radix hist[512 * ceil(n/2048)] | float part[2][ceil(n/32)][kPartLd]
+//            | tmp_key[n] | tmp_val[n] | radix hist[512 * ceil(n/2048)] | its scan [.. + 1] | its block totals
+//            | float part[2][ceil(n/32)][kPartLd]
 // ---------------------------------------------------------------------------------------
 constexpr int kPartLd = 384;          // floats per partial slot (the kernels support D <= 384)
 constexpr int kRsBlock = 2048;        // keys per CTA of the radix passes (8 warps x 8 x 32)
@@ -185,13 +186,16 @@ struct PlanView {
     int32_t* block_tot;
     int32_t* tmp_key;
     int32_t* tmp_val;
-    int32_t* rhist;
+    int32_t* rhist;       // [bins][nblk] digit counts of every 2048-key block (digit-major)
+    int32_t* rscan;       // exclusive scan of rhist (+ the total)
+    int32_t* rblock_tot;  // totals of the scan's 1024-entry blocks
     float* part;          // [2][n_chunks][kPartLd]: slot 0 = piece of a run that began in an EARLIER chunk,
                           //                           slot 1 = piece of a run that continues into the NEXT chunk
     long long n_chunks;
 };
 inline int64_t plan_ints(int64_t n_rows, int32_t vocab) {
-    return 2ll * vocab + 1 + 2 * n_rows + 4 + (vocab + 1023) / 1024 + 2 * n_rows + (int64_t)kRsMaxBins * ceil_div64(n_rows, kRsBlock);
+    const int64_t nh = (int64_t)kRsMaxBins * ceil_div64(n_rows, kRsBlock);
+    return 2ll * vocab + 1 + 2 * n_rows + 4 + (vocab + 1023) / 1024 + 2 * n_rows + nh + (nh + 1) + ceil_div64(nh, 1024);
 }
 inline int64_t plan_bytes(int64_t n_rows, int32_t vocab) {
     return align_up((int64_t)sizeof(int32_t) * plan_ints(n_rows, vocab), 256) +
@@ -209,6 +213,9 @@ inline PlanView plan_view(void* blob, int64_t n_rows, int32_t vocab) {
     v.tmp_key = v.block_tot + (vocab + 1023) / 1024;
     v.tmp_val = v.tmp_key + n_rows;
     v.rhist = v.tmp_val + n_rows;
+    const int64_t nh = (int64_t)kRsMaxBins * ceil_div64(n_rows, kRsBlock);
+    v.rscan = v.rhist + nh;
+    v.rblock_tot = v.rscan + nh + 1;
     v.part = reinterpret_cast<float*>(reinterpret_cast<char*>(blob) +
                                       align_up((int64_t)sizeof(int32_t) * plan_ints(n_rows, vocab), 256));
     v.n_chunks = ceil_div64(n_rows, 32);
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(kScanBlock) plan_scan_kernel(const int32_t* __
     if (i < vocab) offsets[i] = base + inc - c;
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
         offsets[vocab] = base + total;
-        *n_valid = base + total;
+        if (n_valid) *n_valid = base + total;
     }
 }
 
@@ -312,22 +319,8 @@ __global__ void __launch_bounds__(256) rsort_hist_kernel(const int32_t* __restri
     __syncthreads();
     for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[(long long)i * nblk + blockIdx.x] = h[i];
 }
-// exclusive scan of hist[bins * nblk] in place (digit-major: all blocks of digit 0, then digit 1, ...): one CTA
-__global__ void __launch_bounds__(1024) rsort_scan_kernel(int32_t* __restrict__ hist, long long total) {
-    __shared__ int32_t warp_tot[32];
-    __shared__ int32_t tot;
-    const long long per = ceil_div64(total, 1024);
-    const long long lo = threadIdx.x * per, hi = lo + per < total ? lo + per : total;
-    int32_t sum = 0;
-    for (long long i = lo; i < hi; ++i) sum += hist[i];
-    const int32_t inc = block_inclusive_scan(sum, warp_tot, &tot);
-    int32_t run = inc - sum;
-    for (long long i = lo; i < hi; ++i) {
-        const int32_t c = hist[i];
-        hist[i] = run;
-        run += c;
-    }
-}
+// (the exclusive scan of hist[bins * nblk], digit-major — all blocks of digit 0, then digit 1, ... — is the
+// two-level scan above: plan_block_totals_kernel + plan_scan_kernel over 1024-entry blocks)
 // stable scatter: warp w of a block owns keys [256 w, 256 w + 256) of the block and walks them in order, 32
 // at a time; the rank of a key among the block's earlier keys of the same digit = (count in earlier warps) +
 // (count in this warp's earlier groups) + (earlier lanes of its group with the same digit)
