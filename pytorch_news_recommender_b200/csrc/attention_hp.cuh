@@ -153,37 +153,19 @@ __global__ void __launch_bounds__(kHpFwdWarps * 32, 2) attn_hp_fwd_kernel(const 
     uint8_t* sm = reinterpret_cast<uint8_t*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long stride = (long long)gridDim.x * kHpFwdWarps;
-    // Plain-bf16 products (TERMS == 1) never load a lo plane, so the warp's two pairs are used as TWO
-    // K|V buffers of hi planes instead: the next item's K and V are requested (cp.async) before the current
-    // item is computed and land underneath it.  `cur` selects the buffer of the current item.
-    constexpr bool PINGPONG = TERMS == 1;
-    int cur = 0;
-    if (PINGPONG) {
-        const long long item0 = (long long)blockIdx.x * kHpFwdWarps + warp;
-        if (item0 < n_items) {
-            const long long seq0 = item0 / a.n_heads;
-            const int h0 = (int)(item0 - seq0 * a.n_heads);
-            const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(sm + (size_t)warp * 2 * kHpPairB);
-            hp_load_pair<false>(b0, a.qkv_hi, a.qkv_lo, hp_block_off(seq0, 1, h0, a.n_heads), a.L, lane);
-            hp_load_pair<false>(b0 + kHpPlaneB, a.qkv_hi, a.qkv_lo, hp_block_off(seq0, 2, h0, a.n_heads), a.L, lane);
-        }
-    }
     for (long long item = (long long)blockIdx.x * kHpFwdWarps + warp; item < n_items; item += stride) {
     const int L = a.L, D = a.D, dk = a.dk;
     const long long seq = item / a.n_heads;
     const int h = (int)(item - seq * a.n_heads);
-    // K pair (TERMS == 3) or the current K|V buffer (TERMS == 1); later the fp32 output staging
-    uint8_t* Kb = sm + (size_t)warp * 2 * kHpPairB + (PINGPONG ? (size_t)cur * kHpPairB : 0);
-    const uint32_t Ks = (uint32_t)__cvta_generic_to_shared(Kb), Vs = Ks + (PINGPONG ? kHpPlaneB : kHpPairB);
+    uint8_t* Kb = sm + (size_t)warp * 2 * kHpPairB;       // K pair, later the fp32 output staging
+    const uint32_t Ks = (uint32_t)__cvta_generic_to_shared(Kb), Vs = Ks + kHpPairB;
     uint8_t* smask = sm + (size_t)kHpFwdWarps * 2 * kHpPairB + warp * kTile * 8;
     const long long row0 = seq * L;
     const int col = h * dk;
     const int g = lane >> 2, t = lane & 3;
 
-    if (!PINGPONG) {
-        hp_load_pair<TERMS == 3>(Ks, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads), L, lane);
-        hp_load_pair<TERMS == 3>(Vs, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads), L, lane);
-    }
+    hp_load_pair<TERMS == 3>(Ks, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 1, h, a.n_heads), L, lane);
+    hp_load_pair<TERMS == 3>(Vs, a.qkv_hi, a.qkv_lo, hp_block_off(seq, 2, h, a.n_heads), L, lane);
     const long long qblk = hp_block_off(seq, 0, h, a.n_heads);
     // Q is only ever an A operand: its fragments come straight from the global planes
     uint32_t qh[2][2][4], ql[2][2][4];
@@ -212,22 +194,7 @@ __global__ void __launch_bounds__(kHpFwdWarps * 32, 2) attn_hp_fwd_kernel(const 
     }
     cp_async_wait_all();
     __syncwarp();
-    if (PINGPONG) {
-        // the other buffer was the previous item's staging tile (its reads ended at the loop's last
-        // __syncwarp): the next item's K and V go there now; L2 prefetch runs one more item ahead
-        if (item + stride < n_items) {
-            const long long nseq = (item + stride) / a.n_heads;
-            const int nh = (int)(item + stride - nseq * a.n_heads);
-            const uint32_t nb = (uint32_t)__cvta_generic_to_shared(sm + (size_t)warp * 2 * kHpPairB + (size_t)(cur ^ 1) * kHpPairB);
-            hp_load_pair<false>(nb, a.qkv_hi, a.qkv_lo, hp_block_off(nseq, 1, nh, a.n_heads), L, lane);
-            hp_load_pair<false>(nb + kHpPlaneB, a.qkv_hi, a.qkv_lo, hp_block_off(nseq, 2, nh, a.n_heads), L, lane);
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        }
-        if (item + 2 * stride < n_items) {
-            const long long nseq = (item + 2 * stride) / a.n_heads;
-            hp_prefetch_blocks<false>(a, nseq, (int)(item + 2 * stride - nseq * a.n_heads), 0, lane);
-        }
-    } else if (item + stride < n_items) {
+    if (item + stride < n_items) {
         const long long nseq = (item + stride) / a.n_heads;
         hp_prefetch_blocks<TERMS == 3>(a, nseq, (int)(item + stride - nseq * a.n_heads), 0, lane);
     }
@@ -279,7 +246,6 @@ __global__ void __launch_bounds__(kHpFwdWarps * 32, 2) attn_hp_fwd_kernel(const 
     if (a.ctx_img.hi != nullptr)
         pad_image(a.ctx_img, row0, L, D, a.ctx_img.chunks * 64, h == a.n_heads - 1, item == n_items - 1, a.M, lane, true);
     __syncwarp();                               // the staging reads are done before the next item's copies land
-    cur ^= 1;
     }
 }
 
