@@ -6,7 +6,7 @@ every kernel of one step.  Usage (on the GPU box):
     ncu --set full --clock-control none --import-source on --launch-skip <W*L> --launch-count <L> \
         -o gpurun_out/prof_step python scripts/prof_step.py
 
-Env: STEPS (default 3), GEMM_MODE (default 1), B (default 64), EVAL=1 adds one scoring pass.
+Env: STEPS (default 3), CONFIG (cfg2 | cfg3 | cfg5: bench.CONFIGS), GEMM_MODE / B override the config's.
 Prints the number of library launches per step so --launch-skip can be computed."""
 import os
 import sys
@@ -24,12 +24,17 @@ from pytorch_news_recommender_b200.model import NRMS_V0  # noqa: E402
 
 def main():
     steps = int(os.environ.get("STEPS", "3"))
-    bench.WORKLOAD["batch_per_gpu"] = int(os.environ.get("B", "64"))
+    conf = dict(bench.CONFIGS[os.environ.get("CONFIG", "cfg2")])
+    conf.pop("label")
+    gemm_mode = int(os.environ.get("GEMM_MODE", conf.pop("gemm_mode")))
+    bench.WORKLOAD.update(conf)
+    if "B" in os.environ:
+        bench.WORKLOAD["batch_per_gpu"] = int(os.environ["B"])
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
     tmp = os.path.join(tempfile.gettempdir(), "nrms_bench")
     os.makedirs(tmp, exist_ok=True)
-    cfg = bench.make_config(tmp, dev, int(os.environ.get("GEMM_MODE", "1")))
+    cfg = bench.make_config(tmp, dev, gemm_mode)
     torch.manual_seed(42)
     model = NRMS_V0(cfg).to(dev)
     model.train()
