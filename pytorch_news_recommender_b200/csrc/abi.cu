@@ -136,6 +136,10 @@ inline bool hpn48() {
     return on;
 }
 
+inline bool hpn32_fwd() {
+    static const bool on = getenv("NRMS_HPN32_FWD") && atoi(getenv("NRMS_HPN32_FWD")) == 1;
+    return on;
+}
 inline bool hpn48_fwd() {
     static const bool on = !(getenv("NRMS_HPN48_FWD") && atoi(getenv("NRMS_HPN48_FWD")) == 0);
     return on && hpn48();
@@ -448,7 +452,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                 // three warps per (sequence, head) over the first 48 rows of the 64-row blocks (attention_hpn.cuh)
                 using C = HpN<48>;
                 const size_t smem = (size_t)C::ITEMS_FWD * C::ITEM_FWD;
-                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_FWD), 3 * kNumSMs);
+                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_FWD), (terms == 3 ? 3 : 4) * kNumSMs);
                 const int threads = C::ITEMS_FWD * C::NW * 32;
                 if (terms == 3) {
                     if ((rc = set_smem(attn_hpn_fwd_kernel<3, 48>, smem))) return rc;
@@ -483,6 +487,14 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     if ((rc = set_smem(attn_hpn_fwd_kernel<1, 64>, smem))) return rc;
                     NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<1, 64><<<grid, threads, smem, s>>>(a, items)));
                 }
+            } else if (terms == 1 && hpn32_fwd()) {
+                // experiment (NRMS_HPN32_FWD=1): two warps per item for <= 32 tokens with plain-bf16 products
+                using C = HpN<32>;
+                const size_t smem = (size_t)C::ITEMS_FWD * C::ITEM_FWD;
+                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_FWD), 3 * kNumSMs);
+                const int threads = C::ITEMS_FWD * C::NW * 32;
+                if ((rc = set_smem(attn_hpn_fwd_kernel<1, 32>, smem))) return rc;
+                NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<1, 32><<<grid, threads, smem, s>>>(a, items)));
             } else {
             const size_t smem = attn_hp_fwd_smem_bytes();
             const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpFwdWarps), 2 * kNumSMs);   // persistent warps
@@ -668,7 +680,7 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     // 64-row tiles wastes a quarter of the rows and 44 % of the S / P work
                     using C = HpN<48>;
                     const size_t smem = (size_t)C::ITEMS_BWD * C::item_bwd(terms);
-                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), 4 * kNumSMs);
+                    const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_BWD), (terms == 3 ? 4 : 5) * kNumSMs);
                     const int threads = C::ITEMS_BWD * C::NW * 32;
                     if (terms == 3) {
                         if ((rc = set_smem(attn_hpn_bwd_kernel<3, 48>, smem))) return rc;
