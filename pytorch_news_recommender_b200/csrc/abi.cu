@@ -136,10 +136,6 @@ inline bool hpn48() {
     return on;
 }
 
-inline bool hpn32_fwd() {
-    static const bool on = getenv("NRMS_HPN32_FWD") && atoi(getenv("NRMS_HPN32_FWD")) == 1;
-    return on;
-}
 inline bool hpn48_fwd() {
     static const bool on = !(getenv("NRMS_HPN48_FWD") && atoi(getenv("NRMS_HPN48_FWD")) == 0);
     return on && hpn48();
@@ -487,14 +483,6 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
                     if ((rc = set_smem(attn_hpn_fwd_kernel<1, 64>, smem))) return rc;
                     NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<1, 64><<<grid, threads, smem, s>>>(a, items)));
                 }
-            } else if (terms == 1 && hpn32_fwd()) {
-                // experiment (NRMS_HPN32_FWD=1): two warps per item for <= 32 tokens with plain-bf16 products
-                using C = HpN<32>;
-                const size_t smem = (size_t)C::ITEMS_FWD * C::ITEM_FWD;
-                const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, C::ITEMS_FWD), 3 * kNumSMs);
-                const int threads = C::ITEMS_FWD * C::NW * 32;
-                if ((rc = set_smem(attn_hpn_fwd_kernel<1, 32>, smem))) return rc;
-                NRMS_LAUNCH("attn_fwd", s, (attn_hpn_fwd_kernel<1, 32><<<grid, threads, smem, s>>>(a, items)));
             } else {
             const size_t smem = attn_hp_fwd_smem_bytes();
             const unsigned grid = (unsigned)std::min<long long>(ceil_div64(items, kHpFwdWarps), 2 * kNumSMs);   // persistent warps

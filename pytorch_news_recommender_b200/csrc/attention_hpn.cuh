@@ -230,7 +230,7 @@ __device__ __forceinline__ void hpn_prefetch_blocks(const AttnArgs& a, long long
 // forward
 // ------------------------------------------------------------------------------------------------
 template <int TERMS, int LT>
-__global__ void __launch_bounds__(HpN<LT>::ITEMS_FWD* HpN<LT>::NW * 32, LT == 48 ? (TERMS == 1 ? 4 : 3) : (LT == 32 && TERMS == 1) ? 3 : 2) attn_hpn_fwd_kernel(const AttnArgs a, long long n_items) {
+__global__ void __launch_bounds__(HpN<LT>::ITEMS_FWD* HpN<LT>::NW * 32, LT == 48 ? (TERMS == 1 ? 4 : 3) : 2) attn_hpn_fwd_kernel(const AttnArgs a, long long n_items) {
     using C = HpN<LT>;
     extern __shared__ __align__(16) float smem[];
     uint8_t* sm = reinterpret_cast<uint8_t*>(smem);
