@@ -79,7 +79,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 template <bool LO>
 __device__ __forceinline__ void hp_load_pair(uint32_t pair, const uint16_t* hi, const uint16_t* lo, long long blk,
                                              int L, int lane) {
-    const int r8 = lane & 7, u = lane >> 3;      // row-major lanes within a phase: see hpn_load_rows
+    const int r8 = lane >> 2, u = lane & 3;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int r = r8 + 8 * i;

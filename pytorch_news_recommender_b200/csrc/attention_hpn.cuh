@@ -167,17 +167,12 @@ __device__ __forceinline__ void hpn_write_img(const float* tile, int m0, int L, 
     const int r8 = lane >> 2, u = lane & 3;
     const int gg = (gcol0 >> 3) + u;
     const long long cbase = (long long)(gg >> 3) * img.chunk_stride;
-    // a phase of eight lanes reads two rows (40-float pitch = 8 banks apart) x four units: with every lane on
-    // the first half of its unit the halves of row 1 fall on the banks of row 0 (2-way conflict); odd units
-    // read their second half first instead
-    const int sw = (u & 1) * 4;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int l = m0 + r8 + 8 * i;
         if (l < L) {
-            const float4 va = *reinterpret_cast<const float4*>(tile + l * kHpStage + 8 * u + sw);
-            const float4 vb = *reinterpret_cast<const float4*>(tile + l * kHpStage + 8 * u + (4 - sw));
-            const float4 v0 = sw ? vb : va, v1 = sw ? va : vb;
+            const float4 v0 = *reinterpret_cast<const float4*>(tile + l * kHpStage + 8 * u);
+            const float4 v1 = *reinterpret_cast<const float4*>(tile + l * kHpStage + 8 * u + 4);
             uint32_t hi[4], lo[4];
             split_pair(v0.x, v0.y, hi[0], lo[0]);
             split_pair(v0.z, v0.w, hi[1], lo[1]);
@@ -193,13 +188,10 @@ __device__ __forceinline__ void hpn_write_img(const float* tile, int m0, int L, 
 }
 // ---- global -> shared --------------------------------------------------------------------------
 // rows [r0, r0+16) of one head's operand block -> the pair; rows >= L zero-filled
-// (lane -> row lane % 8, 16-byte unit lane / 8: the eight lanes of a shared-memory phase write eight different
-// rows = eight different bank groups at the 80-byte row pitch; unit-major lanes, four units of two rows per
-// phase, measured 15 wavefronts per instruction instead of 4 — 29 % of the forward's shared-memory traffic)
 template <bool LO>
 __device__ __forceinline__ void hpn_load_rows(uint32_t pair, int lo_off, const uint16_t* hi, const uint16_t* lo, long long blk,
                                               int r0, int L, int lane) {
-    const int r8 = lane & 7, u = lane >> 3;
+    const int r8 = lane >> 2, u = lane & 3;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         const int r = r0 + r8 + 8 * i;
