@@ -186,15 +186,16 @@ def test_fused_train_steps_with_dropout_match_oracle(name, gemm_mode, built_lib)
         st.m = {k: v.clone() for k, v in st.m.items()}
 
 
-@pytest.mark.parametrize("gemm_mode", GEMM_MODES)
+@pytest.mark.parametrize("gemm_mode", GEMM_MODES + [2])
 @pytest.mark.parametrize("name", ["mind", "long"])
 def test_train_step_is_bitwise_repeatable(name, gemm_mode, built_lib):
     """compute-sanitizer is not available on the GPU pool, so shared-memory hazards in the
     multi-warp attention kernels (named barriers, cp.async prefetch into dead pairs, persistent
     item loops) are hunted this way: the same fused step from the same state, many times, must give
     bit-identical loss, gradients and updated weights — a race or an unordered floating-point
-    reduction would show up as run-to-run noise.  Covers 30- and 48-token titles (2 and 4 warps per
-    sequence-head) and 50- and 200-slot histories."""
+    reduction would show up as run-to-run noise.  Covers 30- and 48-token titles (2 and 3 warps per
+    sequence-head), 50- and 200-slot histories, and all three product modes (the plain-bf16 mode runs the
+    hi-plane-only instantiations of every kernel)."""
     from pytorch_news_recommender_b200.engine import FusedTrainer
     c = Case(name)
     ref = None
