@@ -270,9 +270,11 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["s_per_step"] * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": workload_label(args), "sample_batch": info["batch"], "arm": "CPU reference arm"},
+        # the SAME config object as our arm prints (the driver compares the two); what this arm sampled of it
+        # is stated in cpu_baseline
+        "config": line_config(args, args.gpus, resolve_table_sync(args, args.gpus)),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                         "sample": info["sample"]},
+                         "sample": info["sample"], "sample_batch": info["batch"]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -321,6 +323,23 @@ def workload_label(args):
     return (f"{base}: NRMS train step (fwd + CE + bwd + dense Adam), batch {w['batch_per_gpu']} per GPU, "
             f"T={w['n_words_title']} H={w['history_len']} K={w['n_neg']} D={w['d_model']} heads={w['n_heads']} "
             f"Q={w['d_query']} V={w['vocab'] // 1000}k, dropout {w['dropout']}")
+
+
+def resolve_table_sync(args, world):
+    """engine.FusedTrainer's resolution of table_sync='auto' (engine.py: sharded for world > 1)."""
+    if args.table_sync != "auto":
+        return args.table_sync
+    return "sharded" if world > 1 else "dense"
+
+
+def line_config(args, world, table_sync):
+    """`config` of the JSON line — one function for both arms, so the two objects are equal key for key."""
+    return {"workload": workload_label(args),
+            "global_batch": world * WORKLOAD["batch_per_gpu"], "parallelism": f"dp{world}",
+            "gemm_mode": args.gemm_mode, "tokens": "zipf" if args.zipf else "uniform",
+            "table_sync": table_sync,
+            "l2": "per-step working set (>= 1.5 GB activations + 607 MB Adam state) exceeds the 126 MB L2; "
+                  "4 distinct batches rotated"}
 
 
 def kernel_work(name, B, gemm_mode=1):
@@ -614,12 +633,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.gemm_mode == 2 else "f32", "data": "synthetic",
-            "config": {"workload": workload_label(args),
-                       "global_batch": world * B, "parallelism": f"dp{world}",
-                       "gemm_mode": args.gemm_mode, "tokens": "zipf" if args.zipf else "uniform",
-                       "table_sync": trainer.table_sync,
-                       "l2": "per-step working set (>= 1.5 GB activations + 607 MB Adam state) exceeds the 126 MB L2; "
-                             "4 distinct batches rotated"},
+            "config": line_config(args, world, trainer.table_sync),
             "news_encodes_per_sec": value * alg["titles_per_impr"],
             "step_model": {"algorithmic_flop_per_step_per_gpu": step_flops,
                            "algorithmic_bytes_per_step_per_gpu": step_bytes,

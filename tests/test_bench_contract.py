@@ -26,6 +26,11 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] == ("reference" if staged else "port")
     assert cb["cores"] >= 1 and cb["value"] == d["value"] and "train_eval.py" in cb["sample"]
     assert d["config"]["workload"].startswith("cfg2")
+    # both arms build `config` with bench.line_config: the reference arm's object is our arm's, key for key
+    assert d["config"] == {**d["config"], "global_batch": 64, "parallelism": "dp1", "gemm_mode": 1,
+                           "tokens": "uniform", "table_sync": "dense"}
+    assert set(d["config"]) == {"workload", "global_batch", "parallelism", "gemm_mode", "tokens", "table_sync", "l2"}
+    assert cb["sample_batch"] >= 8
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
