@@ -141,6 +141,25 @@ inline bool hpn48_fwd() {
     return on && hpn48();
 }
 
+// Second-generation latency-oriented kernels (pooling.cuh: pool_fwd2 / pool_bwd2 / reduce_rows_w).  Measured A/B on
+// one box (scripts/ab_v2.sh, profiles/r02_v2_ab.txt; cfg2, per-launch times of the serialised pass):
+//   * row reducer: 12.8 + 11.5 -> 7.8 + 10.7 us (title encoder), 9.0 -> 6.6 us (user encoder): on by default;
+//   * pooling: the user encoder's launches (64 CTAs: a single CTA's serial chain is the whole cost) 11.3 -> 9.6 us
+//     forward, 17.0 -> 14.8 us backward; the title encoder's 3,520-CTA launches are throughput-bound (backward
+//     4.2 TB/s) and the 80-register v2 kernels run 3 CTAs per SM instead of 8: backward 78 -> 91 us, forward
+//     unchanged — so v2 pooling is used for launches that cannot fill the GPU (kPool2MaxSeq);
+//   * four (instead of two) gather items in flight per thread: 64 -> 72 us; not kept.
+// NRMS_V2 is a bit mask for A/B runs: 1 = pooling forward, 2 = pooling backward (both: also for large launches),
+// 4 = row reducer; unset = the measured default described above.
+constexpr int kV2PoolFwd = 1, kV2PoolBwd = 2, kV2Reduce = 4;
+constexpr int kPool2MaxSeq = 1024;
+inline int v2_mask() {
+    static const int mask = getenv("NRMS_V2") ? atoi(getenv("NRMS_V2")) : -1;
+    return mask;
+}
+inline bool v2_reduce() { return v2_mask() < 0 || (v2_mask() & kV2Reduce) != 0; }
+inline bool v2_pool(int bit, int n_seq) { return v2_mask() < 0 ? n_seq <= kPool2MaxSeq : (v2_mask() & bit) != 0; }
+
 struct Saved {
     float* qkv;      // [M, 3D] fp32; HP: bf16 planes hi [M, NP] then lo [M, NP]
     float* lse;      // [M, h]
@@ -294,6 +313,21 @@ int check_dims(const nrms_encoder_dims* d, bool news) {
 int reduce_rows(const float* in, float* out, long long R, long long n, long long ld, float scale,
                 float* tmp, cudaStream_t s) {
     const int threads = 256;
+    if (v2_reduce()) {
+        // rows over the warps of a CTA (reduce_rows_w_kernel); two levels when there are enough rows to fill SMs
+        const dim3 blk(32, kRedWarps);
+        const unsigned gx = (unsigned)ceil_div64(n, 32);
+        if (R <= 4 * kRedWarps || tmp == nullptr) {
+            NRMS_LAUNCH("reduce_rows", s, reduce_rows_w_kernel<<<dim3(gx, 1), blk, 0, s>>>(in, out, R, n, ld, R, scale));
+        } else {
+            const long long per = ceil_div64(R, kReduceSlices);
+            const int slices = (int)ceil_div64(R, per);
+            NRMS_LAUNCH("reduce_rows_sliced", s, reduce_rows_w_kernel<<<dim3(gx, slices), blk, 0, s>>>(in, tmp, R, n, ld, per, 1.f));
+            NRMS_LAUNCH("reduce_rows", s, reduce_rows_w_kernel<<<dim3(gx, 1), blk, 0, s>>>(tmp, out, slices, n, n, slices, scale));
+        }
+        NRMS_CHECK_CUDA(cudaGetLastError());
+        return NRMS_OK;
+    }
     if (R <= 256 || tmp == nullptr) {
         NRMS_LAUNCH("reduce_rows", s, reduce_rows_kernel<<<(unsigned)ceil_div64(n, threads), threads, 0, s>>>(in, out, R, n, ld,
                                                                                scale, 0));
@@ -394,7 +428,7 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         g.mask = sv.xmask; g.mask_bytes = mb;
         g.drop = news ? drop : make_dropout(0.f, 0);
         const long long items = tcm ? (long long)sv.x_img.rows_pad * sv.x_img.chunks * 8 : (long long)M * ceil_div(D, 8);
-        NRMS_LAUNCH("gather", s, gather_rows_img_kernel<<<grid_for(items, 256, 16), 256, 0, s>>>(g));
+        NRMS_LAUNCH("gather", s, gather_rows_img_kernel<2><<<grid_for(items, 256, 16), 256, 0, s>>>(g));
         NRMS_CHECK_CUDA(cudaGetLastError());
         x_f32 = sv.x_f32;
     }
@@ -555,7 +589,10 @@ int encoder_fwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
         p.M = M; p.L = L; p.D = D; p.Q = Q;
         const int pu = ceil_div(D, 8);
         const size_t pool_smem = (L + (hp ? 8 * pu * (256 / pu) : 0)) * sizeof(float);
-        NRMS_LAUNCH("pool_fwd", s, pool_fwd_kernel<<<d.n_seq, 256, pool_smem, s>>>(p));
+        if (hp && tcm && v2_pool(kV2PoolFwd, d.n_seq))
+            NRMS_LAUNCH("pool_fwd", s, pool_fwd2_kernel<<<d.n_seq, 256, pool_smem, s>>>(p));
+        else
+            NRMS_LAUNCH("pool_fwd", s, pool_fwd_kernel<<<d.n_seq, 256, pool_smem, s>>>(p));
         NRMS_CHECK_CUDA(cudaGetLastError());
     }
     return NRMS_OK;
@@ -602,7 +639,10 @@ int encoder_bwd(const nrms_encoder_dims& d, const int64_t* ids, const float* x_o
             p.d_part = sc.part_q;
             if (tcm) p.d_pre_img = sc.d_pre_img; else { p.d_pre = sc.d_pre; p.d_ctx = sc.d_ctx; }
             p.M = M; p.L = L; p.D = D; p.Q = Q;
-            NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
+            if (hp && tcm && Q % 8 == 0 && Q >= 8 && v2_pool(kV2PoolBwd, d.n_seq))
+                NRMS_LAUNCH("pool_bwd", s, pool_bwd2_kernel<<<d.n_seq, 256, pool_bwd2_smem_floats(L, D, Q) * sizeof(float), s>>>(p));
+            else
+                NRMS_LAUNCH("pool_bwd", s, pool_bwd_kernel<<<d.n_seq, 256, 2 * L * sizeof(float), s>>>(p));
             NRMS_CHECK_CUDA(cudaGetLastError());
         }
         // 2. d_ctx = pool path + d_pre W_a

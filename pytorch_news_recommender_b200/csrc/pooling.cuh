@@ -241,6 +241,266 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const PoolArgs p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Second generation of the two kernels for the tensor-core path (image context, scores from the projection
+// GEMM's epilogue, image-only d_pre), for launches of FEW CTAs (the user encoder: one CTA per impression).
+// The kernels above walk a sequence's rows in DEPENDENT rounds — a warp per row with a shuffle reduction per
+// round, then a per-column loop over all rows for the partials — which is what a launch that cannot fill the
+// GPU pays in full.  Here every phase issues ALL of its loads before it consumes the first one (work items
+// flattened over (row, 16-byte unit), R items per thread in flight), row sums go through a shared [L][units]
+// table in a fixed order, and the bias / query-vector partials are accumulated by the threads that form d_pre
+// (t is read once, not twice).  They need ~80 registers (3 CTAs per SM instead of 8): measured slower for the
+// title encoder's thousands of CTAs, which are throughput-bound (abi.cu: kPool2MaxSeq).
+// Same results as the kernels above up to the summation order (fixed, run-to-run identical).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void unpack8(const uint4& h, const uint4& l, float* x) {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        x[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lw[j] << 16);
+        x[2 * j + 1] = __uint_as_float(hw[j] & 0xffff0000u) + __uint_as_float(lw[j] & 0xffff0000u);
+    }
+}
+
+constexpr int kPool2R = 5;      // (row, unit) items a thread keeps in flight
+
+// dynamic smem: L floats + 8 * units * (256 / units) floats, units = ceil(D / 8)   (as pool_fwd_kernel)
+__global__ void __launch_bounds__(256, 3) pool_fwd2_kernel(const PoolArgs p) {
+    extern __shared__ float sw[];
+    const int seq = blockIdx.x, L = p.L, D = p.D;
+    const long long row0 = (long long)seq * L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int units = ceil_div(D, 8), slices = blockDim.x / units;
+    const int u = threadIdx.x % units, sl = threadIdx.x / units;
+    const bool active = sl < slices, has_lo = p.ctx_img.lo != nullptr;
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    uint4 xh[kPool2R], xl[kPool2R];
+    // the first batch of context rows leaves for the registers before the scores are even read
+#pragma unroll
+    for (int k = 0; k < kPool2R; ++k) {
+        const int l = sl + k * slices;
+        xh[k] = xl[k] = z4;
+        if (active && l < L) {
+            const long long off = ig::img_unit_off(p.ctx_img.chunk_stride, row0 + l, u);
+            xh[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.hi + off));
+            if (has_lo) xl[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.lo + off));
+        }
+    }
+    for (int l = threadIdx.x; l < L; l += blockDim.x) sw[l] = p.score[row0 + l];
+    __syncthreads();
+    // softmax statistics: every warp computes them itself (the same operations in the same order, so all
+    // warps hold the same bits) — no second barrier, no idle warps
+    float mx = -INFINITY;
+    for (int l = lane; l < L; l += 32) mx = fmaxf(mx, sw[l]);
+    mx = warp_max(mx);
+    float den = 0.f;
+    for (int l = lane; l < L; l += 32) den += __expf(sw[l] - mx);
+    den = warp_sum(den);
+    const float inv = 1.f / den;
+    if (warp == 0 && p.w)
+        for (int l = lane; l < L; l += 32) p.w[(long long)seq * L + l] = __expf(sw[l] - mx) * inv;
+    float* part = sw + L;                                  // [slices][units * 8]
+    if (active) {
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int l0 = sl; l0 < L; l0 += kPool2R * slices) {
+            if (l0 != sl) {                                // later batches (L > kPool2R * slices)
+#pragma unroll
+                for (int k = 0; k < kPool2R; ++k) {
+                    const int l = l0 + k * slices;
+                    xh[k] = xl[k] = z4;
+                    if (l < L) {
+                        const long long off = ig::img_unit_off(p.ctx_img.chunk_stride, row0 + l, u);
+                        xh[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.hi + off));
+                        if (has_lo) xl[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.lo + off));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < kPool2R; ++k) {
+                const int l = l0 + k * slices;
+                if (l < L) {
+                    float x[8];
+                    unpack8(xh[k], xl[k], x);
+                    const float wl = __expf(sw[l] - mx) * inv;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(wl, x[j], acc[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) part[(sl * units + u) * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int s2 = 0; s2 < slices; ++s2) acc += part[s2 * units * 8 + d];
+        p.out[(long long)seq * D + d] = acc;
+    }
+}
+
+// floats of dynamic shared memory of pool_bwd2_kernel
+__host__ __device__ inline int pool_bwd2_smem_floats(int L, int D, int Q) {
+    const int a = L * ceil_div(D, 8), b = (256 / (Q >> 3)) * 2 * Q;
+    return ((2 * L + 3) & ~3) + 8 * ceil_div(D, 8) + (a > b ? a : b);
+}
+
+// needs: image context, Q % 8 == 0, 8 <= Q <= 2048, image-only d_pre (no fp32 d_pre / d_ctx outputs)
+__global__ void __launch_bounds__(256, 3) pool_bwd2_kernel(const PoolArgs p) {
+    extern __shared__ float sm[];
+    const int seq = blockIdx.x, L = p.L, D = p.D, Q = p.Q;
+    float* sw = sm;
+    float* sda = sm + L;
+    const int units = ceil_div(D, 8), total = L * units;
+    float* sgo = sm + ((2 * L + 3) & ~3);                  // d_out of the sequence (16-byte aligned), zero beyond column D
+    float* spart = sgo + 8 * units;                        // [L][units] dot pieces, later [slices][2Q] partials
+    __shared__ float s_dot;
+    const long long row0 = (long long)seq * L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const float* go = p.d_out + (long long)seq * D;
+    const bool has_lo = p.ctx_img.lo != nullptr;
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    const float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- dw_l = d_out . ctx_l: one (row, unit) item = 8 columns; all of a thread's items in flight at once
+    uint4 xh[kPool2R], xl[kPool2R];
+#pragma unroll
+    for (int k = 0; k < kPool2R; ++k) {                    // first batch: issued before anything else
+        const int i = (int)threadIdx.x + k * (int)blockDim.x;
+        xh[k] = xl[k] = z4;
+        if (i < total) {
+            const int l = i / units, u = i - l * units;
+            const long long off = ig::img_unit_off(p.ctx_img.chunk_stride, row0 + l, u);
+            xh[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.hi + off));
+            if (has_lo) xl[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.lo + off));
+        }
+    }
+    for (int l = threadIdx.x; l < L; l += blockDim.x) sw[l] = p.w[(long long)seq * L + l];
+    // columns >= D of the image are not context (the ones column of the weight-gradient GEMM, padding): zero weight
+    for (int d = threadIdx.x; d < 8 * units; d += blockDim.x) sgo[d] = d < D ? __ldg(go + d) : 0.f;
+    __syncthreads();
+    for (int i0 = threadIdx.x; i0 < total; i0 += kPool2R * (int)blockDim.x) {
+        if (i0 != (int)threadIdx.x) {                      // later batches (L * units > kPool2R * 256)
+#pragma unroll
+            for (int k = 0; k < kPool2R; ++k) {
+                const int i = i0 + k * (int)blockDim.x;
+                xh[k] = xl[k] = z4;
+                if (i < total) {
+                    const int l = i / units, u = i - l * units;
+                    const long long off = ig::img_unit_off(p.ctx_img.chunk_stride, row0 + l, u);
+                    xh[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.hi + off));
+                    if (has_lo) xl[k] = __ldg(reinterpret_cast<const uint4*>(p.ctx_img.lo + off));
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kPool2R; ++k) {
+            const int i = i0 + k * (int)blockDim.x;
+            if (i < total) {
+                const int u = i % units;
+                float x[8];
+                unpack8(xh[k], xl[k], x);
+                const float4 g0 = *reinterpret_cast<const float4*>(sgo + 8 * u);
+                const float4 g1 = *reinterpret_cast<const float4*>(sgo + 8 * u + 4);
+                float s = g0.x * x[0];
+                s = fmaf(g0.y, x[1], s);
+                s = fmaf(g0.z, x[2], s);
+                s = fmaf(g0.w, x[3], s);
+                s = fmaf(g1.x, x[4], s);
+                s = fmaf(g1.y, x[5], s);
+                s = fmaf(g1.z, x[6], s);
+                s = fmaf(g1.w, x[7], s);
+                spart[i] = s;
+            }
+        }
+    }
+    __syncthreads();
+    for (int l = warp; l < L; l += nw) {
+        float s = 0.f;
+        for (int u = lane; u < units; u += 32) s += spart[l * units + u];
+        s = warp_sum(s);
+        if (lane == 0) sda[l] = s;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        float s = 0.f;
+        for (int l = lane; l < L; l += 32) s = fmaf(sw[l], sda[l], s);
+        s = warp_sum(s);
+        if (lane == 0) s_dot = s;
+    }
+    __syncthreads();
+    const float dot = s_dot;
+    for (int l = threadIdx.x; l < L; l += blockDim.x) sda[l] = sw[l] * (sda[l] - dot);
+    __syncthreads();                                       // (also: every read of spart's dot pieces is over)
+    // ---- d_pre = da_l * q_j * (1 - t^2) as 16-byte image units, and the per-sequence partials of
+    //      d_b_a = sum_l d_pre[l, j] and d_q = sum_l da_l * t[l, j] from the same registers
+    const int q8 = Q >> 3, slices = (int)blockDim.x / q8;
+    {
+        const int u = threadIdx.x % q8, sl = threadIdx.x / q8;
+        if (sl < slices) {
+            const float4 q0 = __ldg(reinterpret_cast<const float4*>(p.q + 8 * u));
+            const float4 q1 = __ldg(reinterpret_cast<const float4*>(p.q + 8 * u + 4));
+            const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            float db[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            constexpr int R3 = 4;
+            for (int l0 = sl; l0 < L; l0 += R3 * slices) {
+                float4 t0[R3], t1[R3];
+#pragma unroll
+                for (int k = 0; k < R3; ++k) {
+                    const int l = l0 + k * slices;
+                    t0[k] = t1[k] = f0;
+                    if (l < L) {
+                        t0[k] = __ldg(reinterpret_cast<const float4*>(p.t + (row0 + l) * Q + 8 * u));
+                        t1[k] = __ldg(reinterpret_cast<const float4*>(p.t + (row0 + l) * Q + 8 * u + 4));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < R3; ++k) {
+                    const int l = l0 + k * slices;
+                    if (l < L) {
+                        const float tv[8] = {t0[k].x, t0[k].y, t0[k].z, t0[k].w, t1[k].x, t1[k].y, t1[k].z, t1[k].w};
+                        const float da = sda[l];
+                        float x[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            x[j] = da * qv[j] * (1.f - tv[j] * tv[j]);
+                            db[j] += x[j];
+                            dq[j] = fmaf(da, tv[j], dq[j]);
+                        }
+                        ig::img_store8(p.d_pre_img, row0 + l, u, x);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                spart[sl * 2 * Q + 8 * u + j] = db[j];
+                spart[sl * 2 * Q + Q + 8 * u + j] = dq[j];
+            }
+        }
+    }
+    // zero padding of the d_pre image (as pool_bwd_kernel): columns [Q, 16*ceil(Q/16)) feed the data-gradient
+    // GEMM's last k-step, rows [M, rows_pad) the weight-gradient reduction
+    {
+        const int cpad = ceil_div(Q, 16) * 16 - Q;         // 0 or 8 (Q % 8 == 0)
+        for (int i = threadIdx.x; i < L * (cpad >> 1); i += blockDim.x) {
+            const int l = i / (cpad >> 1), j = Q + ((i - l * (cpad >> 1)) << 1);
+            const long long off = ig::img_unit_off(p.d_pre_img.chunk_stride, row0 + l, j >> 3) + (j & 7) * 2;
+            *reinterpret_cast<uint32_t*>(p.d_pre_img.hi + off) = 0u;
+            if (p.d_pre_img.lo) *reinterpret_cast<uint32_t*>(p.d_pre_img.lo + off) = 0u;
+        }
+        if (seq == (int)gridDim.x - 1) {
+            const int groups = p.d_pre_img.chunks * 8;
+            const long long npad = p.d_pre_img.rows_pad - p.M;
+            for (long long i = threadIdx.x; i < npad * groups; i += blockDim.x)
+                ig::img_store8_zero(p.d_pre_img, p.M + i / groups, (int)(i % groups));
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * Q; j += blockDim.x) {
+        float acc = 0.f;
+        for (int s2 = 0; s2 < slices; ++s2) acc += spart[s2 * 2 * Q + j];
+        p.d_part[(long long)seq * 2 * Q + j] = acc;
+    }
+}
+
 // out[n] (+)= scale * sum_{r<R} in[r, n]   (deterministic two-level: each thread walks a
 // column; R is at most a few thousand).  Used for bias / query partials and split-K weight
 // gradient partials.
@@ -279,20 +539,66 @@ __global__ void reduce_wgrad_kernel(const float* __restrict__ part, int splits, 
         const int ro = hp_dk > 0 ? ig::hp_unpad(r, hp_D, hp_dk) : r;
         if (ro < 0) continue;
         const float4* p = part4 + ((long long)r * ldp) / 4 + c4;
-        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+        // eight splits in flight per round (the walk over the splits is a chain of L2 round trips: with two in
+        // flight the 74 splits of the additive projection's gradient cost 37 of them), combined in a fixed tree
+        float4 a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         int s = 0;
-        for (; s + 1 < splits; s += 2) {
-            const float4 x = __ldg(p + s * per4), y = __ldg(p + (s + 1) * per4);
-            s0.x += x.x; s0.y += x.y; s0.z += x.z; s0.w += x.w;
-            s1.x += y.x; s1.y += y.y; s1.z += y.z; s1.w += y.w;
+        for (; s + 7 < splits; s += 8) {
+            float4 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = __ldg(p + (s + k) * per4);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a[k].x += x[k].x; a[k].y += x[k].y; a[k].z += x[k].z; a[k].w += x[k].w; }
         }
-        if (s < splits) {
-            const float4 x = __ldg(p + s * per4);
-            s0.x += x.x; s0.y += x.y; s0.z += x.z; s0.w += x.w;
+        {
+            float4 x[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = s + k < splits ? __ldg(p + (s + k) * per4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { a[k].x += x[k].x; a[k].y += x[k].y; a[k].z += x[k].z; a[k].w += x[k].w; }
         }
-        const float4 v = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+#pragma unroll
+        for (int w = 4; w > 0; w >>= 1)
+#pragma unroll
+            for (int k = 0; k < w; ++k) { a[k].x += a[k + w].x; a[k].y += a[k + w].y; a[k].z += a[k + w].z; a[k].w += a[k + w].w; }
+        const float4 v = a[0];
         if (4 * c4 < cols) *reinterpret_cast<float4*>(dW + (long long)ro * cols + 4 * c4) = v;
         else db[ro] = v.x;
+    }
+}
+
+// Column sums with the rows spread over the warps of a CTA: block (32, kRedWarps), warp y of slice
+// blockIdx.y takes rows r0 + y, r0 + y + kRedWarps, ... (four loads in flight), the warps' partials are added
+// in warp order through shared memory:  out[slice, c] = scale * sum_{r in slice} in[r, c].  One thread per
+// column walking all rows (the kernels below) is a chain of R/4 dependent L2 round trips.
+constexpr int kRedWarps = 16;
+__global__ void __launch_bounds__(32 * kRedWarps) reduce_rows_w_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                     long long R, long long n, long long ld, long long per,
+                                                                     float scale) {
+    __shared__ float sh[kRedWarps][33];
+    const long long c = (long long)blockIdx.x * 32 + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * per;
+    const long long r1 = r0 + per < R ? r0 + per : R;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < n) {
+        long long r = r0 + threadIdx.y;
+        for (; r + 3 * kRedWarps < r1; r += 4 * kRedWarps) {
+            s0 += in[(r + 0 * kRedWarps) * ld + c];
+            s1 += in[(r + 1 * kRedWarps) * ld + c];
+            s2 += in[(r + 2 * kRedWarps) * ld + c];
+            s3 += in[(r + 3 * kRedWarps) * ld + c];
+        }
+        for (; r < r1; r += kRedWarps) s0 += in[r * ld + c];
+    }
+    sh[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.y == 0 && c < n) {
+        float acc = 0.f;
+#pragma unroll
+        for (int y = 0; y < kRedWarps; ++y) acc += sh[y][threadIdx.x];
+        out[(long long)blockIdx.y * n + c] = acc * scale;
     }
 }
 
