@@ -1,4 +1,6 @@
-"""Data-parallel equivalence on real GPUs as a test: `scripts/dp_check.py` under torchrun,
+"""(Named to sort LAST: under `pytest -x` nothing may hide behind a multi-process launch.)
+
+Data-parallel equivalence on real GPUs as a test: `scripts/dp_check.py` under torchrun,
 one rank per GPU over NCCL — three `FusedTrainer.step`s on the ranks' shards of a global batch must give the
 gradients (2e-3 of each tensor's norm) and the weights of a single-process run over the whole batch, with
 both table exchanges (all-reduce + replicated Adam; reduce-scatter -> Adam on V/G rows -> all-gather).
